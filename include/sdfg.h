@@ -1,0 +1,203 @@
+/*
+ * include/sdfg.h -- C-ABI of libsdfg.so: the sm_100a kernels of the SDF-generator hot path
+ * (per-ray-sample neural-field evaluation + volume rendering of SDFace-GAN's im2scene SDF generator).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it is marked "host";
+ *   - the caller allocates everything; the library never allocates device memory and never synchronises;
+ *   - every entry point takes the CUDA stream to launch on (`stream`, a cudaStream_t passed as void*) -- the
+ *     reference extensions launch on the legacy default stream (gridencoder.cu:377-380, shencoder.cu:389), which is
+ *     what this replaces;
+ *   - return value: SDFG_OK (0) or a negative SDFG_ERR_*; sdfg_last_error() returns a thread-local message.  The
+ *     Python shim turns non-zero into RuntimeError, as TORCH_CHECK does in the reference (gridencoder.cu:15-18);
+ *   - re-entrant per device/stream (no global mutable state except the immutable SH coefficient table).
+ *
+ * "ref:" comments cite the reference interface each entry point replaces, relative to
+ * /root/reference/im2scene/sdf/models/.
+ */
+#ifndef SDFG_H_
+#define SDFG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDFG_OK 0
+#define SDFG_ERR_INVALID (-1)     /* bad argument (null pointer, zero size where not allowed, ...) */
+#define SDFG_ERR_UNSUPPORTED (-2) /* shape / option outside what the kernels are built for */
+#define SDFG_ERR_CUDA (-3)        /* a CUDA runtime call or kernel launch failed */
+
+/* layouts of the hash-grid feature tensor */
+#define SDFG_LAYOUT_NLC 0 /* [N, L*C]  sample-major (what GridEncoder.forward returns, grid.py:57) */
+#define SDFG_LAYOUT_LNC 1 /* [L, N, C] level-major  (what grid_encode_forward writes, grid.py:47)  */
+
+const char* sdfg_last_error(void);
+int sdfg_version(void);
+/* number of kernels launched by this library (all threads of the process) since the last reset (bench.py's gpu_launches) */
+int64_t sdfg_launch_count(void);
+void sdfg_launch_count_reset(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Ray generation + depth sampling + point construction.
+ * ref: VolumeFeatureRenderer.get_rays sdf_model.py:207-222, render :363-378, render_rays :310-351 (sampling part),
+ *      mlp_init_pass :380-398 (stratified mode).
+ *   c2w [B,3,4], focal/near/far [B]            camera (generate_camera_params, sdf_utils.py:97-159)
+ *   t_vals [S]                                  the renderer's `t_vals` buffer (sdf_model.py:174-179): linspace(0,1-1/S,S)
+ *                                               for offset sampling, linspace(0,1,S) for stratified
+ *   t_rand  NULL (jitter_mode 0) | [B,R,R] (jitter_mode 1: one offset per ray, upper end = far, :326-331)
+ *                                | [B,R,R,S] (jitter_mode 2: stratified between mid-points, :332-338 and :389-396)
+ *   outputs (each may be NULL): z_vals [B,R,R,S]; pts, npts [B,R,R,S,3] (world / normalised by 2/(far-near));
+ *                               viewdirs [B,R,R,3] (unit); rays_d [B,R,R,3]
+ */
+int sdfg_sample_rays(const float* c2w, const float* focal, const float* near, const float* far, const float* t_vals,
+                     const float* t_rand, int jitter_mode, int static_viewdirs, int z_normalize,
+                     uint32_t B, uint32_t R, uint32_t S,
+                     float* z_vals, float* pts, float* npts, float* viewdirs, float* rays_d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Multi-resolution hash grid.
+ * ref: grid_encode_forward gridencoder/src/gridencoder.h:12, gridencoder.cu:448-469 (kernel_grid :87-245) and the
+ *      affine map of GridEncoder.forward gridencoder/grid.py:149.
+ *   inputs [N,D] f32; if bound > 0 the kernel first maps x -> (x + bound) / (2*bound) (grid.py:149), else x is in [0,1]
+ *   embeddings [offsets[L], C] f32; offsets [L+1] i32 (device)
+ *   outputs f32, layout SDFG_LAYOUT_*;  dy_dx NULL or [N, L, D, C]
+ *   S = log2(per_level_scale) as float, H = base resolution, gridtype 0 hash / 1 tiled, interp 0 linear / 1 smoothstep
+ *   D in {2,3}; C in {1,2,4,8}; L <= 32.
+ */
+int sdfg_grid_encode_forward(const float* inputs, const float* embeddings, const int* offsets, float* outputs,
+                             uint32_t N, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, float bound,
+                             float* dy_dx, uint32_t gridtype, int align_corners, uint32_t interp, int out_layout,
+                             void* stream);
+
+/* ref: grid_encode_backward gridencoder.h:13, gridencoder.cu:472-503 (kernel_grid_backward :248-340,
+ *      kernel_input_backward :343-369).
+ *   grad (layout grad_layout) is scattered INTO grad_embeddings (accumulated: the caller pre-zeroes it, or passes a
+ *   live .grad buffer to skip the reference's zeros_like + add, grid.py:77).
+ *   grad_inputs NULL or [N,D] (overwritten; needs dy_dx).  If bound > 0, grad_inputs is already divided by 2*bound.
+ */
+int sdfg_grid_encode_backward(const float* grad, const float* inputs, const float* embeddings, const int* offsets,
+                              float* grad_embeddings, uint32_t N, uint32_t D, uint32_t C, uint32_t L, float S,
+                              uint32_t H, float bound, const float* dy_dx, float* grad_inputs, uint32_t gridtype,
+                              int align_corners, uint32_t interp, int grad_layout, void* stream);
+
+/* ref: grad_total_variation gridencoder.h:15, gridencoder.cu:612-645 (kernel_grad_tv :506-610). inputs in [0,1]. */
+int sdfg_grad_total_variation(const float* inputs, const float* embeddings, float* grad, const int* offsets,
+                              float weight, uint32_t N, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                              uint32_t gridtype, int align_corners, void* stream);
+
+/* the per-level `scale = exp2f(level*S)*H - 1` table exactly as the device computes it (gridencoder.cu:138); the CPU
+ * oracle takes it as an input because libm's exp2f may differ from CUDA's in the last bit.  out [L] f32 (device). */
+int sdfg_grid_level_scales(float* out, uint32_t L, float S, uint32_t H, void* stream);
+
+/* per-level integer cell coordinates and corner rows: the bit-exactness probe used by the parity tests.
+ *   corner_idx [N, L, 2^D] u32 (table row within the level, 0xFFFFFFFF if the sample is out of bounds) */
+int sdfg_grid_corner_indices(const float* inputs, const int* offsets, uint32_t* corner_idx, float* corner_w,
+                             uint32_t N, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, float bound,
+                             uint32_t gridtype, int align_corners, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Spherical harmonics of the view direction.
+ * ref: sh_encode_forward shencoder/src/shencoder.h:9, shencoder.cu:400-416 (kernel_sh :27-355);
+ *      sh_encode_backward shencoder.h:10, shencoder.cu:419-438 (kernel_sh_backward :358-382).
+ *   inputs [N,3]; outputs [N, degree^2]; dy_dx NULL or [N, 3, degree^2]; degree in 1..8
+ *   backward: grad_inputs [N,3] += sum_ch grad[n,ch] * dy_dx[n,d,ch]   (accumulates; caller pre-zeroes)
+ */
+int sdfg_sh_encode_forward(const float* inputs, float* outputs, uint32_t N, uint32_t degree, float* dy_dx, void* stream);
+int sdfg_sh_encode_backward(const float* grad, const float* dy_dx, float* grad_inputs, uint32_t N, uint32_t degree,
+                            void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Style-modulated SIREN field (NGPSIRENGenerator sdf_model.py:1534-1592 / SirenGenerator :101-139).
+ *
+ * Network description (host struct, passed by pointer; all weight pointers are device pointers, row-major [out,in]):
+ *   x_in [N, in_dim]  -> (optional) input_linear [W, in_dim] -> n_film FiLM-SIREN layers (first has K = in_dim if there is
+ *   no input_linear, else W) -> sdf head [1,W]; cat(h, view feature [rays, view_dim] broadcast over the S samples of a
+ *   ray) -> views FiLM-SIREN [W, W+view_dim] -> rgb head [3,W].
+ *   FiLM: h' = sin(gamma * (W h + b) + beta), gamma/beta [B, W] per image (FiLMSiren.forward :61-69); the image of
+ *   sample n is n / samples_per_image.
+ */
+#define SDFG_MAX_FILM 9
+typedef struct {
+    uint32_t width;              /* W (256) */
+    uint32_t in_dim;             /* 32 (hash features) or 3 (raw points) */
+    uint32_t view_dim;           /* 16 (SH degree 4) or 3 (raw dirs) */
+    uint32_t n_film;             /* trunk FiLM layers: 3 (ngp) or 8 (siren) */
+    uint32_t has_input_linear;   /* 1 for ngp */
+    uint32_t samples_per_image;  /* R*R*S */
+    uint32_t samples_per_ray;    /* S */
+    uint32_t reserved;
+    const float* input_w;        /* [W, in_dim] or NULL */
+    const float* input_b;        /* [W] */
+    const float* film_w[SDFG_MAX_FILM];   /* trunk layers 0..n_film-1, then the views layer at index n_film */
+    const float* film_b[SDFG_MAX_FILM];
+    const float* gamma;          /* [B, n_film+1, W]  (15*Lin(w)+30, already evaluated) */
+    const float* beta;           /* [B, n_film+1, W]  (0.25*Lin(w)) */
+    const float* sigma_w;        /* [1, W] */
+    const float* sigma_b;        /* [1] */
+    const float* rgb_w;          /* [3, W] */
+    const float* rgb_b;          /* [3] */
+} sdfg_field_params;
+
+/* gradient sinks, same shapes as the parameters; all accumulated INTO (caller pre-zeroes). NULL = not wanted. */
+typedef struct {
+    float* input_w;
+    float* input_b;
+    float* film_w[SDFG_MAX_FILM];
+    float* film_b[SDFG_MAX_FILM];
+    float* gamma;                /* [B, n_film+1, W] */
+    float* beta;
+    float* sigma_w;
+    float* sigma_b;
+    float* rgb_w;
+    float* rgb_b;
+} sdfg_field_grads;
+
+/* bytes of activation workspace sdfg_field_forward needs; `save_for_backward` keeps every layer's pre-activation. */
+uint64_t sdfg_field_workspace_bytes(const sdfg_field_params* p, uint64_t N, int save_for_backward, int precision);
+
+#define SDFG_PRECISION_FP32 0   /* SIMT fp32 FMA path: parity <= 1e-3 max-abs with the reference fp32 path */
+#define SDFG_PRECISION_TC16 1   /* tcgen05 path: fp16 operands, fp32 accumulate in TMEM (sm_100a) */
+
+/* forward.  x_in [N,in_dim]; view_feat [N/S, view_dim]; out_sdf [N]; out_rgb [N,3] (NULL ok); out_feat [N,W] (NULL ok);
+ * workspace as sized above (kept by the caller until backward). */
+int sdfg_field_forward(const sdfg_field_params* p, const float* x_in, const float* view_feat, uint64_t N,
+                       float* out_sdf, float* out_rgb, float* out_feat, void* workspace, int save_for_backward,
+                       int precision, void* stream);
+
+/* backward.  d_sdf [N], d_rgb [N,3], d_feat [N,W] (each NULL = zero; at least one given) -> parameter grads (g NULL =
+ * none wanted, e.g. for the eikonal pass) + d_x_in [N,in_dim] (NULL ok).  Reads the workspace written by the matching
+ * forward (save_for_backward = 1), `out_feat` = the pointer that forward was given (NULL if none) and uses `scratch`
+ * (sdfg_field_backward_scratch_bytes) for the two [N,W] gradient ping-pong buffers. */
+uint64_t sdfg_field_backward_scratch_bytes(const sdfg_field_params* p, uint64_t N, int precision);
+int sdfg_field_backward(const sdfg_field_params* p, const sdfg_field_grads* g, const float* x_in, const float* view_feat,
+                        uint64_t N, const float* d_sdf, const float* d_rgb, const float* d_feat, const float* out_feat,
+                        const void* workspace, void* scratch, float* d_x_in, int precision, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * SDF -> density -> alpha -> front-to-back compositing.
+ * ref: VolumeFeatureRenderer.sdf_activation sdf_model.py:231-234 + volume_integration :236-301.
+ *   sdf [NR,S]  (or raw density when with_sdf = 0); rgb [NR,S,3]; feat [NR,S,F] or NULL; z_vals [NR,S];
+ *   rays_d [NR,3]; pts [NR,S,3] or NULL (needed for xyz); noise [NR,S] or NULL (non-sdf branch raw_noise)
+ *   sigmoid_beta: device pointer to the learnable scalar (sdf_model.py:163-164)
+ *   outputs: rgb_map [NR,3]; feat_map [NR,F] or NULL; xyz_map [NR,3] or NULL; mask [NR] or NULL;
+ *            weights [NR,S] or NULL (kept for backward)
+ */
+int sdfg_composite_forward(const float* sdf, const float* rgb, const float* feat, const float* z_vals,
+                           const float* rays_d, const float* pts, const float* noise, const float* sigmoid_beta,
+                           uint64_t NR, uint32_t S, uint32_t F, int with_sdf, int force_background,
+                           float* rgb_map, float* feat_map, float* xyz_map, float* mask, float* weights, void* stream);
+
+/* backward of the above wrt sdf, rgb, feat, sigmoid_beta (accumulated into d_sigmoid_beta[0]) and pts (NULL ok).
+ * d_* map gradients may be NULL (= zero). */
+int sdfg_composite_backward(const float* sdf, const float* rgb, const float* feat, const float* z_vals,
+                            const float* rays_d, const float* pts, const float* noise, const float* sigmoid_beta,
+                            uint64_t NR, uint32_t S, uint32_t F, int with_sdf, int force_background,
+                            const float* d_rgb_map, const float* d_feat_map, const float* d_xyz_map, const float* d_mask,
+                            float* d_sdf, float* d_rgb, float* d_feat, float* d_pts, float* d_sigmoid_beta, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDFG_H_ */

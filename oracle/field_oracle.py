@@ -45,7 +45,7 @@ class _GridEncodeOracle(torch.autograd.Function):
         B = inputs.shape[0]
         L = offsets.shape[0] - 1
         C = embeddings.shape[1]
-        g = grad.reshape(B, L, C).permute(1, 0, 2).contiguous().numpy()     # grid.py:75
+        g = grad.detach().reshape(B, L, C).permute(1, 0, 2).contiguous().numpy()     # grid.py:75 (opaque kernel: no double backward)
         ge, gi = grid_encode_backward(g, inputs.detach().numpy(), embeddings.detach().numpy(), offsets.numpy(), S, H,
                                       dy_dx=ctx.dy_dx, level_scales=level_scales)
         return (torch.from_numpy(gi) if gi is not None else None), torch.from_numpy(ge), None, None, None, None

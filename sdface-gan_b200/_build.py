@@ -1,0 +1,72 @@
+"""In-tree build of libsdfg.so (the C-ABI CUDA library) with nvcc for sm_100a.
+
+    python sdface-gan_b200/_build.py [--force]
+
+Objects are cached under csrc/build/ by source mtime; the shared library lands in sdface-gan_b200/lib/libsdfg.so so it
+travels with the repo snapshot to the GPU box (a JIT cache under ~/.cache would not).  No torch headers are involved: the
+library's boundary is plain C (include/sdfg.h).
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "build")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libsdfg.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+def _sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _headers():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(os.path.dirname(HERE), "include", "sdfg.h"))
+    return hs
+
+
+def _compile(src, force):
+    obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+    newest = max(os.path.getmtime(p) for p in [src] + _headers())
+    if not force and os.path.exists(obj) and os.path.getmtime(obj) >= newest:
+        return obj, ""
+    cmd = [NVCC, "-c", src, "-o", obj] + ARCH + FLAGS
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+    return obj, r.stderr
+
+
+def build(force=False, verbose=False):
+    """Compile every csrc/*.cu and link lib/libsdfg.so.  Returns the library path."""
+    if not os.path.exists(NVCC):
+        if os.path.exists(LIB):
+            return LIB
+        raise RuntimeError("nvcc not found at %s and no prebuilt %s" % (NVCC, LIB))
+    os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(LIBDIR, exist_ok=True)
+    srcs = _sources()
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        res = list(ex.map(lambda s: _compile(s, force), srcs))
+    objs = [o for o, _ in res]
+    if verbose:
+        for _, log in res:
+            if log:
+                sys.stderr.write(log)
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ARCH + ["-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

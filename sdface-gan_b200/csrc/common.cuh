@@ -2,20 +2,20 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
-#include <cuda_bf16.h>
 #include <stdint.h>
 
-#define SDFG_OK 0
-#define SDFG_ERR_INVALID (-1)       // bad argument (null pointer, size 0 where not allowed ...)
-#define SDFG_ERR_UNSUPPORTED (-2)   // shape / option outside what the kernels are built for
-#define SDFG_ERR_CUDA (-3)          // a CUDA runtime call or launch failed (see sdfg_last_error_string)
+#include "../../include/sdfg.h"
 
 namespace sdfg {
 
-extern thread_local char g_last_error[256];
 int set_error(int code, const char* fmt, ...);
-int check_launch(const char* what);
+int check_launch(const char* what);   // cudaGetLastError -> SDFG_ERR_CUDA; also bumps the launch counter
 int sm_count();
+
+#define SDFG_REQUIRE(cond, code, ...)                        \
+    do {                                                     \
+        if (!(cond)) return ::sdfg::set_error(code, __VA_ARGS__); \
+    } while (0)
 
 template <typename T>
 __host__ __device__ __forceinline__ T ceil_div(T a, T b) { return (a + b - 1) / b; }
@@ -42,12 +42,18 @@ __device__ __forceinline__ float ldg_stream1(const float* p) {
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
-// vectorised no-return float reduction into global memory (sm_90+): one L2 atomic transaction for 2 floats
+__device__ __forceinline__ void stg_stream4(float4* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// vectorised no-return float reduction into global memory (sm_90+): one L2 atomic transaction for 2 / 4 floats
 __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void red_add_f32(float* addr, float a) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
 
 }  // namespace sdfg

@@ -1,0 +1,522 @@
+// Multi-resolution hash-grid encoder for sm_100a: forward (+ dy_dx), backward scatter, input gradient, TV gradient.
+//
+// Behavioural contract: the reference's gridencoder extension (ref = /root/reference/im2scene/sdf/models/gridencoder):
+//   level geometry      ref src/gridencoder.cu:137-139      scale = exp2f(level*S)*H - 1, resolution = ceil(scale)+1
+//   cell / fraction     ref src/gridencoder.cu:141-159      pos = fma(x, scale, 0.5); g = floor(pos); f = pos - g
+//   corner row          ref src/gridencoder.cu:50-84        dense stride walk while stride <= hashmap, else prime-xor hash
+//   D-linear blend      ref src/gridencoder.cu:166-197      w = prod_d (bit_d ? f_d : 1-f_d), corners in index order 0..2^D-1
+//   dy_dx               ref src/gridencoder.cu:199-244
+//   scatter             ref src/gridencoder.cu:248-340,  input grad :343-369,  TV :506-610
+//   level table         ref grid.py:97-131 (built by the Python side and passed in as `offsets`)
+//
+// This is a re-design, not a translation: one thread owns a SAMPLE and walks all levels (coordinates are read once, a
+// warp is always inside one level so coarse-level corners coalesce in L1), per-level constants live in shared memory,
+// features are written sample-major ([N, L*C]) directly -- the reference writes [L,N,C] and pays a transposing copy
+// (grid.py:57) -- the affine map (x+bound)/(2*bound) of GridEncoder.forward (grid.py:149) is folded in, gradients are
+// scattered with vectorised no-return reductions (red.global.add.v2/v4.f32) straight into the caller's buffer, and every
+// launch goes to the caller's stream.
+#include "common.cuh"
+
+namespace sdfg {
+
+constexpr int kMaxLevels = 32;
+
+struct LevelInfo {
+    float scale;        // exp2f(level*S)*H - 1
+    uint32_t res;       // ceil(scale) + 1
+    uint32_t hashmap;   // offsets[l+1] - offsets[l]
+    uint32_t offset;    // offsets[l]
+    uint32_t stride1;   // stride of dim 1 in the dense walk
+    uint32_t stride2;   // stride of dim 2
+    uint32_t ndims;     // how many dims the dense walk consumed before stride > hashmap
+    uint32_t use_hash;  // gridtype == hash && final stride > hashmap
+    uint32_t pow2mask;  // hashmap - 1 if hashmap is a power of two, else 0
+};
+
+// exp2f() of the CUDA math library and an explicit fma: what nvcc makes of the reference's
+// `exp2f(level * S) * H - 1.0f` with its default -fmad=true.
+__device__ __forceinline__ float level_scale(uint32_t level, float S, uint32_t H) {
+    return fmaf(exp2f((float)level * S), (float)H, -1.0f);
+}
+
+template <uint32_t D>
+__device__ __forceinline__ void fill_level_info(LevelInfo& li, uint32_t level, const int* __restrict__ offsets, float S,
+                                                uint32_t H, uint32_t gridtype, int align_corners) {
+    li.scale = level_scale(level, S, H);
+    li.res = (uint32_t)ceilf(li.scale) + 1;
+    li.offset = (uint32_t)offsets[level];
+    li.hashmap = (uint32_t)(offsets[level + 1] - offsets[level]);
+    const uint32_t step = align_corners ? li.res : li.res + 1;
+    uint32_t stride = 1, nd = 0, s[3] = {1, 1, 1};
+    for (uint32_t d = 0; d < D && stride <= li.hashmap; d++) {   // uint32 wrap-around exactly as the reference walk
+        s[d] = stride;
+        stride *= step;
+        nd++;
+    }
+    li.stride1 = s[1];
+    li.stride2 = s[2];
+    li.ndims = nd;
+    li.use_hash = (gridtype == 0 && stride > li.hashmap) ? 1u : 0u;
+    li.pow2mask = (li.hashmap & (li.hashmap - 1)) == 0 ? li.hashmap - 1 : 0u;
+}
+
+template <uint32_t D>
+__device__ __forceinline__ uint32_t corner_row(const LevelInfo& li, const uint32_t (&g)[D]) {
+    uint32_t idx;
+    if (li.use_hash) {
+        idx = g[0];                                    // prime 1
+        if (D > 1) idx ^= g[1] * 2654435761u;
+        if (D > 2) idx ^= g[2] * 805459861u;
+        return li.pow2mask ? (idx & li.pow2mask) : (idx % li.hashmap);
+    }
+    idx = g[0];
+    if (D > 1 && li.ndims > 1) idx += g[1] * li.stride1;
+    if (D > 2 && li.ndims > 2) idx += g[2] * li.stride2;
+    return idx < li.hashmap ? idx : idx % li.hashmap;
+}
+
+__device__ __forceinline__ float smoothstep_f(float v) { return v * v * (3.0f - 2.0f * v); }
+__device__ __forceinline__ float smoothstep_d(float v) { return 6 * v * (1.0f - v); }
+
+// (x + bound) / (2*bound) with IEEE round-to-nearest add and divide: torch's `(inputs + bound) / (2 * bound)`.
+__device__ __forceinline__ float to_unit(float x, float bound) {
+    return bound > 0.f ? __fdiv_rn(__fadd_rn(x, bound), 2.f * bound) : x;
+}
+
+template <uint32_t D>
+__device__ __forceinline__ bool locate(const float (&u)[D], const LevelInfo& li, int align_corners, uint32_t interp,
+                                       float (&f)[D], float (&fd)[D], uint32_t (&g)[D]) {
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        float pos = fmaf(u[d], li.scale, align_corners ? 0.0f : 0.5f);
+        const float fl = floorf(pos);
+        g[d] = (uint32_t)fl;
+        pos -= (float)g[d];
+        if (interp == 1) { fd[d] = smoothstep_d(pos); f[d] = smoothstep_f(pos); }
+        else { fd[d] = 1.0f; f[d] = pos; }
+    }
+    return true;
+}
+
+template <uint32_t C>
+struct Feat { float v[C]; };
+
+template <uint32_t C>
+__device__ __forceinline__ Feat<C> load_feat(const float* __restrict__ p) {
+    Feat<C> r;
+    if constexpr (C == 1) { r.v[0] = __ldg(p); }
+    else if constexpr (C == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); r.v[0] = t.x; r.v[1] = t.y; }
+    else {
+#pragma unroll
+        for (uint32_t i = 0; i < C; i += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p + i));
+            r.v[i] = t.x; r.v[i + 1] = t.y; r.v[i + 2] = t.z; r.v[i + 3] = t.w;
+        }
+    }
+    return r;
+}
+
+template <uint32_t C>
+__device__ __forceinline__ void store_feat(float* p, const float (&v)[C]) {
+    if constexpr (C == 1) { p[0] = v[0]; }
+    else if constexpr (C == 2) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+    else {
+#pragma unroll
+        for (uint32_t i = 0; i < C; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+}
+
+template <uint32_t C>
+__device__ __forceinline__ void red_feat(float* p, const float (&v)[C]) {
+    if constexpr (C == 1) { red_add_f32(p, v[0]); }
+    else if constexpr (C == 2) { red_add_v2(p, v[0], v[1]); }
+    else {
+#pragma unroll
+        for (uint32_t i = 0; i < C; i += 4) red_add_v4(p + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+}
+
+// One level of one sample: blend (and optional dy_dx).  Returns false (and zeros) when the sample is outside [0,1]^D.
+template <uint32_t D, uint32_t C, bool DYDX>
+__device__ __forceinline__ void encode_level(const float (&u)[D], const LevelInfo& li, const float* __restrict__ table,
+                                             int align_corners, uint32_t interp, float (&out)[C], float (&dd)[D * C]) {
+    float f[D], fd[D];
+    uint32_t g[D];
+    locate<D>(u, li, align_corners, interp, f, fd, g);
+    const float* __restrict__ grid = table + (size_t)li.offset * C;
+    Feat<C> corner[1u << D];
+#pragma unroll
+    for (uint32_t idx = 0; idx < (1u << D); idx++) {          // issue all 2^D gathers before any use
+        uint32_t gl[D];
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) gl[d] = g[d] + ((idx >> d) & 1u);
+        corner[idx] = load_feat<C>(grid + (size_t)corner_row<D>(li, gl) * C);
+    }
+#pragma unroll
+    for (uint32_t c = 0; c < C; c++) out[c] = 0.f;
+#pragma unroll
+    for (uint32_t idx = 0; idx < (1u << D); idx++) {
+        float w = 1.f;
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) w *= ((idx >> d) & 1u) ? f[d] : 1.f - f[d];
+#pragma unroll
+        for (uint32_t c = 0; c < C; c++) out[c] = fmaf(w, corner[idx].v[c], out[c]);
+    }
+    if constexpr (DYDX) {
+        // d/dx_gd: pairs (left,right) along gd of the 2^(D-1) corners of the other axes -- all already in registers.
+#pragma unroll
+        for (uint32_t gd = 0; gd < D; gd++) {
+            float acc[C];
+#pragma unroll
+            for (uint32_t c = 0; c < C; c++) acc[c] = 0.f;
+#pragma unroll
+            for (uint32_t sub = 0; sub < (1u << (D - 1)); sub++) {
+                float w = li.scale;
+                uint32_t left = 0;
+#pragma unroll
+                for (uint32_t nd = 0; nd < D - 1; nd++) {
+                    const uint32_t d = (nd >= gd) ? nd + 1 : nd;
+                    const uint32_t bit = (sub >> nd) & 1u;
+                    w *= bit ? f[d] : 1.f - f[d];
+                    left |= bit << d;
+                }
+                const uint32_t right = left | (1u << gd);
+#pragma unroll
+                for (uint32_t c = 0; c < C; c++)
+                    acc[c] = fmaf(w * (corner[right].v[c] - corner[left].v[c]), fd[gd], acc[c]);
+            }
+#pragma unroll
+            for (uint32_t c = 0; c < C; c++) dd[gd * C + c] = acc[c];
+        }
+    }
+}
+
+template <uint32_t D>
+__device__ __forceinline__ bool load_unit(const float* __restrict__ inputs, size_t n, float bound, float (&u)[D]) {
+    bool inside = true;
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        u[d] = to_unit(__ldg(inputs + n * D + d), bound);
+        inside = inside && !(u[d] < 0.f || u[d] > 1.f);
+    }
+    return inside;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward: thread per sample, loop over levels
+template <uint32_t D, uint32_t C, bool DYDX>
+__global__ void __launch_bounds__(256) grid_forward_kernel(const float* __restrict__ inputs, const float* __restrict__ table,
+                                                           const int* __restrict__ offsets, float* __restrict__ outputs,
+                                                           uint32_t N, uint32_t L, float S, uint32_t H, float bound,
+                                                           float* __restrict__ dy_dx, uint32_t gridtype, int align_corners,
+                                                           uint32_t interp, int out_layout) {
+    __shared__ LevelInfo info[kMaxLevels];
+    if (threadIdx.x < L) fill_level_info<D>(info[threadIdx.x], threadIdx.x, offsets, S, H, gridtype, align_corners);
+    __syncthreads();
+    const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float u[D];
+    const bool inside = load_unit<D>(inputs, n, bound, u);
+#pragma unroll 2
+    for (uint32_t level = 0; level < L; level++) {
+        float out[C], dd[D * C];
+        if (inside) {
+            encode_level<D, C, DYDX>(u, info[level], table, align_corners, interp, out, dd);
+        } else {
+#pragma unroll
+            for (uint32_t c = 0; c < C; c++) out[c] = 0.f;
+#pragma unroll
+            for (uint32_t i = 0; i < D * C; i++) dd[i] = 0.f;
+        }
+        float* o = out_layout == SDFG_LAYOUT_NLC ? outputs + (n * L + level) * C : outputs + ((size_t)level * N + n) * C;
+        store_feat<C>(o, out);
+        if constexpr (DYDX) {
+            float* q = dy_dx + (n * L + level) * (D * C);
+#pragma unroll
+            for (uint32_t i = 0; i < D * C; i++) q[i] = dd[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward scatter: thread per (sample, level); the level is blockIdx.y so a warp's reductions hit one level's table
+template <uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(256) grid_backward_kernel(const float* __restrict__ grad, const float* __restrict__ inputs,
+                                                            const int* __restrict__ offsets, float* __restrict__ grad_table,
+                                                            uint32_t N, uint32_t L, float S, uint32_t H, float bound,
+                                                            uint32_t gridtype, int align_corners, uint32_t interp,
+                                                            int grad_layout) {
+    __shared__ LevelInfo li_s;
+    const uint32_t level = blockIdx.y;
+    if (threadIdx.x == 0) fill_level_info<D>(li_s, level, offsets, S, H, gridtype, align_corners);
+    __syncthreads();
+    const LevelInfo li = li_s;
+    const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float u[D];
+    if (!load_unit<D>(inputs, n, bound, u)) return;
+    const float* gp = grad_layout == SDFG_LAYOUT_NLC ? grad + (n * L + level) * C : grad + ((size_t)level * N + n) * C;
+    const Feat<C> g = load_feat<C>(gp);
+    float f[D], fd[D];
+    uint32_t cell[D];
+    locate<D>(u, li, align_corners, interp, f, fd, cell);
+    float* __restrict__ gt = grad_table + (size_t)li.offset * C;
+#pragma unroll
+    for (uint32_t idx = 0; idx < (1u << D); idx++) {
+        float w = 1.f;
+        uint32_t gl[D];
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++) {
+            const uint32_t bit = (idx >> d) & 1u;
+            w *= bit ? f[d] : 1.f - f[d];
+            gl[d] = cell[d] + bit;
+        }
+        float v[C];
+#pragma unroll
+        for (uint32_t c = 0; c < C; c++) v[c] = w * g.v[c];
+        red_feat<C>(gt + (size_t)corner_row<D>(li, gl) * C, v);
+    }
+}
+
+// grad_inputs[n,d] = sum_{l,c} grad[n,l,c] * dy_dx[n,l,d,c]  (/ (2*bound) when the affine map was folded in)
+template <uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(256) grid_input_backward_kernel(const float* __restrict__ grad, const float* __restrict__ dy_dx,
+                                                                  float* __restrict__ grad_inputs, uint32_t N, uint32_t L,
+                                                                  float bound, int grad_layout) {
+    const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float acc[D];
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) acc[d] = 0.f;
+    for (uint32_t l = 0; l < L; l++) {
+        const float* gp = grad_layout == SDFG_LAYOUT_NLC ? grad + (n * L + l) * C : grad + ((size_t)l * N + n) * C;
+        const Feat<C> g = load_feat<C>(gp);
+        const float* q = dy_dx + (n * L + l) * (D * C);
+#pragma unroll
+        for (uint32_t d = 0; d < D; d++)
+#pragma unroll
+            for (uint32_t c = 0; c < C; c++) acc[d] = fmaf(g.v[c], __ldg(q + d * C + c), acc[d]);
+    }
+    const float k = bound > 0.f ? 1.f / (2.f * bound) : 1.f;
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) grad_inputs[n * D + d] = acc[d] * k;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// total-variation gradient at the cell of each input point (ref kernel_grad_tv; no caller in the reference tree)
+template <uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(256) grid_tv_kernel(const float* __restrict__ inputs, const float* __restrict__ table,
+                                                      float* __restrict__ grad, const int* __restrict__ offsets, float weight,
+                                                      uint32_t N, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                                                      int align_corners) {
+    __shared__ LevelInfo li_s;
+    const uint32_t level = blockIdx.y;
+    if (threadIdx.x == 0) fill_level_info<D>(li_s, level, offsets, S, H, gridtype, align_corners);
+    __syncthreads();
+    const LevelInfo li = li_s;
+    const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float u[D];
+    if (!load_unit<D>(inputs, n, 0.f, u)) return;
+    uint32_t cell[D];
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) cell[d] = (uint32_t)floorf(fmaf(u[d], li.scale, align_corners ? 0.0f : 0.5f));
+    const float* __restrict__ grid = table + (size_t)li.offset * C;
+    const uint32_t row = corner_row<D>(li, cell);
+    const Feat<C> centre = load_feat<C>(grid + (size_t)row * C);
+    float sum[C], sq[C];
+#pragma unroll
+    for (uint32_t c = 0; c < C; c++) { sum[c] = 0.f; sq[c] = 0.f; }
+    const float w = weight / (2 * D);
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) {
+        const uint32_t cur = cell[d];
+        if (cur < li.res) {
+            cell[d] = cur + 1;
+            const Feat<C> o = load_feat<C>(grid + (size_t)corner_row<D>(li, cell) * C);
+#pragma unroll
+            for (uint32_t c = 0; c < C; c++) { const float gv = centre.v[c] - o.v[c]; sum[c] += gv; sq[c] = fmaf(gv, gv, sq[c]); }
+        }
+        if (cur > 0) {
+            cell[d] = cur - 1;
+            const Feat<C> o = load_feat<C>(grid + (size_t)corner_row<D>(li, cell) * C);
+#pragma unroll
+            for (uint32_t c = 0; c < C; c++) { const float gv = centre.v[c] - o.v[c]; sum[c] += gv; sq[c] = fmaf(gv, gv, sq[c]); }
+        }
+        cell[d] = cur;
+    }
+    float v[C];
+#pragma unroll
+    for (uint32_t c = 0; c < C; c++) v[c] = w * sum[c] * rsqrtf(sq[c] + 1e-9f);
+    red_feat<C>(grad + ((size_t)li.offset + row) * C, v);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// probes for the parity tests
+__global__ void grid_level_scales_kernel(float* out, uint32_t L, float S, uint32_t H) {
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < L) out[l] = level_scale(l, S, H);
+}
+
+template <uint32_t D>
+__global__ void __launch_bounds__(256) grid_corner_kernel(const float* __restrict__ inputs, const int* __restrict__ offsets,
+                                                          uint32_t* __restrict__ corner_idx, float* __restrict__ corner_w,
+                                                          uint32_t N, uint32_t L, float S, uint32_t H, float bound,
+                                                          uint32_t gridtype, int align_corners) {
+    __shared__ LevelInfo info[kMaxLevels];
+    if (threadIdx.x < L) fill_level_info<D>(info[threadIdx.x], threadIdx.x, offsets, S, H, gridtype, align_corners);
+    __syncthreads();
+    const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float u[D];
+    const bool inside = load_unit<D>(inputs, n, bound, u);
+    for (uint32_t level = 0; level < L; level++) {
+        float f[D], fd[D];
+        uint32_t cell[D];
+        locate<D>(u, info[level], align_corners, 0, f, fd, cell);
+        for (uint32_t idx = 0; idx < (1u << D); idx++) {
+            float w = 1.f;
+            uint32_t gl[D];
+#pragma unroll
+            for (uint32_t d = 0; d < D; d++) {
+                const uint32_t bit = (idx >> d) & 1u;
+                w *= bit ? f[d] : 1.f - f[d];
+                gl[d] = cell[d] + bit;
+            }
+            const size_t o = (n * L + level) * (1u << D) + idx;
+            corner_idx[o] = inside ? corner_row<D>(info[level], gl) : 0xFFFFFFFFu;
+            if (corner_w) corner_w[o] = inside ? w : 0.f;
+        }
+    }
+}
+
+template <uint32_t D, uint32_t C>
+static int launch_forward(const float* inputs, const float* table, const int* offsets, float* outputs, uint32_t N, uint32_t L,
+                          float S, uint32_t H, float bound, float* dy_dx, uint32_t gridtype, int align_corners, uint32_t interp,
+                          int out_layout, cudaStream_t st) {
+    const dim3 grid(ceil_div<uint32_t>(N, 256));
+    if (dy_dx)
+        grid_forward_kernel<D, C, true><<<grid, 256, 0, st>>>(inputs, table, offsets, outputs, N, L, S, H, bound, dy_dx, gridtype,
+                                                              align_corners, interp, out_layout);
+    else
+        grid_forward_kernel<D, C, false><<<grid, 256, 0, st>>>(inputs, table, offsets, outputs, N, L, S, H, bound, nullptr,
+                                                               gridtype, align_corners, interp, out_layout);
+    return check_launch("grid_forward_kernel");
+}
+
+template <uint32_t D, uint32_t C>
+static int launch_backward(const float* grad, const float* inputs, const int* offsets, float* grad_table, uint32_t N, uint32_t L,
+                           float S, uint32_t H, float bound, const float* dy_dx, float* grad_inputs, uint32_t gridtype,
+                           int align_corners, uint32_t interp, int grad_layout, cudaStream_t st) {
+    if (grad_table) {
+        const dim3 grid(ceil_div<uint32_t>(N, 256), L);
+        grid_backward_kernel<D, C><<<grid, 256, 0, st>>>(grad, inputs, offsets, grad_table, N, L, S, H, bound, gridtype,
+                                                         align_corners, interp, grad_layout);
+        if (int e = check_launch("grid_backward_kernel")) return e;
+    }
+    if (grad_inputs) {
+        grid_input_backward_kernel<D, C><<<ceil_div<uint32_t>(N, 256), 256, 0, st>>>(grad, dy_dx, grad_inputs, N, L, bound,
+                                                                                     grad_layout);
+        if (int e = check_launch("grid_input_backward_kernel")) return e;
+    }
+    return SDFG_OK;
+}
+
+template <uint32_t D, uint32_t C>
+static int launch_tv(const float* inputs, const float* table, float* grad, const int* offsets, float weight, uint32_t N,
+                     uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners, cudaStream_t st) {
+    const dim3 grid(ceil_div<uint32_t>(N, 256), L);
+    grid_tv_kernel<D, C><<<grid, 256, 0, st>>>(inputs, table, grad, offsets, weight, N, L, S, H, gridtype, align_corners);
+    return check_launch("grid_tv_kernel");
+}
+
+static int check_shape(uint32_t D, uint32_t C, uint32_t L) {
+    SDFG_REQUIRE(D == 2 || D == 3, SDFG_ERR_UNSUPPORTED, "hash grid: input_dim must be 2 or 3 (got %u)", D);
+    SDFG_REQUIRE(C == 1 || C == 2 || C == 4 || C == 8, SDFG_ERR_UNSUPPORTED, "hash grid: level_dim must be 1, 2, 4 or 8 (got %u)", C);
+    SDFG_REQUIRE(L >= 1 && L <= (uint32_t)kMaxLevels, SDFG_ERR_UNSUPPORTED, "hash grid: num_levels must be in 1..%d (got %u)", kMaxLevels, L);
+    return SDFG_OK;
+}
+
+#define SDFG_DISPATCH_DC(D, C, CALL)                                   \
+    do {                                                               \
+        if (D == 3) {                                                  \
+            switch (C) {                                               \
+                case 1: return CALL(3, 1);                             \
+                case 2: return CALL(3, 2);                             \
+                case 4: return CALL(3, 4);                             \
+                default: return CALL(3, 8);                            \
+            }                                                          \
+        } else {                                                       \
+            switch (C) {                                               \
+                case 1: return CALL(2, 1);                             \
+                case 2: return CALL(2, 2);                             \
+                case 4: return CALL(2, 4);                             \
+                default: return CALL(2, 8);                            \
+            }                                                          \
+        }                                                              \
+    } while (0)
+
+}  // namespace sdfg
+
+using namespace sdfg;
+
+extern "C" int sdfg_grid_encode_forward(const float* inputs, const float* embeddings, const int* offsets, float* outputs,
+                                        uint32_t N, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, float bound,
+                                        float* dy_dx, uint32_t gridtype, int align_corners, uint32_t interp, int out_layout,
+                                        void* stream) {
+    if (int e = check_shape(D, C, L)) return e;
+    SDFG_REQUIRE(inputs && embeddings && offsets && outputs, SDFG_ERR_INVALID, "grid_encode_forward: null pointer");
+    SDFG_REQUIRE(out_layout == SDFG_LAYOUT_NLC || out_layout == SDFG_LAYOUT_LNC, SDFG_ERR_INVALID, "grid_encode_forward: bad layout %d", out_layout);
+    if (N == 0) return SDFG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(DD, CC) launch_forward<DD, CC>(inputs, embeddings, offsets, outputs, N, L, S, H, bound, dy_dx, gridtype, align_corners, interp, out_layout, st)
+    SDFG_DISPATCH_DC(D, C, CALL);
+#undef CALL
+}
+
+extern "C" int sdfg_grid_encode_backward(const float* grad, const float* inputs, const float* embeddings, const int* offsets,
+                                         float* grad_embeddings, uint32_t N, uint32_t D, uint32_t C, uint32_t L, float S,
+                                         uint32_t H, float bound, const float* dy_dx, float* grad_inputs, uint32_t gridtype,
+                                         int align_corners, uint32_t interp, int grad_layout, void* stream) {
+    (void)embeddings;
+    if (int e = check_shape(D, C, L)) return e;
+    SDFG_REQUIRE(grad && inputs && offsets, SDFG_ERR_INVALID, "grid_encode_backward: null pointer");
+    SDFG_REQUIRE(!grad_inputs || dy_dx, SDFG_ERR_INVALID, "grid_encode_backward: grad_inputs needs dy_dx");
+    SDFG_REQUIRE(grad_layout == SDFG_LAYOUT_NLC || grad_layout == SDFG_LAYOUT_LNC, SDFG_ERR_INVALID, "grid_encode_backward: bad layout %d", grad_layout);
+    if (N == 0) return SDFG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(DD, CC) launch_backward<DD, CC>(grad, inputs, offsets, grad_embeddings, N, L, S, H, bound, dy_dx, grad_inputs, gridtype, align_corners, interp, grad_layout, st)
+    SDFG_DISPATCH_DC(D, C, CALL);
+#undef CALL
+}
+
+extern "C" int sdfg_grad_total_variation(const float* inputs, const float* embeddings, float* grad, const int* offsets,
+                                         float weight, uint32_t N, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                                         uint32_t gridtype, int align_corners, void* stream) {
+    if (int e = check_shape(D, C, L)) return e;
+    SDFG_REQUIRE(inputs && embeddings && grad && offsets, SDFG_ERR_INVALID, "grad_total_variation: null pointer");
+    if (N == 0) return SDFG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL(DD, CC) launch_tv<DD, CC>(inputs, embeddings, grad, offsets, weight, N, L, S, H, gridtype, align_corners, st)
+    SDFG_DISPATCH_DC(D, C, CALL);
+#undef CALL
+}
+
+extern "C" int sdfg_grid_level_scales(float* out, uint32_t L, float S, uint32_t H, void* stream) {
+    SDFG_REQUIRE(out && L >= 1, SDFG_ERR_INVALID, "grid_level_scales: bad arguments");
+    grid_level_scales_kernel<<<ceil_div<uint32_t>(L, 32), 32, 0, (cudaStream_t)stream>>>(out, L, S, H);
+    return check_launch("grid_level_scales_kernel");
+}
+
+extern "C" int sdfg_grid_corner_indices(const float* inputs, const int* offsets, uint32_t* corner_idx, float* corner_w,
+                                        uint32_t N, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, float bound,
+                                        uint32_t gridtype, int align_corners, void* stream) {
+    if (int e = check_shape(D, C, L)) return e;
+    SDFG_REQUIRE(inputs && offsets && corner_idx, SDFG_ERR_INVALID, "grid_corner_indices: null pointer");
+    if (N == 0) return SDFG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t blocks = ceil_div<uint32_t>(N, 256);
+    if (D == 3) grid_corner_kernel<3><<<blocks, 256, 0, st>>>(inputs, offsets, corner_idx, corner_w, N, L, S, H, bound, gridtype, align_corners);
+    else grid_corner_kernel<2><<<blocks, 256, 0, st>>>(inputs, offsets, corner_idx, corner_w, N, L, S, H, bound, gridtype, align_corners);
+    return check_launch("grid_corner_kernel");
+}

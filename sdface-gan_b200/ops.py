@@ -1,0 +1,291 @@
+"""Tensor-level wrappers over the C-ABI (include/sdfg.h): argument checking, output allocation, current-stream launch.
+
+Every function here takes CUDA float32 tensors, calls exactly one C entry point on torch's current stream and raises
+RuntimeError on a non-zero status.  Nothing in this module (or anywhere in the package) computes on the CPU.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _chk(t, name, dtype=torch.float32):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (this path has no CPU fallback)" % name)
+    if t.dtype != dtype:
+        raise RuntimeError("%s must be %s (got %s)" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous" % name)
+    return t
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# rays
+
+def sample_rays(c2w, focal, near, far, t_vals, t_rand, jitter_mode, static_viewdirs, z_normalize, R, S, want_pts=True):
+    """sdfg_sample_rays.  Returns dict(z_vals [B,R,R,S], pts, npts [B,R,R,S,3], viewdirs, rays_d [B,R,R,3])."""
+    lib = _lib.load()
+    B = c2w.shape[0]
+    c2w = _chk(c2w.reshape(B, 12).contiguous().float(), "c2w")
+    focal = _chk(focal.reshape(B).contiguous().float(), "focal")
+    near = _chk(near.reshape(B).contiguous().float(), "near")
+    far = _chk(far.reshape(B).contiguous().float(), "far")
+    t_vals = _chk(t_vals.reshape(S).contiguous().float(), "t_vals")
+    if t_rand is not None:
+        t_rand = _chk(t_rand.contiguous().float(), "t_rand")
+        want = B * R * R * (S if jitter_mode == 2 else 1)
+        if t_rand.numel() != want:
+            raise RuntimeError("t_rand has %d elements, expected %d" % (t_rand.numel(), want))
+    dev = c2w.device
+    z = torch.empty(B, R, R, S, device=dev)
+    pts = torch.empty(B, R, R, S, 3, device=dev) if want_pts else None
+    npts = torch.empty(B, R, R, S, 3, device=dev)
+    vd = torch.empty(B, R, R, 3, device=dev)
+    rd = torch.empty(B, R, R, 3, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.sdfg_sample_rays(_ptr(c2w), _ptr(focal), _ptr(near), _ptr(far), _ptr(t_vals), _ptr(t_rand),
+                                        int(jitter_mode), int(bool(static_viewdirs)), int(bool(z_normalize)), B, R, S,
+                                        _ptr(z), _ptr(pts), _ptr(npts), _ptr(vd), _ptr(rd), _stream()), "sdfg_sample_rays")
+    return dict(z_vals=z, pts=pts, npts=npts, viewdirs=vd, rays_d=rd)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# hash grid
+
+def grid_encode_forward(inputs, embeddings, offsets, S, H, bound=0.0, calc_dy_dx=False, gridtype=0, align_corners=False,
+                        interp=0, layout=_lib.LAYOUT_NLC, outputs=None, dy_dx=None):
+    lib = _lib.load()
+    _chk(inputs, "inputs"); _chk(embeddings, "embeddings"); _chk(offsets, "offsets", torch.int32)
+    N, D = inputs.shape
+    C = embeddings.shape[1]
+    L = offsets.shape[0] - 1
+    if outputs is None:
+        outputs = torch.empty((N, L * C) if layout == _lib.LAYOUT_NLC else (L, N, C), device=inputs.device)
+    if calc_dy_dx and dy_dx is None:
+        dy_dx = torch.empty(N, L * D * C, device=inputs.device)
+    with torch.cuda.device(inputs.device):
+        _lib.check(lib.sdfg_grid_encode_forward(_ptr(inputs), _ptr(embeddings), _ptr(offsets), _ptr(_chk(outputs, "outputs")), N, D, C, L,
+                                                float(S), int(H), float(bound), _ptr(_chk(dy_dx, "dy_dx")), int(gridtype), int(bool(align_corners)),
+                                                int(interp), int(layout), _stream()), "sdfg_grid_encode_forward")
+    return outputs, dy_dx
+
+
+def grid_encode_backward(grad, inputs, embeddings, offsets, S, H, bound=0.0, dy_dx=None, grad_embeddings=None, want_grad_inputs=False,
+                         gridtype=0, align_corners=False, interp=0, layout=_lib.LAYOUT_NLC):
+    """Scatter `grad` into grad_embeddings (accumulating; pass None to skip) and/or reduce grad_inputs."""
+    lib = _lib.load()
+    _chk(grad, "grad"); _chk(inputs, "inputs"); _chk(offsets, "offsets", torch.int32)
+    N, D = inputs.shape
+    C = embeddings.shape[1]
+    L = offsets.shape[0] - 1
+    gi = torch.empty(N, D, device=inputs.device) if want_grad_inputs else None
+    with torch.cuda.device(inputs.device):
+        _lib.check(lib.sdfg_grid_encode_backward(_ptr(grad), _ptr(inputs), _ptr(embeddings), _ptr(offsets), _ptr(_chk(grad_embeddings, "grad_embeddings")),
+                                                 N, D, C, L, float(S), int(H), float(bound), _ptr(_chk(dy_dx, "dy_dx")), _ptr(gi), int(gridtype),
+                                                 int(bool(align_corners)), int(interp), int(layout), _stream()), "sdfg_grid_encode_backward")
+    return grad_embeddings, gi
+
+
+def grad_total_variation(inputs, embeddings, grad, offsets, weight, S, H, gridtype=0, align_corners=False):
+    lib = _lib.load()
+    _chk(inputs, "inputs"); _chk(embeddings, "embeddings"); _chk(grad, "grad"); _chk(offsets, "offsets", torch.int32)
+    N, D = inputs.shape
+    C = embeddings.shape[1]
+    L = offsets.shape[0] - 1
+    with torch.cuda.device(inputs.device):
+        _lib.check(lib.sdfg_grad_total_variation(_ptr(inputs), _ptr(embeddings), _ptr(grad), _ptr(offsets), float(weight), N, D, C, L,
+                                                 float(S), int(H), int(gridtype), int(bool(align_corners)), _stream()), "sdfg_grad_total_variation")
+
+
+def grid_level_scales(L, S, H, device):
+    lib = _lib.load()
+    out = torch.empty(L, device=device)
+    with torch.cuda.device(out.device):
+        _lib.check(lib.sdfg_grid_level_scales(_ptr(out), L, float(S), int(H), _stream()), "sdfg_grid_level_scales")
+    return out
+
+
+def grid_corner_indices(inputs, offsets, C, S, H, bound=0.0, gridtype=0, align_corners=False):
+    lib = _lib.load()
+    _chk(inputs, "inputs"); _chk(offsets, "offsets", torch.int32)
+    N, D = inputs.shape
+    L = offsets.shape[0] - 1
+    idx = torch.empty(N, L, 1 << D, device=inputs.device, dtype=torch.int32)
+    w = torch.empty(N, L, 1 << D, device=inputs.device)
+    with torch.cuda.device(inputs.device):
+        _lib.check(lib.sdfg_grid_corner_indices(_ptr(inputs), _ptr(offsets), _ptr(idx), _ptr(w), N, D, C, L, float(S), int(H), float(bound),
+                                                int(gridtype), int(bool(align_corners)), _stream()), "sdfg_grid_corner_indices")
+    return idx, w
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# spherical harmonics
+
+def sh_encode_forward(inputs, degree, calc_dy_dx=False):
+    lib = _lib.load()
+    _chk(inputs, "inputs")
+    N = inputs.shape[0]
+    out = torch.empty(N, degree * degree, device=inputs.device)
+    dy_dx = torch.empty(N, 3 * degree * degree, device=inputs.device) if calc_dy_dx else None
+    with torch.cuda.device(inputs.device):
+        _lib.check(lib.sdfg_sh_encode_forward(_ptr(inputs), _ptr(out), N, int(degree), _ptr(dy_dx), _stream()), "sdfg_sh_encode_forward")
+    return out, dy_dx
+
+
+def sh_encode_backward(grad, dy_dx, degree):
+    lib = _lib.load()
+    _chk(grad, "grad"); _chk(dy_dx, "dy_dx")
+    N = grad.shape[0]
+    gi = torch.zeros(N, 3, device=grad.device)
+    with torch.cuda.device(grad.device):
+        _lib.check(lib.sdfg_sh_encode_backward(_ptr(grad), _ptr(dy_dx), _ptr(gi), N, int(degree), _stream()), "sdfg_sh_encode_backward")
+    return gi
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# field
+
+class FieldSpec:
+    """Host description of one network (weights are read at call time, so optimizer updates are seen)."""
+
+    def __init__(self, width, in_dim, view_dim, n_film, has_input_linear):
+        self.width, self.in_dim, self.view_dim, self.n_film, self.has_input_linear = width, in_dim, view_dim, n_film, has_input_linear
+
+
+def _field_params(spec, samples_per_image, samples_per_ray, gamma, beta, weights):
+    """weights: dict(input_w, input_b, film_w [n+1], film_b [n+1], sigma_w, sigma_b, rgb_w, rgb_b) of CUDA tensors."""
+    p = _lib.FieldParams()
+    p.width, p.in_dim, p.view_dim, p.n_film = spec.width, spec.in_dim, spec.view_dim, spec.n_film
+    p.has_input_linear = int(spec.has_input_linear)
+    p.samples_per_image, p.samples_per_ray = int(samples_per_image), int(samples_per_ray)
+    if spec.has_input_linear:
+        p.input_w = _chk(weights["input_w"], "input_w").data_ptr()
+        p.input_b = _chk(weights["input_b"], "input_b").data_ptr()
+    for i in range(spec.n_film + 1):
+        p.film_w[i] = _chk(weights["film_w"][i], "film_w").data_ptr()
+        p.film_b[i] = _chk(weights["film_b"][i], "film_b").data_ptr()
+    p.gamma = _chk(gamma, "gamma").data_ptr()
+    p.beta = _chk(beta, "beta").data_ptr()
+    p.sigma_w = _chk(weights["sigma_w"], "sigma_w").data_ptr()
+    p.sigma_b = _chk(weights["sigma_b"], "sigma_b").data_ptr()
+    if weights.get("rgb_w") is not None:
+        p.rgb_w = _chk(weights["rgb_w"], "rgb_w").data_ptr()
+        p.rgb_b = _chk(weights["rgb_b"], "rgb_b").data_ptr()
+    return p
+
+
+def field_forward(spec, x_in, view_feat, gamma, beta, weights, samples_per_image, samples_per_ray, want_rgb=True, want_feat=True,
+                  save_for_backward=False, precision=_lib.PRECISION_FP32):
+    """Returns (sdf [N], rgb [N,3]|None, feat [N,W]|None, workspace)."""
+    lib = _lib.load()
+    _chk(x_in, "x_in"); _chk(view_feat, "view_feat")
+    N = x_in.shape[0]
+    dev = x_in.device
+    p = _field_params(spec, samples_per_image, samples_per_ray, gamma, beta, weights)
+    nbytes = int(lib.sdfg_field_workspace_bytes(ctypes.byref(p), N, int(save_for_backward), int(precision)))
+    ws = torch.empty(max(nbytes, 16) // 4, device=dev, dtype=torch.float32)
+    sdf = torch.empty(N, device=dev)
+    rgb = torch.empty(N, 3, device=dev) if want_rgb else None
+    feat = torch.empty(N, spec.width, device=dev) if want_feat else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.sdfg_field_forward(ctypes.byref(p), _ptr(x_in), _ptr(view_feat), N, _ptr(sdf), _ptr(rgb), _ptr(feat), _ptr(ws),
+                                          int(save_for_backward), int(precision), _stream()), "sdfg_field_forward")
+    return sdf, rgb, feat, ws
+
+
+def field_backward(spec, x_in, view_feat, gamma, beta, weights, samples_per_image, samples_per_ray, workspace, out_feat,
+                   d_sdf, d_rgb, d_feat, grads=None, want_dx=False, precision=_lib.PRECISION_FP32):
+    """grads: None (no parameter gradients) or dict like `weights` + gamma/beta of pre-zeroed (or live .grad) buffers that are
+    accumulated into.  Returns d_x_in [N,in_dim] or None."""
+    lib = _lib.load()
+    N = x_in.shape[0]
+    dev = x_in.device
+    p = _field_params(spec, samples_per_image, samples_per_ray, gamma, beta, weights)
+    g = None
+    if grads is not None:
+        g = _lib.FieldGrads()
+        if spec.has_input_linear:
+            g.input_w = _chk(grads["input_w"], "d_input_w").data_ptr()
+            g.input_b = _chk(grads["input_b"], "d_input_b").data_ptr()
+        for i in range(spec.n_film + 1):
+            g.film_w[i] = _chk(grads["film_w"][i], "d_film_w").data_ptr()
+            g.film_b[i] = _chk(grads["film_b"][i], "d_film_b").data_ptr()
+        g.gamma = _chk(grads["gamma"], "d_gamma").data_ptr()
+        g.beta = _chk(grads["beta"], "d_beta").data_ptr()
+        g.sigma_w = _chk(grads["sigma_w"], "d_sigma_w").data_ptr()
+        g.sigma_b = _chk(grads["sigma_b"], "d_sigma_b").data_ptr()
+        if grads.get("rgb_w") is not None:
+            g.rgb_w = _chk(grads["rgb_w"], "d_rgb_w").data_ptr()
+            g.rgb_b = _chk(grads["rgb_b"], "d_rgb_b").data_ptr()
+    nbytes = int(lib.sdfg_field_backward_scratch_bytes(ctypes.byref(p), N, int(precision)))
+    scratch = torch.empty(max(nbytes, 16) // 4, device=dev, dtype=torch.float32)
+    dx = torch.empty(N, spec.in_dim, device=dev) if want_dx else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.sdfg_field_backward(ctypes.byref(p), ctypes.byref(g) if g is not None else None, _ptr(x_in), _ptr(view_feat), N,
+                                           _ptr(_chk(d_sdf, "d_sdf")), _ptr(_chk(d_rgb, "d_rgb")), _ptr(_chk(d_feat, "d_feat")),
+                                           _ptr(out_feat), _ptr(workspace), _ptr(scratch), _ptr(dx), int(precision), _stream()),
+                   "sdfg_field_backward")
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# compositing
+
+def composite_forward(sdf, rgb, feat, z_vals, rays_d, pts, noise, sigmoid_beta, S, with_sdf, force_background, want_xyz):
+    """sdf [NR*S]; rgb [NR*S,3]; feat [NR*S,F]|None; z_vals [NR*S]; rays_d [NR,3]; pts [NR*S,3]|None.
+    Returns (rgb_map [NR,3], feat_map [NR,F]|None, xyz [NR,3]|None, mask [NR]|None)."""
+    lib = _lib.load()
+    NR = rays_d.shape[0]
+    dev = sdf.device
+    F = feat.shape[-1] if feat is not None else 0
+    rgb_map = torch.empty(NR, 3, device=dev)
+    feat_map = torch.empty(NR, F, device=dev) if feat is not None else None
+    xyz = torch.empty(NR, 3, device=dev) if want_xyz else None
+    mask = torch.empty(NR, device=dev) if want_xyz else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.sdfg_composite_forward(_ptr(_chk(sdf, "sdf")), _ptr(_chk(rgb, "rgb")), _ptr(_chk(feat, "feat")), _ptr(_chk(z_vals, "z_vals")),
+                                              _ptr(_chk(rays_d, "rays_d")), _ptr(_chk(pts, "pts")), _ptr(_chk(noise, "noise")),
+                                              _ptr(_chk(sigmoid_beta, "sigmoid_beta")), NR, int(S), int(F), int(bool(with_sdf)),
+                                              int(bool(force_background)), _ptr(rgb_map), _ptr(feat_map), _ptr(xyz), _ptr(mask), None,
+                                              _stream()), "sdfg_composite_forward")
+    return rgb_map, feat_map, xyz, mask
+
+
+def composite_backward(sdf, rgb, feat, z_vals, rays_d, pts, noise, sigmoid_beta, S, with_sdf, force_background,
+                       d_rgb_map, d_feat_map, d_xyz, d_mask, want_d_feat):
+    """Returns (d_sdf, d_rgb, d_feat|None, d_sigmoid_beta [1]|None)."""
+    lib = _lib.load()
+    NR = rays_d.shape[0]
+    dev = sdf.device
+    F = feat.shape[-1] if feat is not None else 0
+    d_sdf = torch.empty_like(sdf)
+    d_rgb = torch.empty_like(rgb)
+    d_feat = torch.empty_like(feat) if (feat is not None and want_d_feat) else None
+    d_beta = torch.zeros(1, device=dev) if with_sdf else None
+    use_feat = feat if (d_feat is not None or d_feat_map is not None) else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.sdfg_composite_backward(_ptr(sdf), _ptr(rgb), _ptr(use_feat), _ptr(z_vals), _ptr(rays_d), _ptr(pts), _ptr(noise),
+                                               _ptr(sigmoid_beta), NR, int(S), int(F), int(bool(with_sdf)), int(bool(force_background)),
+                                               _ptr(_chk(d_rgb_map, "d_rgb_map")), _ptr(_chk(d_feat_map, "d_feat_map")),
+                                               _ptr(_chk(d_xyz, "d_xyz")), _ptr(_chk(d_mask, "d_mask")), _ptr(d_sdf), _ptr(d_rgb),
+                                               _ptr(d_feat), None, _ptr(d_beta), _stream()), "sdfg_composite_backward")
+    return d_sdf, d_rgb, d_feat, d_beta
+
+
+def log2_scale(per_level_scale):
+    """S = log2(per_level_scale), rounded to float32 as the reference's pybind call does (gridencoder/grid.py:38)."""
+    return float(np.float32(np.log2(per_level_scale)))
