@@ -38,6 +38,11 @@ int sdfg_version(void);
 /* number of kernels launched by this library (all threads of the process) since the last reset (bench.py's gpu_launches) */
 int64_t sdfg_launch_count(void);
 void sdfg_launch_count_reset(void);
+/* per-kernel device timing for the roofline line of bench.py: while enabled, every launch whose tag contains
+ * `tag_substring` is bracketed by CUDA events on its own stream; collect() synchronises on them, returns the summed
+ * milliseconds and the number of launches, and clears the list. */
+void sdfg_prof_enable(int on, const char* tag_substring);
+int sdfg_prof_collect(double* total_ms, int64_t* launches);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Ray generation + depth sampling + point construction.

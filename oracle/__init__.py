@@ -45,6 +45,19 @@ def _p(a, ty=ctypes.c_float):
     return a.ctypes.data_as(ctypes.POINTER(ty))
 
 
+def cuda_level_scales(L, S, H):
+    """The per-level scale table as the CUDA device computes it (the reference evaluates `exp2f(level*S)*H - 1` on the GPU,
+    gridencoder.cu:138, and CUDA's exp2f is 1 ulp off libm's on some levels), from the values recorded on a B200 in
+    oracle/cuda_level_scales.json.  Returns None for configurations that were never recorded."""
+    import json
+    tabs = json.load(open(os.path.join(_HERE, "cuda_level_scales.json")))["tables"]
+    s_hex = int(np.float32(S).view(np.uint32))
+    for t in tabs:
+        if t["S_hex"] == s_hex and t["H"] == H and t["L"] >= L:
+            return np.array(t["scale_hex"][:L], np.uint32).view(np.float32).copy()
+    return None
+
+
 def grid_level_scales(L, S, H):
     out = np.empty(L, np.float32)
     lib().oracle_grid_level_scales(ctypes.c_uint32(L), ctypes.c_float(S), ctypes.c_uint32(H), _p(out))
@@ -65,6 +78,8 @@ def grid_encode_forward(inputs, embeddings, offsets, S, H, calc_dy_dx=False, gri
     dy_dx = np.empty((B, L, D, C), np.float32) if calc_dy_dx else None
     cidx = np.empty((B, L, 1 << D), np.uint32) if want_corners else None
     cw = np.empty((B, L, 1 << D), np.float32) if want_corners else None
+    if level_scales is None:
+        level_scales = cuda_level_scales(L, S, H)
     ls = None if level_scales is None else np.ascontiguousarray(level_scales, np.float32)
     lib().oracle_grid_encode_forward(
         _p(inputs), _p(embeddings), _p(offsets, ctypes.c_int), _p(out),
@@ -88,6 +103,8 @@ def grid_encode_backward(grad, inputs, embeddings, offsets, S, H, dy_dx=None, gr
         grad_embeddings = np.zeros_like(embeddings)
     gi = np.zeros((B, D), np.float32) if dy_dx is not None else None
     dd = None if dy_dx is None else np.ascontiguousarray(dy_dx, np.float32)
+    if level_scales is None:
+        level_scales = cuda_level_scales(L, S, H)
     ls = None if level_scales is None else np.ascontiguousarray(level_scales, np.float32)
     lib().oracle_grid_encode_backward(
         _p(grad), _p(inputs), _p(embeddings), _p(offsets, ctypes.c_int), _p(grad_embeddings),
@@ -106,6 +123,8 @@ def grad_total_variation(inputs, embeddings, grad, offsets, weight, S, H, gridty
     B, D = inputs.shape
     C = embeddings.shape[1]
     L = offsets.shape[0] - 1
+    if level_scales is None:
+        level_scales = cuda_level_scales(L, S, H)
     ls = None if level_scales is None else np.ascontiguousarray(level_scales, np.float32)
     lib().oracle_grad_total_variation(
         _p(inputs), _p(embeddings), _p(grad), _p(offsets, ctypes.c_int), ctypes.c_float(weight),

@@ -42,6 +42,8 @@ PROTOTYPES = {
     "sdfg_version": (i32, []),
     "sdfg_launch_count": (ctypes.c_int64, []),
     "sdfg_launch_count_reset": (None, []),
+    "sdfg_prof_enable": (None, [i32, ctypes.c_char_p]),
+    "sdfg_prof_collect": (i32, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "sdfg_sample_rays": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, u32, u32, u32, vp, vp, vp, vp, vp, vp]),
     "sdfg_grid_encode_forward": (i32, [vp, vp, vp, vp, u32, u32, u32, u32, f32, u32, f32, vp, u32, i32, u32, i32, vp]),
     "sdfg_grid_encode_backward": (i32, [vp, vp, vp, vp, vp, u32, u32, u32, u32, f32, u32, f32, vp, vp, u32, i32, u32, i32, vp]),
@@ -105,3 +107,14 @@ def launch_count():
 
 def launch_count_reset():
     load().sdfg_launch_count_reset()
+
+
+def prof_enable(on, tag=""):
+    load().sdfg_prof_enable(int(bool(on)), tag.encode())
+
+
+def prof_collect():
+    """-> (total milliseconds, launches) of the profiled kernels since the last collect."""
+    ms, n = ctypes.c_double(0), ctypes.c_int64(0)
+    load().sdfg_prof_collect(ctypes.byref(ms), ctypes.byref(n))
+    return ms.value, n.value

@@ -12,6 +12,15 @@ int set_error(int code, const char* fmt, ...);
 int check_launch(const char* what);   // cudaGetLastError -> SDFG_ERR_CUDA; also bumps the launch counter
 int sm_count();
 
+// Optional per-kernel timing for bench.py's roofline line: when enabled (sdfg_prof_enable) every launch site wrapped in a
+// ProfScope whose tag contains the configured substring is bracketed by CUDA events on its own stream.
+struct ProfScope {
+    ProfScope(const char* tag, cudaStream_t st);
+    ~ProfScope();
+    void* rec;
+    cudaStream_t st;
+};
+
 #define SDFG_REQUIRE(cond, code, ...)                        \
     do {                                                     \
         if (!(cond)) return ::sdfg::set_error(code, __VA_ARGS__); \

@@ -329,11 +329,11 @@ extern "C" int sdfg_composite_forward(const float* sdf, const float* rgb, const 
                                       uint64_t NR, uint32_t S, uint32_t F, int with_sdf, int force_background, float* rgb_map,
                                       float* feat_map, float* xyz_map, float* mask, float* weights, void* stream) {
     if (int e = check_composite(S, F, feat)) return e;
+    if (NR == 0) return SDFG_OK;
     SDFG_REQUIRE(sdf && rgb && z_vals && rays_d && rgb_map, SDFG_ERR_INVALID, "composite_forward: null pointer");
     SDFG_REQUIRE(!with_sdf || sigmoid_beta, SDFG_ERR_INVALID, "composite_forward: sdf mode needs sigmoid_beta");
     SDFG_REQUIRE(!xyz_map || pts, SDFG_ERR_INVALID, "composite_forward: xyz_map needs pts");
     SDFG_REQUIRE(!feat_map || feat, SDFG_ERR_INVALID, "composite_forward: feat_map needs feat");
-    if (NR == 0) return SDFG_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned blocks = (unsigned)ceil_div<uint64_t>(NR, 8);
 #define LAUNCH(KS)                                                                                                          \
@@ -354,11 +354,11 @@ extern "C" int sdfg_composite_backward(const float* sdf, const float* rgb, const
                                        const float* d_mask, float* d_sdf, float* d_rgb, float* d_feat, float* d_pts,
                                        float* d_sigmoid_beta, void* stream) {
     if (int e = check_composite(S, F, feat)) return e;
+    if (NR == 0) return SDFG_OK;
     SDFG_REQUIRE(sdf && rgb && z_vals && rays_d && d_sdf, SDFG_ERR_INVALID, "composite_backward: null pointer");
     SDFG_REQUIRE(!with_sdf || sigmoid_beta, SDFG_ERR_INVALID, "composite_backward: sdf mode needs sigmoid_beta");
     SDFG_REQUIRE(!d_xyz_map || pts, SDFG_ERR_INVALID, "composite_backward: d_xyz_map needs pts");
     SDFG_REQUIRE(!(d_feat_map || d_feat) || feat, SDFG_ERR_INVALID, "composite_backward: feature gradients need feat");
-    if (NR == 0) return SDFG_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned blocks = (unsigned)ceil_div<uint64_t>(NR, 8);
 #define LAUNCH(KS)                                                                                                          \

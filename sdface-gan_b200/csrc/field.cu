@@ -19,9 +19,9 @@ extern "C" int sdfg_field_forward(const sdfg_field_params* p, const float* x_in,
                                   float* out_sdf, float* out_rgb, float* out_feat, void* workspace, int save_for_backward,
                                   int precision, void* stream) {
     if (int e = field_check_params(p, N)) return e;
+    if (N == 0) return SDFG_OK;
     SDFG_REQUIRE(x_in && workspace, SDFG_ERR_INVALID, "field_forward: null pointer");
     SDFG_REQUIRE(out_sdf || out_rgb || out_feat, SDFG_ERR_INVALID, "field_forward: no output requested");
-    if (N == 0) return SDFG_OK;
     if (precision == SDFG_PRECISION_FP32)
         return field_forward_f32(p, x_in, view_feat, N, out_sdf, out_rgb, out_feat, workspace, save_for_backward, (cudaStream_t)stream);
     return set_error(SDFG_ERR_UNSUPPORTED, "field_forward: unknown precision %d", precision);
@@ -31,8 +31,8 @@ extern "C" int sdfg_field_backward(const sdfg_field_params* p, const sdfg_field_
                                    uint64_t N, const float* d_sdf, const float* d_rgb, const float* d_feat, const float* out_feat,
                                    const void* workspace, void* scratch, float* d_x_in, int precision, void* stream) {
     if (int e = field_check_params(p, N)) return e;
-    SDFG_REQUIRE(x_in && workspace && scratch, SDFG_ERR_INVALID, "field_backward: null pointer");
     if (N == 0) return SDFG_OK;
+    SDFG_REQUIRE(x_in && workspace && scratch, SDFG_ERR_INVALID, "field_backward: null pointer");
     if (precision == SDFG_PRECISION_FP32)
         return field_backward_f32(p, g, x_in, view_feat, N, d_sdf, d_rgb, d_feat, out_feat, workspace, scratch, d_x_in, (cudaStream_t)stream);
     return set_error(SDFG_ERR_UNSUPPORTED, "field_backward: unknown precision %d", precision);

@@ -188,6 +188,7 @@ static int launch_gemm(const GemmParams& P, cudaStream_t st, const char* what) {
         Q.k_split = per;
         grid.z = ceil_div<uint32_t>(K, per);
     }
+    ProfScope prof(what, st);
     gemm_f32_kernel<A_RC, B_RC, EPI><<<grid, 256, 0, st>>>(Q);
     return check_launch(what);
 }

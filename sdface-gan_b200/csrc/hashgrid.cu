@@ -465,9 +465,9 @@ extern "C" int sdfg_grid_encode_forward(const float* inputs, const float* embedd
                                         float* dy_dx, uint32_t gridtype, int align_corners, uint32_t interp, int out_layout,
                                         void* stream) {
     if (int e = check_shape(D, C, L)) return e;
+    if (N == 0) return SDFG_OK;
     SDFG_REQUIRE(inputs && embeddings && offsets && outputs, SDFG_ERR_INVALID, "grid_encode_forward: null pointer");
     SDFG_REQUIRE(out_layout == SDFG_LAYOUT_NLC || out_layout == SDFG_LAYOUT_LNC, SDFG_ERR_INVALID, "grid_encode_forward: bad layout %d", out_layout);
-    if (N == 0) return SDFG_OK;
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(DD, CC) launch_forward<DD, CC>(inputs, embeddings, offsets, outputs, N, L, S, H, bound, dy_dx, gridtype, align_corners, interp, out_layout, st)
     SDFG_DISPATCH_DC(D, C, CALL);
@@ -480,10 +480,10 @@ extern "C" int sdfg_grid_encode_backward(const float* grad, const float* inputs,
                                          int align_corners, uint32_t interp, int grad_layout, void* stream) {
     (void)embeddings;
     if (int e = check_shape(D, C, L)) return e;
+    if (N == 0) return SDFG_OK;
     SDFG_REQUIRE(grad && inputs && offsets, SDFG_ERR_INVALID, "grid_encode_backward: null pointer");
     SDFG_REQUIRE(!grad_inputs || dy_dx, SDFG_ERR_INVALID, "grid_encode_backward: grad_inputs needs dy_dx");
     SDFG_REQUIRE(grad_layout == SDFG_LAYOUT_NLC || grad_layout == SDFG_LAYOUT_LNC, SDFG_ERR_INVALID, "grid_encode_backward: bad layout %d", grad_layout);
-    if (N == 0) return SDFG_OK;
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(DD, CC) launch_backward<DD, CC>(grad, inputs, offsets, grad_embeddings, N, L, S, H, bound, dy_dx, grad_inputs, gridtype, align_corners, interp, grad_layout, st)
     SDFG_DISPATCH_DC(D, C, CALL);
@@ -494,8 +494,8 @@ extern "C" int sdfg_grad_total_variation(const float* inputs, const float* embed
                                          float weight, uint32_t N, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
                                          uint32_t gridtype, int align_corners, void* stream) {
     if (int e = check_shape(D, C, L)) return e;
-    SDFG_REQUIRE(inputs && embeddings && grad && offsets, SDFG_ERR_INVALID, "grad_total_variation: null pointer");
     if (N == 0) return SDFG_OK;
+    SDFG_REQUIRE(inputs && embeddings && grad && offsets, SDFG_ERR_INVALID, "grad_total_variation: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL(DD, CC) launch_tv<DD, CC>(inputs, embeddings, grad, offsets, weight, N, L, S, H, gridtype, align_corners, st)
     SDFG_DISPATCH_DC(D, C, CALL);
@@ -512,8 +512,8 @@ extern "C" int sdfg_grid_corner_indices(const float* inputs, const int* offsets,
                                         uint32_t N, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, float bound,
                                         uint32_t gridtype, int align_corners, void* stream) {
     if (int e = check_shape(D, C, L)) return e;
-    SDFG_REQUIRE(inputs && offsets && corner_idx, SDFG_ERR_INVALID, "grid_corner_indices: null pointer");
     if (N == 0) return SDFG_OK;
+    SDFG_REQUIRE(inputs && offsets && corner_idx, SDFG_ERR_INVALID, "grid_corner_indices: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t blocks = ceil_div<uint32_t>(N, 256);
     if (D == 3) grid_corner_kernel<3><<<blocks, 256, 0, st>>>(inputs, offsets, corner_idx, corner_w, N, L, S, H, bound, gridtype, align_corners);

@@ -116,8 +116,8 @@ using namespace sdfg;
 extern "C" int sdfg_sh_encode_forward(const float* inputs, float* outputs, uint32_t N, uint32_t degree, float* dy_dx,
                                       void* stream) {
     SDFG_REQUIRE(degree >= 1 && degree <= (uint32_t)kMaxDeg, SDFG_ERR_UNSUPPORTED, "sh_encode: degree must be in 1..8 (got %u)", degree);
-    SDFG_REQUIRE(inputs && outputs, SDFG_ERR_INVALID, "sh_encode_forward: null pointer");
     if (N == 0) return SDFG_OK;
+    SDFG_REQUIRE(inputs && outputs, SDFG_ERR_INVALID, "sh_encode_forward: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned blocks = ceil_div<uint32_t>(N, 256);
     if (dy_dx) sh_forward_kernel<true><<<blocks, 256, 0, st>>>(inputs, outputs, dy_dx, N, (int)degree, table());
@@ -128,8 +128,8 @@ extern "C" int sdfg_sh_encode_forward(const float* inputs, float* outputs, uint3
 extern "C" int sdfg_sh_encode_backward(const float* grad, const float* dy_dx, float* grad_inputs, uint32_t N, uint32_t degree,
                                        void* stream) {
     SDFG_REQUIRE(degree >= 1 && degree <= (uint32_t)kMaxDeg, SDFG_ERR_UNSUPPORTED, "sh_encode: degree must be in 1..8 (got %u)", degree);
-    SDFG_REQUIRE(grad && dy_dx && grad_inputs, SDFG_ERR_INVALID, "sh_encode_backward: null pointer");
     if (N == 0) return SDFG_OK;
+    SDFG_REQUIRE(grad && dy_dx && grad_inputs, SDFG_ERR_INVALID, "sh_encode_backward: null pointer");
     sh_backward_kernel<<<(unsigned)ceil_div<size_t>((size_t)N * 3, 256), 256, 0, (cudaStream_t)stream>>>(
         grad, dy_dx, grad_inputs, N, (int)(degree * degree));
     return check_launch("sh_backward_kernel");

@@ -1,0 +1,228 @@
+"""GPU parity of the field, the compositing and the whole Generator against the oracle and the reference-generated fixtures.
+
+Tolerances (north star): fp32 path max-abs 1e-3 on rendered maps; gradients 1e-2 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+import param_fill as pf
+from oracle import field_oracle as fo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _tuple_names(kw):
+    names = ["rgb", "thumb_rgb"]
+    if kw.get("return_xyz"):
+        names.append("xyz")
+    if kw.get("return_sdf"):
+        names.append("sdf")
+    if kw.get("return_eikonal"):
+        names.append("eikonal")
+    if kw.get("return_xyz"):
+        names.append("mask")
+    return names
+
+
+def _gen_kwargs(z):
+    kw = {}
+    if "out_sdf" in z.files:
+        kw["return_sdf"] = True
+    if "out_xyz" in z.files:
+        kw["return_xyz"] = True
+    if "out_eikonal" in z.files:
+        kw["return_eikonal"] = True
+    return kw
+
+
+@pytest.mark.parametrize("name", ["siren_fwd", "ngp_fwd_init", "ngp_fwd_tab1", "ngp_mesh", "ngp_nosdf_strat"])
+def test_generator_forward_matches_reference_fixture(name):
+    z = H.load_fixture(name)
+    g = H.product_generator(z, DEV)
+    inp = H.fixture_inputs(z, DEV)
+    kw = _gen_kwargs(z)
+    with torch.no_grad():
+        out = dict(zip(_tuple_names(kw), g([inp["z"]], inp["cam"], inp["focal"], inp["near"], inp["far"], t_rand=inp["t_rand"], **kw)))
+        style = g.style(inp["z"])
+        r_rgb, r_feat, _, _, _, _ = g.renderer(inp["cam"], inp["focal"], inp["near"], inp["far"], styles=style, t_rand=inp["t_rand"])
+    assert out["rgb"] is None
+    assert H.max_abs(style, z["style"]) < 1e-4
+    assert H.max_abs(out["thumb_rgb"], z["out_thumb_rgb"]) < 1e-3
+    if "features" in z.files:
+        assert H.max_abs(r_feat, z["features"]) < 1e-3
+    for k in ("sdf", "xyz", "mask"):
+        if "out_" + k in z.files:
+            assert H.max_abs(out[k], z["out_" + k]) < 1e-3, k
+
+
+@pytest.mark.parametrize("name", ["ngp_train", "ngp_train_feat", "siren_train"])
+def test_generator_training_step_matches_reference_fixture(name):
+    """Forward incl. sdf + eikonal, then the fixture's seeded linear loss; every parameter gradient is compared with the
+    reference's digest (L2 norm, random projection, 16 strided samples) at 1e-2 relative."""
+    z = H.load_fixture(name)
+    g = H.product_generator(z, DEV)
+    inp = H.fixture_inputs(z, DEV)
+    kw = _gen_kwargs(z)
+    if name == "siren_train":
+        kw.pop("return_eikonal", None)      # double backward through the SIREN trunk is outside the accelerated path
+    out = dict(zip(_tuple_names(kw), g([inp["z"]], inp["cam"], inp["focal"], inp["near"], inp["far"], t_rand=inp["t_rand"], **kw)))
+    assert H.max_abs(out["thumb_rgb"], z["out_thumb_rgb"]) < 1e-3
+    if "sdf" in out:
+        assert H.max_abs(out["sdf"], z["out_sdf"]) < 1e-3
+    if "eikonal" in out:
+        ref = z["out_eikonal"]
+        assert H.max_abs(out["eikonal"], ref) < 1e-3 * max(1.0, float(np.abs(ref).max()))
+        assert not out["eikonal"].requires_grad      # SURVEY finding 4: constant w.r.t. the parameters in ngp mode
+    loss = 0
+    for k in ("thumb_rgb", "sdf"):
+        if "lossw_" + k in z.files and k in out:
+            loss = loss + (torch.from_numpy(z["lossw_" + k]).to(DEV) * out[k]).sum() / out[k].numel() ** 0.5
+    assert abs(float(loss) - float(z["loss"])) < 1e-3
+    g.zero_grad()
+    loss.backward()
+    checked = 0
+    for pname, p in g.named_parameters():
+        if "g_norm_" + pname not in z.files:
+            continue
+        ref_norm = float(z["g_norm_" + pname])
+        if p.grad is None:
+            assert ref_norm == 0.0, pname
+            continue
+        d = pf.grad_digest(pname, p.grad.cpu().numpy())
+        assert abs(d["norm"] - ref_norm) <= 1e-2 * ref_norm + 1e-9, (pname, d["norm"], ref_norm)
+        assert abs(d["proj"] - float(z["g_proj_" + pname])) <= 1e-2 * ref_norm + 1e-9, pname
+        assert np.abs(d["val"] - z["g_val_" + pname]).max() <= 1e-2 * max(np.abs(z["g_val_" + pname]).max(), ref_norm / np.sqrt(p.numel())) + 1e-9, pname
+        checked += 1
+    assert checked >= 20
+    if "g_top_idx_embeddings" in z.files:
+        flat = dict(g.named_parameters())["renderer.network.encoder.embeddings"].grad.reshape(-1).cpu().numpy()
+        ref = z["g_top_val_embeddings"]
+        assert np.abs(flat[z["g_top_idx_embeddings"]] - ref).max() <= 1e-2 * np.abs(ref).max()
+
+
+def test_init_pass_matches_reference_fixture():
+    z = H.load_fixture("ngp_init_pass")
+    g = H.product_generator(z, DEV)
+    inp = H.fixture_inputs(z, DEV)
+    sdf, target = g.init_forward([inp["z"]], inp["cam"], inp["focal"], inp["near"], inp["far"], t_rand=inp["t_rand"])
+    assert H.max_abs(sdf, z["init_sdf"]) < 1e-3
+    assert H.max_abs(target, z["init_target"]) < 1e-5
+    torch.nn.functional.l1_loss(sdf, target).backward()
+    assert g.renderer.network.encoder.embeddings.grad.abs().sum() > 0
+
+
+def test_compat_network_forward_matches_oracle():
+    """NGPSIRENGenerator.forward(x[...,6], styles) -- the reference's own entry (sdf_model.py:1566) -- against the oracle."""
+    z = H.load_fixture("ngp_fwd_tab1")
+    g = H.product_generator(z, DEV)
+    params = H.fixture_params(z)
+    rp, sp = H.oracle_param_dicts(params)
+    torch.manual_seed(3)
+    x = torch.cat([torch.rand(2, 5, 7, 3) * 2 - 1, torch.nn.functional.normalize(torch.randn(2, 5, 7, 3), dim=-1)], -1)
+    style = fo.mapping(sp, torch.from_numpy(z["z"]))
+    with torch.no_grad():
+        ref = fo.field_ngp(rp, x[..., :3].unsqueeze(1), x[..., 3:].unsqueeze(1), style).squeeze(1)
+        out = g.renderer.network(x.to(DEV), style.to(DEV))
+    assert out.shape == ref.shape == (2, 5, 7, 260)
+    assert H.max_abs(out, ref) < 1e-3
+
+
+@pytest.mark.parametrize("S,F,with_sdf,fb", [(24, 256, True, False), (24, 0, True, False), (128, 256, True, True), (40, 64, False, False),
+                                              (1, 8, True, False)])
+def test_composite_forward_backward_matches_oracle(S, F, with_sdf, fb):
+    import sdface_gan_b200 as sg
+    from importlib import import_module
+    sm = import_module("sdface-gan_b200.sdf_model")
+    torch.manual_seed(S + F)
+    NR = 37
+    sdf = (torch.randn(NR, S) * 0.05).requires_grad_(True)
+    rgb = torch.randn(NR, S, 3).requires_grad_(True)
+    feat = torch.randn(NR, S, F).requires_grad_(True) if F else None
+    beta = torch.tensor([0.07], requires_grad=True)
+    z_vals = 0.88 + 0.24 * torch.sort(torch.rand(NR, S), -1)[0]
+    rays_d = torch.randn(NR, 3)
+    pts = torch.randn(NR, S, 3)
+    noise = torch.randn(NR, S) * 0.1 if not with_sdf else None
+    # oracle: shapes [B=1, H=NR, W=1, S, C]
+    raw = torch.cat([rgb, sdf.unsqueeze(-1)] + ([feat] if F else []), -1).view(1, NR, 1, S, -1)
+    o_rgb, o_feat, _, o_mask, o_xyz = fo.volume_integration(raw, z_vals.view(1, NR, 1, S), rays_d.view(1, NR, 1, 3), pts.view(1, NR, 1, S, 3), beta,
+                                                           with_sdf=with_sdf, output_features=bool(F), force_background=fb, return_xyz=True,
+                                                           raw_noise=None if noise is None else noise.view(1, NR, 1, S, 1), feature_dim=F)
+    ws = [torch.randn_like(o_rgb), torch.randn_like(o_xyz), torch.randn_like(o_mask)] + ([torch.randn_like(o_feat)] if F else [])
+    lo = (o_rgb * ws[0]).sum() + (o_xyz * ws[1]).sum() + (o_mask * ws[2]).sum() + ((o_feat * ws[3]).sum() if F else 0)
+    lo.backward()
+    # product
+    d = lambda t: None if t is None else t.detach().to(DEV)
+    sdf2 = d(sdf).reshape(-1).requires_grad_(True)
+    rgb2 = d(rgb).reshape(-1, 3).requires_grad_(True)
+    feat2 = d(feat).reshape(-1, F).requires_grad_(True) if F else None
+    beta2 = d(beta).requires_grad_(True)
+    p_rgb, p_feat, p_xyz, p_mask = sm._composite.apply(sdf2, rgb2, feat2, beta2 if with_sdf else None, d(z_vals).reshape(-1), d(rays_d),
+                                                      d(pts).reshape(-1, 3), None if noise is None else d(noise).reshape(-1), S, with_sdf, fb, True)
+    assert H.max_abs(p_rgb, o_rgb.view(NR, 3)) < 1e-5
+    assert H.max_abs(p_xyz, o_xyz.view(NR, 3)) < 1e-5
+    assert H.max_abs(p_mask, o_mask.view(NR)) < 1e-5
+    if F:
+        assert H.max_abs(p_feat, o_feat.view(NR, F)) < 2e-5
+    lp = (p_rgb * ws[0].view(NR, 3).to(DEV)).sum() + (p_xyz * ws[1].view(NR, 3).to(DEV)).sum() + (p_mask * ws[2].view(NR).to(DEV)).sum()
+    if F:
+        lp = lp + (p_feat * ws[3].view(NR, F).to(DEV)).sum()
+    lp.backward()
+    assert H.rel_err(sdf2.grad.view(NR, S), sdf.grad) < 1e-4
+    assert H.rel_err(rgb2.grad.view(NR, S, 3), rgb.grad) < 1e-4
+    if F:
+        assert H.rel_err(feat2.grad.view(NR, S, F), feat.grad) < 1e-4
+    if with_sdf:
+        assert H.rel_err(beta2.grad, beta.grad) < 1e-3
+
+
+def test_field_fp32_gradients_match_oracle_autograd():
+    """Field alone (no compositing): all parameter gradients + d/dx_in against torch autograd over the oracle, random upstream grads."""
+    z = H.load_fixture("ngp_fwd_tab1")
+    g = H.product_generator(z, DEV)
+    net = g.renderer.network
+    params = H.fixture_params(z, requires_grad=True)
+    rp, sp = H.oracle_param_dicts(params)
+    torch.manual_seed(11)
+    B, R, S = 2, 5, 6
+    npts = (torch.rand(B, R, R, S, 3) * 2 - 1)
+    vd = torch.nn.functional.normalize(torch.randn(B, R, R, 3), dim=-1)
+    style = torch.randn(B, 256) * 0.5
+    raw = fo.field_ngp(rp, npts, vd.unsqueeze(3).expand(B, R, R, S, 3), style)
+    w = torch.randn_like(raw)
+    (raw * w).sum().backward()
+    sdf, rgb, feat, _ = net.forward_rays(npts.to(DEV), vd.to(DEV), style.to(DEV))
+    out = torch.cat([rgb, sdf.unsqueeze(-1), feat], -1).view(raw.shape)
+    assert H.max_abs(out, raw) < 1e-3
+    (out * w.to(DEV)).sum().backward()
+    for pname, p in net.named_parameters():
+        ref = params["renderer.network." + pname].grad
+        assert ref is not None and p.grad is not None, pname
+        assert H.rel_err(p.grad, ref) < 1e-2, (pname, H.rel_err(p.grad, ref))
+
+
+def test_full_size_properties():
+    """BASELINE config-2 shape (B=4 here to bound memory; rows per image are the real 98 304): size-independent properties."""
+    import sdface_gan_b200 as sg
+    torch.manual_seed(0)
+    mo, ro = sg.default_options("ngp", renderer_res=64, n_samples=24, perturb=0., return_xyz=True, force_background=True)
+    g = sg.Generator(mo, ro, full_pipeline=False).to(DEV)
+    g.renderer.network.encoder.embeddings.data.uniform_(-0.5, 0.5)
+    B = 4
+    cam, focal, near, far, _ = sg.generate_camera_params(64, DEV, batch=B)
+    zlat = torch.randn(B, 256, device=DEV)
+    with torch.no_grad():
+        _, thumb, xyz, mask = g([zlat], cam, focal, near, far, return_xyz=True)
+        # batch independence: image 2 rendered alone equals image 2 of the batch (FiLM indexing by image, no cross-talk)
+        _, thumb1, xyz1, mask1 = g([zlat[2:3]], cam[2:3], focal[2:3], near[2:3], far[2:3], return_xyz=True)
+    assert thumb.shape == (B, 3, 64, 64) and torch.isfinite(thumb).all()
+    assert thumb.abs().max() <= 1.0 + 1e-5                          # rgb = -1 + 2 sum w sigmoid, sum w = 1 with forced background
+    assert H.max_abs(thumb[2:3], thumb1) < 1e-5 and H.max_abs(xyz[2:3], xyz1) < 1e-5
+    assert mask.min() >= -1e-5 and mask.max() <= 1 + 1e-5
+    # determinism of the forward (no atomics on the forward path)
+    with torch.no_grad():
+        _, thumb_b, _, _ = g([zlat], cam, focal, near, far, return_xyz=True)
+    assert torch.equal(thumb, thumb_b)
