@@ -163,7 +163,8 @@ typedef struct {
 uint64_t sdfg_field_workspace_bytes(const sdfg_field_params* p, uint64_t N, int save_for_backward, int precision);
 
 #define SDFG_PRECISION_FP32 0   /* SIMT fp32 FMA path: parity <= 1e-3 max-abs with the reference fp32 path */
-#define SDFG_PRECISION_TC16 1   /* tcgen05 path: fp16 operands, fp32 accumulate in TMEM (sm_100a) */
+#define SDFG_PRECISION_TC16 1   /* tcgen05 path: bf16 operands, fp32 accumulate in TMEM (sm_100a); needs width == 256 and
+                                   samples_per_image % 128 == 0 */
 
 /* forward.  x_in [N,in_dim]; view_feat [N/S, view_dim]; out_sdf [N]; out_rgb [N,3] (NULL ok); out_feat [N,W] (NULL ok);
  * workspace as sized above (kept by the caller until backward). */
@@ -179,6 +180,12 @@ uint64_t sdfg_field_backward_scratch_bytes(const sdfg_field_params* p, uint64_t 
 int sdfg_field_backward(const sdfg_field_params* p, const sdfg_field_grads* g, const float* x_in, const float* view_feat,
                         uint64_t N, const float* d_sdf, const float* d_rgb, const float* d_feat, const float* out_feat,
                         const void* workspace, void* scratch, float* d_x_in, int precision, void* stream);
+
+/* probe of the tcgen05 pipeline for the parity tests: out[M,N] (fp32) = bf16(x)[M,K] * bf16(w)[N,K]^T with fp32 accumulation.
+ * N multiple of 32 in 32..256, K <= 320. */
+uint64_t sdfg_tc_linear_probe_workspace_bytes(uint32_t M, uint32_t K, uint32_t N);
+int sdfg_tc_linear_probe(const float* x, const float* w, float* out, uint32_t M, uint32_t K, uint32_t N, void* workspace,
+                         void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * SDF -> density -> alpha -> front-to-back compositing.

@@ -6,6 +6,7 @@ using namespace sdfg;
 extern "C" uint64_t sdfg_field_workspace_bytes(const sdfg_field_params* p, uint64_t N, int save_for_backward, int precision) {
     if (!p) return 0;
     if (precision == SDFG_PRECISION_FP32) return field_workspace_bytes_f32(p, N, save_for_backward);
+    if (precision == SDFG_PRECISION_TC16) return field_workspace_bytes_tc(p, N, save_for_backward);
     return 0;
 }
 
@@ -24,6 +25,8 @@ extern "C" int sdfg_field_forward(const sdfg_field_params* p, const float* x_in,
     SDFG_REQUIRE(out_sdf || out_rgb || out_feat, SDFG_ERR_INVALID, "field_forward: no output requested");
     if (precision == SDFG_PRECISION_FP32)
         return field_forward_f32(p, x_in, view_feat, N, out_sdf, out_rgb, out_feat, workspace, save_for_backward, (cudaStream_t)stream);
+    if (precision == SDFG_PRECISION_TC16)
+        return field_forward_tc(p, x_in, view_feat, N, out_sdf, out_rgb, out_feat, workspace, save_for_backward, (cudaStream_t)stream);
     return set_error(SDFG_ERR_UNSUPPORTED, "field_forward: unknown precision %d", precision);
 }
 

@@ -242,6 +242,19 @@ def field_backward(spec, x_in, view_feat, gamma, beta, weights, samples_per_imag
     return dx
 
 
+def tc_linear_probe(x, w):
+    """out = bf16(x) @ bf16(w).T with fp32 accumulation, through the tcgen05 layer pipeline (parity-test probe)."""
+    lib = _lib.load()
+    _chk(x, "x"); _chk(w, "w")
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, device=x.device)
+    ws = torch.empty(int(lib.sdfg_tc_linear_probe_workspace_bytes(M, K, N)), device=x.device, dtype=torch.uint8)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sdfg_tc_linear_probe(_ptr(x), _ptr(w), _ptr(out), M, K, N, _ptr(ws), _stream()), "sdfg_tc_linear_probe")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # compositing
 

@@ -1,0 +1,93 @@
+"""GPU parity of the tcgen05 (bf16 operands, fp32 accumulate) path.
+
+Tolerance (north star): 2e-2 relative where the MLP runs in bf16; the raw GEMM probe is compared against an fp32 matmul of the
+same bf16-rounded operands, where only the accumulation order differs (1e-3 relative to the row scale)."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _sg():
+    import sdface_gan_b200 as sg
+    return sg
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 256), (1000, 256, 256), (4096 + 77, 272, 256), (300, 32, 256), (513, 256, 32), (129, 8, 256),
+                                   (20000, 256, 256)])
+def test_tc_linear_probe_matches_f16_matmul(M, K, N):
+    sg = _sg()
+    torch.manual_seed(M + K + N)
+    x = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV) / K ** 0.5
+    out = sg.ops.tc_linear_probe(x, w)
+    ref = x.half().float() @ w.half().float().t()
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3 * ref.abs().max().item(), (err, ref.abs().max().item())
+    # exactness of the data path: a one-hot x row picks out single (bf16-rounded) weights
+    e = torch.zeros(M, K, device=DEV)
+    idx = torch.arange(M, device=DEV) % K
+    e[torch.arange(M, device=DEV), idx] = 1.0
+    out = sg.ops.tc_linear_probe(e, w)
+    assert torch.equal(out, w.half().float().t()[idx])
+
+
+@pytest.mark.parametrize("name", ["ngp_fwd_tab1", "ngp_fwd_init", "ngp_mesh", "siren_fwd"])
+def test_tc_generator_forward_close_to_reference_fixture(name):
+    z = H.load_fixture(name)
+    g = H.product_generator(z, DEV, precision="tc16")
+    inp = H.fixture_inputs(z, DEV)
+    kw = {}
+    if "out_sdf" in z.files:
+        kw["return_sdf"] = True
+    if "out_xyz" in z.files:
+        kw["return_xyz"] = True
+    with torch.no_grad():
+        out = g([inp["z"]], inp["cam"], inp["focal"], inp["near"], inp["far"], t_rand=inp["t_rand"], **kw)
+        style = g.style(inp["z"])
+        _, feat, _, _, _, _ = g.renderer(inp["cam"], inp["focal"], inp["near"], inp["far"], styles=style, t_rand=inp["t_rand"])
+    thumb = out[1]
+    # the rgb map is -1 + 2*sum(w*sigmoid(.)): a difference of O(1) terms, so its error is measured against its [-1, 1] range;
+    # the direct MLP outputs (features, sdf) are compared in relative L2
+    assert H.max_abs(thumb, z["out_thumb_rgb"]) < 2e-2
+    if "features" in z.files:
+        assert H.rel_err(feat, z["features"]) < 2e-2
+    if "out_sdf" in z.files:
+        sdf = out[3] if "out_xyz" in z.files else out[2]
+        assert H.rel_err(sdf, z["out_sdf"]) < 2e-2
+
+
+def test_tc_field_matches_fp32_field_large():
+    """98 304 samples per image (the real 64x64x24 layout), 3 images: per-sample field outputs of the two CUDA paths."""
+    sg = _sg()
+    torch.manual_seed(0)
+    mo, ro = sg.default_options("ngp", renderer_res=64, n_samples=24, perturb=0.)
+    g = sg.Generator(mo, ro, full_pipeline=False).to(DEV)
+    net = g.renderer.network
+    net.encoder.embeddings.data.uniform_(-0.5, 0.5)
+    B = 3
+    npts = torch.rand(B, 64, 64, 24, 3, device=DEV) * 2 - 1
+    vd = torch.nn.functional.normalize(torch.randn(B, 64, 64, 3, device=DEV), dim=-1)
+    style = torch.randn(B, 256, device=DEV) * 0.5
+    with torch.no_grad():
+        net.precision = "fp32"
+        sdf0, rgb0, feat0, _ = net.forward_rays(npts, vd, style)
+        net.precision = "tc16"
+        sdf1, rgb1, feat1, _ = net.forward_rays(npts, vd, style)
+    assert H.rel_err(sdf1, sdf0) < 2e-2 and H.rel_err(rgb1, rgb0) < 2e-2 and H.rel_err(feat1, feat0) < 2e-2
+
+
+def test_tc_rejects_unaligned_images_loudly():
+    sg = _sg()
+    mo, ro = sg.default_options("ngp", renderer_res=6, n_samples=24, perturb=0.)       # 864 samples per image
+    g = sg.Generator(mo, ro, full_pipeline=False).to(DEV)
+    g.renderer.network.precision = "tc16"
+    cam, focal, near, far, _ = sg.generate_camera_params(6, DEV, batch=2)
+    with pytest.raises(RuntimeError, match="multiple of 128"):
+        with torch.no_grad():
+            g([torch.randn(2, 256, device=DEV)], cam, focal, near, far)
