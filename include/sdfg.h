@@ -187,6 +187,12 @@ uint64_t sdfg_tc_linear_probe_workspace_bytes(uint32_t M, uint32_t K, uint32_t N
 int sdfg_tc_linear_probe(const float* x, const float* w, float* out, uint32_t M, uint32_t K, uint32_t N, void* workspace,
                          void* stream);
 
+/* probe of the sample-axis (MN-major) weight-gradient contraction: G [B, 256, *ldg] (pre-zeroed, B = N / rows_per_image)
+ * G[b,j,k<Kx] = sum_{n in image b} bf16(dz)[n,j] * x16(x)[n,k];  G[b,j,*ones_col] = sum_n bf16(dz)[n,j].  x_fmt: 0 fp16, 1 bf16.
+ * workspace >= 2*N*(256 + Kx + 8) + 512 bytes. */
+int sdfg_tc_wgrad_probe(const float* dz, const float* x, float* G, uint32_t N, uint32_t Kx, uint32_t rows_per_image, uint32_t x_fmt,
+                        uint32_t* ldg, uint32_t* ones_col, void* workspace, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * SDF -> density -> alpha -> front-to-back compositing.
  * ref: VolumeFeatureRenderer.sdf_activation sdf_model.py:231-234 + volume_integration :236-301.

@@ -59,6 +59,7 @@ PROTOTYPES = {
                                   vp, i32, vp]),
     "sdfg_tc_linear_probe_workspace_bytes": (u64, [u32, u32, u32]),
     "sdfg_tc_linear_probe": (i32, [vp, vp, vp, u32, u32, u32, vp, vp]),
+    "sdfg_tc_wgrad_probe": (i32, [vp, vp, vp, u32, u32, u32, u32, ctypes.POINTER(u32), ctypes.POINTER(u32), vp, vp]),
     "sdfg_composite_forward": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "sdfg_composite_backward": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,
                                       vp, vp]),

@@ -12,7 +12,7 @@ extern "C" uint64_t sdfg_field_workspace_bytes(const sdfg_field_params* p, uint6
 
 extern "C" uint64_t sdfg_field_backward_scratch_bytes(const sdfg_field_params* p, uint64_t N, int precision) {
     if (!p) return 0;
-    (void)precision;
+    if (precision == SDFG_PRECISION_TC16) return field_backward_scratch_bytes_tc(p, N);
     return 2ull * N * p->width * sizeof(float);
 }
 
@@ -38,5 +38,7 @@ extern "C" int sdfg_field_backward(const sdfg_field_params* p, const sdfg_field_
     SDFG_REQUIRE(x_in && workspace && scratch, SDFG_ERR_INVALID, "field_backward: null pointer");
     if (precision == SDFG_PRECISION_FP32)
         return field_backward_f32(p, g, x_in, view_feat, N, d_sdf, d_rgb, d_feat, out_feat, workspace, scratch, d_x_in, (cudaStream_t)stream);
+    if (precision == SDFG_PRECISION_TC16)
+        return field_backward_tc(p, g, x_in, view_feat, N, d_sdf, d_rgb, d_feat, workspace, scratch, d_x_in, (cudaStream_t)stream);
     return set_error(SDFG_ERR_UNSUPPORTED, "field_backward: unknown precision %d", precision);
 }

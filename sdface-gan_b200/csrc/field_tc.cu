@@ -10,11 +10,15 @@
 //   A_l     fp16 [N, Kp_l]      input of FiLM layer l; the last trunk output is written with pitch Kp_views and the per-ray view
 //                               feature is expanded into its tail columns, so the views layer is one K = W + V contraction
 //   HV      fp16 [N, W]         output of the views layer (kept for the rgb-head weight gradient)
+//   X0b/Ab_l bf16 copies of X0 / A_l, written by the same epilogues when the forward is saved for backward: tcgen05.mma
+//                               .kind::f16 rejects mixed fp16 x bf16 operands (illegal instruction, measured), and the weight
+//                               gradient multiplies them with bf16 gradients
 // Algorithmic HBM bytes per sample and layer: 2*K in + 2*W out (fp16) -- 1 KB for a 256x256 layer, against 2 * 131072 flop.
 #include <algorithm>
 
 #include "field.cuh"
 #include "tc_layer.cuh"
+#include "tc_wgrad.cuh"
 
 namespace sdfg {
 
@@ -76,6 +80,7 @@ struct TcLayout {
     uint64_t N;
     uint64_t off_w[SDFG_MAX_FILM + 1];           // fp16 weights: [0] = input_linear, [1 + l] = FiLM layer l
     uint64_t off_x0, off_a[SDFG_MAX_FILM + 1], off_hv, total;
+    uint64_t off_x0b, off_ab[SDFG_MAX_FILM + 1];  // bf16 copies of X0 / A_l for the weight-gradient contraction (save only)
     int save;
 };
 
@@ -102,6 +107,11 @@ static TcLayout tc_layout(const sdfg_field_params* p, uint64_t N, int save) {
         L.off_a[l] = take(N * L.W * 2);
     }
     L.off_hv = take(save ? N * L.W * 2 : 0);
+    L.off_x0b = take(save ? N * L.Kp_in * 2 : 0);
+    for (uint32_t l = 0; l < L.n_layers; l++) {
+        if (l == 0 && !p->has_input_linear) { L.off_ab[0] = L.off_x0b; continue; }
+        L.off_ab[l] = take(save ? N * (l == L.n_film ? L.Kp_v : L.W) * 2 : 0);
+    }
     L.total = off;
     return L;
 }
@@ -125,6 +135,7 @@ int field_forward_tc(const sdfg_field_params* p, const float* x_in, const float*
     uint8_t* ws = (uint8_t*)workspace;
     auto Wb = [&](uint32_t i) { return (h16*)(ws + L.off_w[i]); };
     auto A = [&](uint32_t l) { return (h16*)(ws + L.off_a[l]); };
+    auto Ab = [&](uint32_t l) { return (h16*)(ws + L.off_ab[l]); };
     const uint32_t W = L.W, nf = L.n_film;
     const int64_t gstride = (int64_t)(nf + 1) * W;
     const bool want_views = out_rgb || out_feat;
@@ -139,11 +150,14 @@ int field_forward_tc(const sdfg_field_params* p, const float* x_in, const float*
     // 2. encoder features -> fp16
     h16* X0 = (h16*)(ws + L.off_x0);
     if (int e = cast_pad(x_in, p->in_dim, 1, X0, L.Kp_in, N, p->in_dim, L.Kp_in, st)) return e;
+    if (save)
+        if (int e = cast_pad(x_in, p->in_dim, 1, (h16*)(ws + L.off_x0b), L.Kp_in, N, p->in_dim, L.Kp_in, st, tc::FMT_BF16)) return e;
     // 3. input_linear
     if (p->has_input_linear) {
         LayerParams P = {};
         P.M_total = (uint32_t)N; P.N_out = W; P.rows_per_image = p->samples_per_image; P.act = 0; P.bias = p->input_b;
         P.out16 = A(0); P.ld_out = W;
+        if (save) { P.out16b = Ab(0); P.ld_out_b = W; }
         if (int e = launch_layer<tc::MODE_F>(X0, N, L.Kp_in, L.Kp_in, Wb(0), W, L.Kp_in, P, st, "tc_layer_kernel<F,gemm,linear>")) return e;
     }
     // 4. trunk
@@ -154,9 +168,12 @@ int field_forward_tc(const sdfg_field_params* p, const float* x_in, const float*
         P.gamma = p->gamma + (size_t)l * W; P.beta = p->beta + (size_t)l * W; P.gstride = gstride;
         const bool last = l + 1 == nf;
         if (!last || want_views || save) { P.out16 = A(l + 1); P.ld_out = last ? L.Kp_v : W; }
+        if (save) { P.out16b = Ab(l + 1); P.ld_out_b = last ? L.Kp_v : W; }
         if (last && out_sdf) { P.nh = 1; P.head_w = p->sigma_w; P.head_b = p->sigma_b; P.out_head = out_sdf; }
         if (int e = launch_layer<tc::MODE_F>(A(l), N, K, K, Wb(1 + l), W, K, P, st, "tc_layer_kernel<F,gemm,film>")) return e;
     }
+    if (save && view_feat)
+        if (int e = cast_pad(view_feat, p->view_dim, p->samples_per_ray, Ab(nf) + W, L.Kp_v, N, p->view_dim, L.Kp_v - W, st, tc::FMT_BF16)) return e;
     if (!want_views) return SDFG_OK;
     SDFG_REQUIRE(view_feat, SDFG_ERR_INVALID, "field_forward: view_feat is required for the rgb / feature outputs");
     SDFG_REQUIRE(!out_rgb || (p->rgb_w && p->rgb_b), SDFG_ERR_INVALID, "field_forward: rgb head missing");
@@ -175,6 +192,238 @@ int field_forward_tc(const sdfg_field_params* p, const float* x_in, const float*
     return SDFG_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// backward helpers
+
+// WgT[b][k][j] = bf16(gamma[b, j] * W[j, k])  for k < Kuse  (gamma == NULL: plain transpose, one "image")
+__global__ void __launch_bounds__(256) wgt_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ gamma, int64_t gstride,
+                                                   h16* __restrict__ out, uint32_t Kuse, uint32_t B) {
+    const uint32_t j = threadIdx.x;                 // 256 output neurons
+    const uint32_t k = blockIdx.x, b = blockIdx.y;
+    const float g = gamma ? __ldg(gamma + (int64_t)b * gstride + j) : 1.f;
+    out[((size_t)b * Kuse + k) * 256 + j] = __bfloat16_as_ushort(__float2bfloat16(g * __ldg(W + (int64_t)j * ldw + k)));
+}
+
+// finishing kernel of one layer's weight gradient: G [B, 256, ldg] -> dW, db, dgamma, dbeta   (block = neuron j, threads over k)
+__global__ void __launch_bounds__(128) wgrad_finish_kernel(const float* __restrict__ G, uint32_t ldg, uint32_t ones_col, uint32_t B,
+                                                            const float* __restrict__ W, int64_t ldw, uint32_t Kx, const float* __restrict__ bias,
+                                                            const float* __restrict__ gamma, int64_t gstride, int film,
+                                                            float* __restrict__ dW, float* __restrict__ db, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta) {
+    __shared__ float red[4];
+    const uint32_t j = blockIdx.x;
+    float dbj = 0.f;
+    for (uint32_t k = threadIdx.x; k < Kx; k += blockDim.x) {
+        float acc = 0.f;
+        for (uint32_t b = 0; b < B; b++) {
+            const float g = film ? __ldg(gamma + (int64_t)b * gstride + j) : 1.f;
+            acc = fmaf(g, __ldg(G + ((size_t)b * 256 + j) * ldg + k), acc);
+        }
+        dW[(int64_t)j * ldw + k] += acc;
+    }
+    for (uint32_t b = 0; b < B; b++) {
+        const float ones = __ldg(G + ((size_t)b * 256 + j) * ldg + ones_col);
+        if (film) {
+            float part = 0.f;
+            for (uint32_t k = threadIdx.x; k < Kx; k += blockDim.x) part = fmaf(__ldg(W + (int64_t)j * ldw + k), __ldg(G + ((size_t)b * 256 + j) * ldg + k), part);
+            part = warp_sum(part);
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const float tot = red[0] + red[1] + red[2] + red[3];
+                dgamma[(int64_t)b * gstride + j] += fmaf(__ldg(bias + j), ones, tot);
+                dbeta[(int64_t)b * gstride + j] += ones;
+            }
+            dbj = fmaf(__ldg(gamma + (int64_t)b * gstride + j), ones, dbj);
+        } else {
+            dbj += ones;
+        }
+    }
+    if (threadIdx.x == 0) db[j] += dbj;
+}
+
+// head weight gradient: dw[c, k] += sum_n dout[n, c] * h[n, k]   (h fp16, pitch ld), db[c] += sum_n dout[n, c];  block = 256 columns
+template <int NOUT>
+__global__ void __launch_bounds__(256) head_wgrad16_kernel(const float* __restrict__ dout, const h16* __restrict__ h, int64_t ld,
+                                                            float* __restrict__ dw, float* __restrict__ db, uint64_t M, uint32_t rows_per_block) {
+    const uint32_t k = threadIdx.x;
+    const uint64_t m0 = (uint64_t)blockIdx.x * rows_per_block, m1 = min(M, m0 + rows_per_block);
+    float gw[NOUT], gb[NOUT];
+#pragma unroll
+    for (int c = 0; c < NOUT; c++) { gw[c] = 0.f; gb[c] = 0.f; }
+    for (uint64_t m = m0; m < m1; m++) {
+        const float hv = __half2float(__ushort_as_half(h[m * ld + k]));
+#pragma unroll
+        for (int c = 0; c < NOUT; c++) {
+            const float d = __ldg(dout + m * NOUT + c);
+            gw[c] = fmaf(d, hv, gw[c]);
+            gb[c] += d;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NOUT; c++) {
+        red_add_f32(dw + (size_t)c * 256 + k, gw[c]);
+        if (k == 0) red_add_f32(db + c, gb[c]);
+    }
+}
+
+static int launch_wgrad(const h16* dz, const h16* x, uint32_t Kx, int64_t ldx, uint64_t N, uint32_t rows_per_image, float* G, uint32_t* ldg_out,
+                        uint32_t* ones_out, cudaStream_t st, uint32_t x_fmt = tc::FMT_F16) {
+    tc::WgradParams P = {};
+    P.n_stage_total = (uint32_t)(N / tc::WG_ROWS);
+    P.rows_per_image = rows_per_image;
+    P.Kx = Kx;
+    P.n_xbox = ceil_div<uint32_t>(Kx, 64);
+    P.n_main = std::min<uint32_t>(round_up(Kx, 64), 256);
+    P.n_extra = P.n_xbox > 4 ? 64 : 0;
+    P.ones_col = P.n_main + P.n_extra;
+    P.ldg = P.ones_col + 16;
+    P.x_fmt = x_fmt;
+    P.G = G;
+    *ldg_out = P.ldg;
+    *ones_out = P.ones_col;
+    const uint32_t pairs = std::max(1u, std::min<uint32_t>((uint32_t)sm_count() / 2, P.n_stage_total));
+    P.stages_per_pair = ceil_div<uint32_t>(P.n_stage_total, pairs);
+    const uint32_t grid = 2 * ceil_div<uint32_t>(P.n_stage_total, P.stages_per_pair);
+    CUtensorMap tmDZ, tmX;
+    if (int e = make_tensor_map_16(&tmDZ, dz, N, 256, 256, tc::WG_ROWS, 64, tc::FMT_BF16)) return e;
+    if (int e = make_tensor_map_16(&tmX, x, N, (uint64_t)ldx, (uint64_t)ldx, tc::WG_ROWS, 64, x_fmt)) return e;
+    const uint32_t smem = tc::wgrad_smem_bytes(P.n_xbox);
+    static thread_local uint32_t configured = 0;
+    if (configured < smem) {
+        if (cudaFuncSetAttribute(tc::tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return set_error(SDFG_ERR_CUDA, "tc_wgrad_kernel: cannot opt in to %u bytes of shared memory", smem);
+        configured = smem;
+    }
+    ProfScope prof("tc_wgrad_kernel<gemm>", st);
+    tc::tc_wgrad_kernel<<<grid, tc::WG_THREADS, smem, st>>>(tmDZ, tmX, P);
+    return check_launch("tc_wgrad_kernel<gemm>");
+}
+
+// scratch: DZ [N,256] bf16 | DH [N,256] bf16 | WgT [B, 256, 256] bf16 | G [B, 256, 336] fp32
+struct TcScratch { uint64_t off_dz, off_dh, off_wgt, off_g, total; };
+static TcScratch tc_scratch(const sdfg_field_params* p, uint64_t N) {
+    TcScratch s = {};
+    const uint64_t B = ceil_div<uint64_t>(N, p->samples_per_image);
+    uint64_t off = 0;
+    auto take = [&](uint64_t bytes) { const uint64_t o = off; off = align256(off + bytes); return o; };
+    s.off_dz = take(N * 256 * 2);
+    s.off_dh = take(N * 256 * 2);
+    s.off_wgt = take(B * 256 * 256 * 2);
+    s.off_g = take(B * 256 * 336 * 4);
+    s.total = off;
+    return s;
+}
+uint64_t field_backward_scratch_bytes_tc(const sdfg_field_params* p, uint64_t N) { return tc_scratch(p, N).total; }
+
+int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, const float* x_in, const float* view_feat, uint64_t N,
+                      const float* d_sdf, const float* d_rgb, const float* d_feat, const void* workspace, void* scratch, float* d_x_in,
+                      cudaStream_t st) {
+    (void)x_in; (void)view_feat;
+    if (int e = check_tc(p, N)) return e;
+    SDFG_REQUIRE(d_sdf || d_rgb || d_feat, SDFG_ERR_INVALID, "field_backward: no output gradient given");
+    SDFG_REQUIRE(!d_x_in || (p->has_input_linear && p->in_dim % 32 == 0), SDFG_ERR_UNSUPPORTED,
+                 "tc field_backward: d_x_in needs an input_linear layer and in_dim %% 32 == 0");
+    const TcLayout L = tc_layout(p, N, 1);
+    const TcScratch SC = tc_scratch(p, N);
+    const uint8_t* ws = (const uint8_t*)workspace;
+    uint8_t* sc = (uint8_t*)scratch;
+    auto Wb = [&](uint32_t i) { return (const h16*)(ws + L.off_w[i]); };
+    auto A = [&](uint32_t l) { return (const h16*)(ws + L.off_a[l]); };
+    auto Ab = [&](uint32_t l) { return (const h16*)(ws + L.off_ab[l]); };
+    h16* DZ = (h16*)(sc + SC.off_dz);
+    h16* DH = (h16*)(sc + SC.off_dh);
+    h16* WGT = (h16*)(sc + SC.off_wgt);
+    float* G = (float*)(sc + SC.off_g);
+    const uint32_t W = L.W, nf = L.n_film;
+    const uint32_t B = (uint32_t)ceil_div<uint64_t>(N, p->samples_per_image);
+    const int64_t gstride = (int64_t)(nf + 1) * W;
+    const uint32_t spi = p->samples_per_image;
+
+    auto layer_K = [&](uint32_t l) { return l == nf ? L.Kp_v : ((l == 0 && !p->has_input_linear) ? L.Kp_in : W); };      // padded
+    auto layer_Kx = [&](uint32_t l) { return l == nf ? W + p->view_dim : ((l == 0 && !p->has_input_linear) ? p->in_dim : W); };
+
+    // R: DZ = dh * cos(z_l), z recomputed from A_l
+    auto run_R = [&](uint32_t l, const h16* dh16, const float* dh32, int rank, const float* rs, const float* rv) -> int {
+        LayerParams P = {};
+        P.M_total = (uint32_t)N; P.N_out = W; P.rows_per_image = spi; P.bias = p->film_b[l];
+        P.gamma = p->gamma + (size_t)l * W; P.beta = p->beta + (size_t)l * W; P.gstride = gstride;
+        P.ab_fmt = tc::FMT_F16; P.out_fmt = tc::FMT_BF16; P.out16 = DZ; P.ld_out = W;
+        P.dh_bf16 = reinterpret_cast<const __nv_bfloat16*>(dh16); P.ld_dh = W; P.dh_f32 = dh32; P.ld_dh_f32 = W;
+        P.rank = rank; P.rank_s = rs; P.rank_v = rv;
+        return launch_layer<tc::MODE_R>(A(l), N, layer_K(l), layer_K(l), Wb(1 + l), W, layer_K(l), P, st, "tc_layer_kernel<R,gemm>");
+    };
+    // W: parameter gradients of layer l from DZ and its input
+    auto run_W = [&](uint32_t l) -> int {
+        if (!g || !g->film_w[l]) return SDFG_OK;
+        if (cudaMemsetAsync(G, 0, (size_t)B * 256 * 336 * 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");
+        uint32_t ldg, ones;
+        if (int e = launch_wgrad(DZ, Ab(l), layer_Kx(l), layer_K(l), N, spi, G, &ldg, &ones, st, tc::FMT_BF16)) return e;
+        wgrad_finish_kernel<<<256, 128, 0, st>>>(G, ldg, ones, B, p->film_w[l], layer_Kx(l), layer_Kx(l), p->film_b[l], p->gamma + (size_t)l * W,
+                                                 gstride, 1, g->film_w[l], g->film_b[l], g->gamma + (size_t)l * W, g->beta + (size_t)l * W);
+        return check_launch("wgrad_finish_kernel");
+    };
+    // D: DH = DZ * (gamma o W_l)[:, :Kout]  (+ rank-1)
+    auto run_D = [&](uint32_t l, uint32_t Kout, const float* rs, const float* rv) -> int {
+        wgt_kernel<<<dim3(Kout, B), 256, 0, st>>>(p->film_w[l], layer_Kx(l), p->gamma + (size_t)l * W, gstride, WGT, Kout, B);
+        if (int e = check_launch("wgt_kernel")) return e;
+        LayerParams P = {};
+        P.M_total = (uint32_t)N; P.N_out = Kout; P.rows_per_image = spi; P.b_rows_per_image = Kout;
+        P.ab_fmt = tc::FMT_BF16; P.out_fmt = tc::FMT_BF16; P.out16 = DH; P.ld_out = W;
+        P.rank = rs ? 1 : 0; P.rank_s = rs; P.rank_v = rv;
+        return launch_layer<tc::MODE_D>(DZ, N, W, W, WGT, (uint64_t)B * Kout, W, P, st, "tc_layer_kernel<D,gemm>");
+    };
+
+    const h16* dh16 = nullptr;      // where d(h of the last trunk layer) lives, if in memory
+    bool rank1_sdf = false;         // ... or whether it is the rank-1 term d_sdf * w_sigma
+    const h16* h_last = A(nf);      // last trunk output (pitch Kp_v)
+    if (d_rgb || d_feat) {
+        if (int e = run_R(nf, nullptr, d_feat, d_rgb ? 3 : 0, d_rgb, p->rgb_w)) return e;
+        if (g && g->rgb_w && d_rgb) {
+            head_wgrad16_kernel<3><<<(unsigned)ceil_div<uint64_t>(N, 512), 256, 0, st>>>(d_rgb, (const h16*)(ws + L.off_hv), W, g->rgb_w, g->rgb_b, N, 512);
+            if (int e = check_launch("head_wgrad16_kernel<3>")) return e;
+        }
+        if (int e = run_W(nf)) return e;
+        if (int e = run_D(nf, W, d_sdf, p->sigma_w)) return e;
+        dh16 = DH;
+    } else {
+        rank1_sdf = true;
+    }
+    if (g && g->sigma_w && d_sdf) {
+        head_wgrad16_kernel<1><<<(unsigned)ceil_div<uint64_t>(N, 512), 256, 0, st>>>(d_sdf, h_last, L.Kp_v, g->sigma_w, g->sigma_b, N, 512);
+        if (int e = check_launch("head_wgrad16_kernel<1>")) return e;
+    }
+    for (int l = (int)nf - 1; l >= 0; l--) {
+        const bool top = l == (int)nf - 1;
+        if (int e = run_R((uint32_t)l, top && rank1_sdf ? nullptr : DH, nullptr, top && rank1_sdf ? 1 : 0, d_sdf, p->sigma_w)) return e;
+        if (int e = run_W((uint32_t)l)) return e;
+        const bool need_dx = l > 0 || p->has_input_linear;
+        if (need_dx)
+            if (int e = run_D((uint32_t)l, W, nullptr, nullptr)) return e;
+    }
+    (void)dh16;
+    if (p->has_input_linear) {
+        if (g && g->input_w) {
+            if (cudaMemsetAsync(G, 0, (size_t)B * 256 * 336 * 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");
+            uint32_t ldg, ones;
+            if (int e = launch_wgrad(DH, (const h16*)(ws + L.off_x0b), p->in_dim, L.Kp_in, N, spi, G, &ldg, &ones, st, tc::FMT_BF16)) return e;
+            wgrad_finish_kernel<<<256, 128, 0, st>>>(G, ldg, ones, B, p->input_w, p->in_dim, p->in_dim, p->input_b, nullptr, 0, 0, g->input_w,
+                                                     g->input_b, nullptr, nullptr);
+            if (int e = check_launch("wgrad_finish_kernel")) return e;
+        }
+        if (d_x_in) {
+            wgt_kernel<<<dim3(p->in_dim, 1), 256, 0, st>>>(p->input_w, p->in_dim, nullptr, 0, WGT, p->in_dim, 1);
+            if (int e = check_launch("wgt_kernel")) return e;
+            LayerParams P = {};
+            P.M_total = (uint32_t)N; P.N_out = p->in_dim; P.rows_per_image = spi; P.b_rows_per_image = 0;
+            P.ab_fmt = tc::FMT_BF16; P.out_f32 = d_x_in; P.ld_out_f32 = p->in_dim;
+            if (int e = launch_layer<tc::MODE_D>(DH, N, W, W, WGT, p->in_dim, W, P, st, "tc_layer_kernel<D,gemm,in>")) return e;
+        }
+    }
+    return SDFG_OK;
+}
+
 // probe for the parity tests: out[M,N] = f16(x)[M,K] * f16(w)[N,K]^T through the MODE_F pipeline (linear epilogue, zero bias)
 int tc_linear_probe(const float* x, const float* w, float* out, uint32_t M, uint32_t K, uint32_t N, void* workspace, cudaStream_t st) {
     const uint32_t Kp = round_up(K, 8);
@@ -189,7 +438,26 @@ int tc_linear_probe(const float* x, const float* w, float* out, uint32_t M, uint
     return launch_layer<tc::MODE_F>(xb, M, Kp, Kp, wb, N, Kp, P, st, "tc_layer_kernel<F,gemm,probe>");
 }
 
+// probe of the weight-gradient contraction: G[b, j, 0..Kx) = sum_{n in image b} bf16(dz)[n, j] * fmt(x)[n, k]; G[b, j, ones] = sum dz
+int tc_wgrad_probe(const float* dz, const float* x, float* G, uint32_t N, uint32_t Kx, uint32_t rows_per_image, uint32_t x_fmt, uint32_t* ldg,
+                   uint32_t* ones, void* workspace, cudaStream_t st) {
+    const uint32_t Kp = round_up(Kx, 8);
+    h16* dzb = (h16*)workspace;
+    h16* xb = dzb + align256((uint64_t)N * 256 * 2) / 2;
+    if (int e = cast_pad(dz, 256, 1, dzb, 256, N, 256, 256, st, tc::FMT_BF16)) return e;
+    if (int e = cast_pad(x, Kx, 1, xb, Kp, N, Kx, Kp, st, x_fmt)) return e;
+    return launch_wgrad(dzb, xb, Kx, Kp, N, rows_per_image, G, ldg, ones, st, x_fmt);
+}
+
 }  // namespace sdfg
+
+extern "C" int sdfg_tc_wgrad_probe(const float* dz, const float* x, float* G, uint32_t N, uint32_t Kx, uint32_t rows_per_image, uint32_t x_fmt,
+                                   uint32_t* ldg, uint32_t* ones_col, void* workspace, void* stream) {
+    using namespace sdfg;
+    SDFG_REQUIRE(dz && x && G && workspace && ldg && ones_col, SDFG_ERR_INVALID, "tc_wgrad_probe: null pointer");
+    SDFG_REQUIRE(N % 128 == 0 && rows_per_image % 128 == 0 && Kx <= 320, SDFG_ERR_UNSUPPORTED, "tc_wgrad_probe: N and rows_per_image must be multiples of 128, Kx <= 320");
+    return tc_wgrad_probe(dz, x, G, N, Kx, rows_per_image, x_fmt, ldg, ones_col, workspace, (cudaStream_t)stream);
+}
 
 extern "C" uint64_t sdfg_tc_linear_probe_workspace_bytes(uint32_t M, uint32_t K, uint32_t N) {
     const uint64_t Kp = sdfg::round_up(K, 8);

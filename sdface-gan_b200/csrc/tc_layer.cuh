@@ -40,6 +40,8 @@ struct LayerParams {
     int64_t gstride;
     uint16_t* out16;                // F: h (fp16), R: dz (bf16), D: dh_in (bf16)     [M_total, ld_out]   (NULL ok)
     int64_t ld_out;
+    uint16_t* out16b;               // F: second copy of h in bf16 (operand of the weight-gradient contraction)   (NULL ok)
+    int64_t ld_out_b;
     float* out_f32;                 // F: fp32 copy of h, D: fp32 result             [M_total, ld_out_f32]   (NULL ok)
     int64_t ld_out_f32;
     int nh;                         // MODE_F heads: out_head[row*nh + c] = sum_n h[row,n] * head_w[c*N_out + n] + head_b[c]
@@ -281,6 +283,13 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         for (int j = 0; j < 4; j++)
                             dst[j] = make_uint4(pack16(v[j * 8], v[j * 8 + 1], f), pack16(v[j * 8 + 2], v[j * 8 + 3], f),
                                                 pack16(v[j * 8 + 4], v[j * 8 + 5], f), pack16(v[j * 8 + 6], v[j * 8 + 7], f));
+                    }
+                    if (MODE == MODE_F && P.out16b) {
+                        uint4* dst = reinterpret_cast<uint4*>(P.out16b + row * P.ld_out_b + c);
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            dst[j] = make_uint4(pack_bf16(v[j * 8], v[j * 8 + 1]), pack_bf16(v[j * 8 + 2], v[j * 8 + 3]),
+                                                pack_bf16(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16(v[j * 8 + 6], v[j * 8 + 7]));
                     }
                     if (P.out_f32) {
                         float4* dst = reinterpret_cast<float4*>(P.out_f32 + row * P.ld_out_f32 + c);

@@ -255,6 +255,23 @@ def tc_linear_probe(x, w):
     return out
 
 
+def tc_wgrad_probe(dz, x, rows_per_image, x_fmt=0):
+    """G[b, j, k] = sum_{n in image b} bf16(dz)[n, j] * x16(x)[n, k] plus the ones column; returns (G [B,256,Kx], colsum [B,256])."""
+    lib = _lib.load()
+    _chk(dz, "dz"); _chk(x, "x")
+    N, Kx = x.shape
+    B = N // rows_per_image
+    G = torch.zeros(B, 256, 336, device=x.device)
+    ws = torch.empty(2 * N * (256 + Kx + 8) + 512, device=x.device, dtype=torch.uint8)
+    ldg, ones = ctypes.c_uint32(0), ctypes.c_uint32(0)
+    # the kernel is told the pitch it must use through G's allocation: probe once for ldg, then view
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sdfg_tc_wgrad_probe(_ptr(dz), _ptr(x), _ptr(G), N, Kx, int(rows_per_image), int(x_fmt), ctypes.byref(ldg), ctypes.byref(ones),
+                                           _ptr(ws), _stream()), "sdfg_tc_wgrad_probe")
+    flat = G.reshape(-1)[:B * 256 * ldg.value].view(B, 256, ldg.value)
+    return flat[:, :, :Kx], flat[:, :, ones.value]
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # compositing
 
