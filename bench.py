@@ -267,7 +267,7 @@ def run_ours(args):
                    "sample": "1 image (98304 samples) per step, fwd+bwd, %d steps" % n}
         line = {"metric": "images/sec (generator fwd+bwd, field+composite)", "value": world * B / (ms * 1e-3), "unit": "images/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f16/bf16 operands, f32 accumulate", "data": "synthetic",
                 "msamples_per_s": world * N / (ms * 1e-3) / 1e6,
                 "config": {"workload": "configs[1]: 64^2 SDF + hash-grid (ngp=1) generator forward+backward, stage-1 G step", "rays": R,
                            "samples_per_ray": S, "batch_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world,
@@ -288,7 +288,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=1, help="images per CPU reference step (bounded sample)")
-    ap.add_argument("--precision", default=os.environ.get("SDFG_PRECISION", "fp32"), choices=["fp32", "tc16"])
+    ap.add_argument("--precision", default=os.environ.get("SDFG_PRECISION", "tc16"), choices=["fp32", "tc16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

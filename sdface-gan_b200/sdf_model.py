@@ -165,7 +165,15 @@ def _unpack_weights(spec, w):
 class _FieldNetwork(nn.Module):
     """Shared driver of SirenGenerator / NGPSIRENGenerator: evaluates the whole network through `_field`."""
 
-    precision = "fp32"
+    # "auto": the tcgen05 path (fp16 activations / bf16 gradients, fp32 accumulate) whenever its shape constraints hold
+    # (width 256, samples per image a multiple of 128), else the fp32 SIMT path.  Both are CUDA; neither falls back to the CPU.
+    precision = "auto"
+
+    def _pick_precision(self, samples_per_image):
+        if self.precision != "auto":
+            return _PRECISIONS[self.precision]
+        ok = self._spec.width == 256 and samples_per_image % 128 == 0 and (not self._spec.has_input_linear or self._spec.in_dim % 32 == 0)
+        return _lib.PRECISION_TC16 if ok else _lib.PRECISION_FP32
 
     def _modulation(self, styles):
         layers = list(self.pts_linears) + [self.views_linears]
@@ -177,7 +185,7 @@ class _FieldNetwork(nn.Module):
         spec = self._spec
         gamma, beta = self._modulation(styles)
         meta = dict(spi=int(samples_per_image), spr=int(samples_per_ray), want_rgb=bool(want_rgb), want_feat=bool(want_feat),
-                    want_dsdf=bool(want_dsdf), precision=_PRECISIONS[self.precision])
+                    want_dsdf=bool(want_dsdf), precision=self._pick_precision(int(samples_per_image)))
         sdf, rgb, feat, dsdf = _field.apply(spec, meta, x_in, view_feat, gamma, beta, *_pack_weights(spec, self))
         return sdf, (rgb if rgb.numel() else None), (feat if feat.numel() else None), (dsdf if dsdf.numel() else None)
 
