@@ -67,7 +67,8 @@ int sdfg_sample_rays(const float* c2w, const float* focal, const float* near, co
  *      affine map of GridEncoder.forward gridencoder/grid.py:149.
  *   inputs [N,D] f32; if bound > 0 the kernel first maps x -> (x + bound) / (2*bound) (grid.py:149), else x is in [0,1]
  *   embeddings [offsets[L], C] f32; offsets [L+1] i32 (device)
- *   outputs f32, layout SDFG_LAYOUT_*;  dy_dx NULL or [N, L, D, C]
+ *   outputs f32, layout SDFG_LAYOUT_*;  dy_dx NULL or [L, D, C, N] (component-major, so that a warp of samples writes and reads
+ *   coalesced lines; the reference keeps [N, L*D*C], grid.py:50, and pays 32 partial sectors per store)
  *   S = log2(per_level_scale) as float, H = base resolution, gridtype 0 hash / 1 tiled, interp 0 linear / 1 smoothstep
  *   D in {2,3}; C in {1,2,4,8}; L <= 32.
  */

@@ -217,6 +217,8 @@ __global__ void __launch_bounds__(256) grid_forward_kernel(const float* __restri
     if (n >= N) return;
     float u[D];
     const bool inside = load_unit<D>(inputs, n, bound, u);
+    const bool pair_store = C == 2 && out_layout == SDFG_LAYOUT_NLC && (L & 1) == 0;   // two levels = one aligned float4
+    float pend[C];
 #pragma unroll 2
     for (uint32_t level = 0; level < L; level++) {
         float out[C], dd[D * C];
@@ -228,12 +230,21 @@ __global__ void __launch_bounds__(256) grid_forward_kernel(const float* __restri
 #pragma unroll
             for (uint32_t i = 0; i < D * C; i++) dd[i] = 0.f;
         }
-        float* o = out_layout == SDFG_LAYOUT_NLC ? outputs + (n * L + level) * C : outputs + ((size_t)level * N + n) * C;
-        store_feat<C>(o, out);
-        if constexpr (DYDX) {
-            float* q = dy_dx + (n * L + level) * (D * C);
+        if (pair_store) {
+            if (level & 1) *reinterpret_cast<float4*>(outputs + (n * L + level - 1) * C) = make_float4(pend[0], pend[C - 1], out[0], out[C - 1]);
+            else {
 #pragma unroll
-            for (uint32_t i = 0; i < D * C; i++) q[i] = dd[i];
+                for (uint32_t c = 0; c < C; c++) pend[c] = out[c];
+            }
+        } else {
+            float* o = out_layout == SDFG_LAYOUT_NLC ? outputs + (n * L + level) * C : outputs + ((size_t)level * N + n) * C;
+            store_feat<C>(o, out);
+        }
+        if constexpr (DYDX) {
+            // component-major [L*D*C, N]: a warp writes 32 consecutive floats per component (fully coalesced)
+            float* q = dy_dx + (size_t)level * (D * C) * N + n;
+#pragma unroll
+            for (uint32_t i = 0; i < D * C; i++) q[(size_t)i * N] = dd[i];
         }
     }
 }
@@ -252,15 +263,26 @@ __global__ void __launch_bounds__(256) grid_backward_kernel(const float* __restr
     __syncthreads();
     const LevelInfo li = li_s;
     const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+    const uint32_t lane = threadIdx.x & 31;
     float u[D];
-    if (!load_unit<D>(inputs, n, bound, u)) return;
-    const float* gp = grad_layout == SDFG_LAYOUT_NLC ? grad + (n * L + level) * C : grad + ((size_t)level * N + n) * C;
-    const Feat<C> g = load_feat<C>(gp);
+#pragma unroll
+    for (uint32_t d = 0; d < D; d++) u[d] = 0.f;
+    const bool active = n < N && load_unit<D>(inputs, n, bound, u);
+    Feat<C> g;
+#pragma unroll
+    for (uint32_t c = 0; c < C; c++) g.v[c] = 0.f;
+    if (active) {
+        const float* gp = grad_layout == SDFG_LAYOUT_NLC ? grad + (n * L + level) * C : grad + ((size_t)level * N + n) * C;
+        g = load_feat<C>(gp);
+    }
     float f[D], fd[D];
     uint32_t cell[D];
     locate<D>(u, li, align_corners, interp, f, fd, cell);
     float* __restrict__ gt = grad_table + (size_t)li.offset * C;
+    // Coarse levels: consecutive samples of a ray share cells, so a warp would hammer a handful of addresses (the L2 atomic
+    // unit serialises per address).  Runs of adjacent lanes with the same row are summed with a segmented shuffle reduction and
+    // only the run head issues the reduction.  Fine levels (about one sample per cell) scatter directly.
+    const bool aggregate = li.scale <= 1024.f;
 #pragma unroll
     for (uint32_t idx = 0; idx < (1u << D); idx++) {
         float w = 1.f;
@@ -274,7 +296,25 @@ __global__ void __launch_bounds__(256) grid_backward_kernel(const float* __restr
         float v[C];
 #pragma unroll
         for (uint32_t c = 0; c < C; c++) v[c] = w * g.v[c];
-        red_feat<C>(gt + (size_t)corner_row<D>(li, gl) * C, v);
+        const uint32_t row = active ? corner_row<D>(li, gl) : 0xFFFFFFFFu;
+        if (aggregate) {
+            const uint32_t prev = __shfl_up_sync(0xffffffffu, row, 1);
+            const bool head = lane == 0 || row != prev;
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+            const uint32_t above = heads & ~((2u << lane) - 1u);
+            const uint32_t end = above ? (uint32_t)__ffs(above) - 1u : 32u;
+#pragma unroll
+            for (uint32_t o = 1; o < 32; o <<= 1) {
+#pragma unroll
+                for (uint32_t c = 0; c < C; c++) {
+                    const float t = __shfl_down_sync(0xffffffffu, v[c], o);
+                    if (lane + o < end) v[c] += t;
+                }
+            }
+            if (head && active) red_feat<C>(gt + (size_t)row * C, v);
+        } else if (active) {
+            red_feat<C>(gt + (size_t)row * C, v);
+        }
     }
 }
 
@@ -291,11 +331,11 @@ __global__ void __launch_bounds__(256) grid_input_backward_kernel(const float* _
     for (uint32_t l = 0; l < L; l++) {
         const float* gp = grad_layout == SDFG_LAYOUT_NLC ? grad + (n * L + l) * C : grad + ((size_t)l * N + n) * C;
         const Feat<C> g = load_feat<C>(gp);
-        const float* q = dy_dx + (n * L + l) * (D * C);
+        const float* q = dy_dx + (size_t)l * (D * C) * N + n;
 #pragma unroll
         for (uint32_t d = 0; d < D; d++)
 #pragma unroll
-            for (uint32_t c = 0; c < C; c++) acc[d] = fmaf(g.v[c], __ldg(q + d * C + c), acc[d]);
+            for (uint32_t c = 0; c < C; c++) acc[d] = fmaf(g.v[c], ldg_stream1(q + (size_t)(d * C + c) * N), acc[d]);
     }
     const float k = bound > 0.f ? 1.f / (2.f * bound) : 1.f;
 #pragma unroll

@@ -76,7 +76,7 @@ def grid_encode_forward(inputs, embeddings, offsets, S, H, bound=0.0, calc_dy_dx
     if outputs is None:
         outputs = torch.empty((N, L * C) if layout == _lib.LAYOUT_NLC else (L, N, C), device=inputs.device)
     if calc_dy_dx and dy_dx is None:
-        dy_dx = torch.empty(N, L * D * C, device=inputs.device)
+        dy_dx = torch.empty(L * D * C, N, device=inputs.device)      # component-major (include/sdfg.h)
     with torch.cuda.device(inputs.device):
         _lib.check(lib.sdfg_grid_encode_forward(_ptr(inputs), _ptr(embeddings), _ptr(offsets), _ptr(_chk(outputs, "outputs")), N, D, C, L,
                                                 float(S), int(H), float(bound), _ptr(_chk(dy_dx, "dy_dx")), int(gridtype), int(bool(align_corners)),
