@@ -9,11 +9,11 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 dev = "cuda"
 torch.manual_seed(0)
 mo, ro = sg.default_options("ngp", renderer_res=64, n_samples=24, perturb=0.)
-g = sg.Generator(mo, ro, full_pipeline=False).to(dev).eval()
+g = sg.Generator(mo, ro, full_pipeline=False, ema=True).to(dev).eval()
 cam, focal, near, far, _ = sg.generate_camera_params(64, dev, batch=B)
 z = torch.randn(B, 256, device=dev)
 N = B * 64 * 64 * 24
-for prec in ("tc16", "fp32"):
+for prec in ([os.environ["SDFG_ONLY"]] if os.environ.get("SDFG_ONLY") else ("tc16", "fp32")):
     g.renderer.network.precision = prec
     with torch.no_grad():
         for _ in range(3):

@@ -15,8 +15,11 @@
 //                               gradient multiplies them with bf16 gradients
 // Algorithmic HBM bytes per sample and layer: 2*K in + 2*W out (fp16) -- 1 KB for a 256x256 layer, against 2 * 131072 flop.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "field.cuh"
+#include "tc_chain.cuh"
 #include "tc_layer.cuh"
 #include "tc_wgrad.cuh"
 
@@ -80,7 +83,6 @@ struct TcLayout {
     uint64_t N;
     uint64_t off_w[SDFG_MAX_FILM + 1];           // fp16 weights: [0] = input_linear, [1 + l] = FiLM layer l
     uint64_t off_x0, off_a[SDFG_MAX_FILM + 1], off_hv, total;
-    uint64_t off_x0b, off_ab[SDFG_MAX_FILM + 1];  // bf16 copies of X0 / A_l for the weight-gradient contraction (save only)
     int save;
 };
 
@@ -107,11 +109,6 @@ static TcLayout tc_layout(const sdfg_field_params* p, uint64_t N, int save) {
         L.off_a[l] = take(N * L.W * 2);
     }
     L.off_hv = take(save ? N * L.W * 2 : 0);
-    L.off_x0b = take(save ? N * L.Kp_in * 2 : 0);
-    for (uint32_t l = 0; l < L.n_layers; l++) {
-        if (l == 0 && !p->has_input_linear) { L.off_ab[0] = L.off_x0b; continue; }
-        L.off_ab[l] = take(save ? N * (l == L.n_film ? L.Kp_v : L.W) * 2 : 0);
-    }
     L.total = off;
     return L;
 }
@@ -128,6 +125,119 @@ static int check_tc(const sdfg_field_params* p, uint64_t N) {
     return SDFG_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused forward: every layer in one persistent kernel (tc_chain.cuh)
+
+static bool chain_enabled() {
+    static const bool on = []() { const char* e = getenv("SDFG_TC_CHAIN"); return !(e && e[0] == '0'); }();
+    return on;
+}
+static bool chain_eligible(const sdfg_field_params* p, bool want_views) {
+    if (p->width != 256 || p->in_dim > 32 || p->n_film < 1) return false;
+    if (want_views && p->view_dim > 16) return false;
+    const uint32_t n_main = p->n_film - (p->has_input_linear ? 0u : 1u) + (want_views ? 1u : 0u);
+    return n_main <= tc::CH_MAX_MAPS;
+}
+
+static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, const float* x_in, const float* view_feat, uint64_t N,
+                               float* out_sdf, float* out_rgb, float* out_feat, uint8_t* ws, int save, cudaStream_t st) {
+    const bool want_views = out_rgb || out_feat;
+    const uint32_t W = L.W, nf = L.n_film;
+    auto Wb = [&](uint32_t i) { return (h16*)(ws + L.off_w[i]); };
+    auto A = [&](uint32_t l) { return (h16*)(ws + L.off_a[l]); };
+    SDFG_REQUIRE(!want_views || view_feat, SDFG_ERR_INVALID, "field_forward: view_feat is required for the rgb / feature outputs");
+    SDFG_REQUIRE(!out_rgb || (p->rgb_w && p->rgb_b), SDFG_ERR_INVALID, "field_forward: rgb head missing");
+
+    tc::ChainMaps maps;
+    tc::ChainParams P = {};
+    P.M_total = (uint32_t)N; P.rows_per_image = p->samples_per_image; P.rows_per_ray = p->samples_per_ray;
+    P.in_dim = p->in_dim; P.view_dim = p->view_dim;
+    P.x_nk = ceil_div<uint32_t>(p->in_dim, 16);
+    P.v_nk = want_views ? ceil_div<uint32_t>(p->view_dim, 16) : 0;   // the view part is loaded only when a layer consumes it
+    P.x_in = x_in; P.view_feat = view_feat;
+    P.w_x = p->has_input_linear ? p->input_w : p->film_w[0]; P.ld_wx = p->in_dim;
+    P.w_v = p->film_w[nf] ? p->film_w[nf] + W : nullptr; P.ld_wv = W + p->view_dim;
+    P.gamma = p->gamma; P.beta = p->beta; P.gstride = (int64_t)(nf + 1) * W;
+    P.kp_x = L.Kp_in; P.kp_v = L.Kp_v - W;
+    if (save) {
+        P.x16 = (h16*)(ws + L.off_x0);
+        if (P.v_nk) { P.v16 = A(nf) + W; P.ld_v16 = L.Kp_v; }
+    }
+    uint32_t nl = 0, nm = 0;
+    auto add_main_map = [&](uint32_t wi, uint32_t ldw) -> int {
+        return make_tensor_map_16(&maps.m[nm], Wb(wi), W, W, ldw, 256, 64, tc::FMT_F16);
+    };
+    // layer 0: input_linear (ngp) or the first FiLM layer on the raw x part (siren)
+    {
+        tc::ChainLayer& Y = P.layer[nl++];
+        Y.small_k0 = 0; Y.small_nk = P.x_nk;
+        if (p->has_input_linear) {
+            Y.act = 0; Y.bias = p->input_b;
+            if (save) { Y.out16 = A(0); Y.ld_out = W; }
+        } else {
+            Y.act = 1; Y.film = 0; Y.bias = p->film_b[0];
+        }
+    }
+    const uint32_t first_trunk = p->has_input_linear ? 0u : 1u;
+    auto trunk_outputs = [&](tc::ChainLayer& Y, uint32_t l) {       // output of trunk layer l = A(l+1)
+        const bool last = l + 1 == nf;
+        if (save) { Y.out16 = A(l + 1); Y.ld_out = last ? L.Kp_v : W; }
+        if (last && out_sdf) { Y.nh = 1; Y.head_w = p->sigma_w; Y.head_b = p->sigma_b; Y.out_head = out_sdf; }
+    };
+    if (!p->has_input_linear) trunk_outputs(P.layer[0], 0);
+    for (uint32_t l = first_trunk; l < nf; l++) {
+        tc::ChainLayer& Y = P.layer[nl++];
+        Y.has_main = 1; Y.tm = nm; Y.act = 1; Y.film = l; Y.bias = p->film_b[l];
+        if (int e = add_main_map(1 + l, W)) return e;
+        nm++;
+        trunk_outputs(Y, l);
+    }
+    if (want_views) {
+        tc::ChainLayer& Y = P.layer[nl++];
+        Y.has_main = 1; Y.tm = nm; Y.act = 1; Y.film = nf; Y.bias = p->film_b[nf];
+        Y.small_k0 = P.x_nk; Y.small_nk = P.v_nk;
+        if (int e = add_main_map(1 + nf, L.Kp_v)) return e;
+        nm++;
+        if (save) { Y.out16 = (h16*)(ws + L.off_hv); Y.ld_out = W; }
+        if (out_feat) { Y.out_f32 = out_feat; Y.ld_out_f32 = W; }
+        if (out_rgb) { Y.nh = 3; Y.head_w = p->rgb_w; Y.head_b = p->rgb_b; Y.out_head = out_rgb; }
+    }
+    P.n_layers = nl;
+    for (uint32_t i = 0; i + 1 < nl; i++) P.layer[i].to_act = 1;
+    P.n_tiles = (uint32_t)ceil_div<uint64_t>(N, tc::CH_TILE_M);
+    const uint32_t ctas = std::min<uint32_t>((uint32_t)sm_count(), P.n_tiles);
+    P.tiles_per_cta = ceil_div<uint32_t>(P.n_tiles, ctas);
+    const uint32_t grid = ceil_div<uint32_t>(P.n_tiles, P.tiles_per_cta);
+    const uint32_t smem = tc::chain_smem_bytes();
+    static thread_local bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(tc::tc_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return set_error(SDFG_ERR_CUDA, "tc_chain_fwd_kernel: cannot opt in to %u bytes of shared memory", smem);
+        configured = true;
+    }
+    static const bool dbg_on = getenv("SDFG_CHAIN_DBG") != nullptr;     // debugging aid: event log of CTA 0 to stderr
+    if (dbg_on) {
+        static unsigned long long* dbuf = nullptr;
+        if (!dbuf) cudaMalloc(&dbuf, 4 * 2048 * 8);
+        cudaMemsetAsync(dbuf, 0, 4 * 2048 * 8, st);
+        P.dbg = dbuf;
+        tc::tc_chain_fwd_kernel<<<grid, tc::CH_THREADS, smem, st>>>(maps, P);
+        cudaStreamSynchronize(st);
+        static unsigned long long host[4 * 2048];
+        cudaMemcpy(host, dbuf, sizeof(host), cudaMemcpyDeviceToHost);
+        static int dumps = 0;
+        if (dumps++ == 2)
+            for (int role = 0; role < 4; role++)
+                for (int k = 0; k < 1024 && host[role * 2048 + 2 * k + 1]; k++)
+                    fprintf(stderr, "CHDBG %d %llu %llu\n", role, host[role * 2048 + 2 * k], host[role * 2048 + 2 * k + 1]);
+        return check_launch("tc_chain_fwd_kernel<gemm>");
+    }
+    ProfScope prof("tc_chain_fwd_kernel<gemm>", st);
+    tc::tc_chain_fwd_kernel<<<grid, tc::CH_THREADS, smem, st>>>(maps, P);
+    return check_launch("tc_chain_fwd_kernel<gemm>");
+}
+
 int field_forward_tc(const sdfg_field_params* p, const float* x_in, const float* view_feat, uint64_t N, float* out_sdf, float* out_rgb,
                      float* out_feat, void* workspace, int save, cudaStream_t st) {
     if (int e = check_tc(p, N)) return e;
@@ -135,7 +245,6 @@ int field_forward_tc(const sdfg_field_params* p, const float* x_in, const float*
     uint8_t* ws = (uint8_t*)workspace;
     auto Wb = [&](uint32_t i) { return (h16*)(ws + L.off_w[i]); };
     auto A = [&](uint32_t l) { return (h16*)(ws + L.off_a[l]); };
-    auto Ab = [&](uint32_t l) { return (h16*)(ws + L.off_ab[l]); };
     const uint32_t W = L.W, nf = L.n_film;
     const int64_t gstride = (int64_t)(nf + 1) * W;
     const bool want_views = out_rgb || out_feat;
@@ -147,17 +256,16 @@ int field_forward_tc(const sdfg_field_params* p, const float* x_in, const float*
         const uint32_t K = l == nf ? W + p->view_dim : ((l == 0 && !p->has_input_linear) ? p->in_dim : W);
         if (int e = cast_pad(p->film_w[l], K, 1, Wb(1 + l), round_up(K, 8), W, K, round_up(K, 8), st)) return e;
     }
+    if (chain_enabled() && chain_eligible(p, want_views))
+        return field_forward_chain(p, L, x_in, view_feat, N, out_sdf, out_rgb, out_feat, ws, save, st);
     // 2. encoder features -> fp16
     h16* X0 = (h16*)(ws + L.off_x0);
     if (int e = cast_pad(x_in, p->in_dim, 1, X0, L.Kp_in, N, p->in_dim, L.Kp_in, st)) return e;
-    if (save)
-        if (int e = cast_pad(x_in, p->in_dim, 1, (h16*)(ws + L.off_x0b), L.Kp_in, N, p->in_dim, L.Kp_in, st, tc::FMT_BF16)) return e;
     // 3. input_linear
     if (p->has_input_linear) {
         LayerParams P = {};
         P.M_total = (uint32_t)N; P.N_out = W; P.rows_per_image = p->samples_per_image; P.act = 0; P.bias = p->input_b;
         P.out16 = A(0); P.ld_out = W;
-        if (save) { P.out16b = Ab(0); P.ld_out_b = W; }
         if (int e = launch_layer<tc::MODE_F>(X0, N, L.Kp_in, L.Kp_in, Wb(0), W, L.Kp_in, P, st, "tc_layer_kernel<F,gemm,linear>")) return e;
     }
     // 4. trunk
@@ -168,12 +276,9 @@ int field_forward_tc(const sdfg_field_params* p, const float* x_in, const float*
         P.gamma = p->gamma + (size_t)l * W; P.beta = p->beta + (size_t)l * W; P.gstride = gstride;
         const bool last = l + 1 == nf;
         if (!last || want_views || save) { P.out16 = A(l + 1); P.ld_out = last ? L.Kp_v : W; }
-        if (save) { P.out16b = Ab(l + 1); P.ld_out_b = last ? L.Kp_v : W; }
         if (last && out_sdf) { P.nh = 1; P.head_w = p->sigma_w; P.head_b = p->sigma_b; P.out_head = out_sdf; }
         if (int e = launch_layer<tc::MODE_F>(A(l), N, K, K, Wb(1 + l), W, K, P, st, "tc_layer_kernel<F,gemm,film>")) return e;
     }
-    if (save && view_feat)
-        if (int e = cast_pad(view_feat, p->view_dim, p->samples_per_ray, Ab(nf) + W, L.Kp_v, N, p->view_dim, L.Kp_v - W, st, tc::FMT_BF16)) return e;
     if (!want_views) return SDFG_OK;
     SDFG_REQUIRE(view_feat, SDFG_ERR_INVALID, "field_forward: view_feat is required for the rgb / feature outputs");
     SDFG_REQUIRE(!out_rgb || (p->rgb_w && p->rgb_b), SDFG_ERR_INVALID, "field_forward: rgb head missing");
@@ -195,13 +300,13 @@ int field_forward_tc(const sdfg_field_params* p, const float* x_in, const float*
 // ---------------------------------------------------------------------------------------------------------------
 // backward helpers
 
-// WgT[b][k][j] = bf16(gamma[b, j] * W[j, k])  for k < Kuse  (gamma == NULL: plain transpose, one "image")
+// WgT[b][k][j] = fp16(gamma[b, j] * W[j, k])  for k < Kuse  (gamma == NULL: plain transpose, one "image")
 __global__ void __launch_bounds__(256) wgt_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ gamma, int64_t gstride,
                                                    h16* __restrict__ out, uint32_t Kuse, uint32_t B) {
     const uint32_t j = threadIdx.x;                 // 256 output neurons
     const uint32_t k = blockIdx.x, b = blockIdx.y;
     const float g = gamma ? __ldg(gamma + (int64_t)b * gstride + j) : 1.f;
-    out[((size_t)b * Kuse + k) * 256 + j] = __bfloat16_as_ushort(__float2bfloat16(g * __ldg(W + (int64_t)j * ldw + k)));
+    out[((size_t)b * Kuse + k) * 256 + j] = __half_as_ushort(__float2half_rn(g * __ldg(W + (int64_t)j * ldw + k)));
 }
 
 // finishing kernel of one layer's weight gradient: G [B, 256, ldg] -> dW, db, dgamma, dbeta   (block = neuron j, threads over k)
@@ -209,9 +314,10 @@ __global__ void __launch_bounds__(128) wgrad_finish_kernel(const float* __restri
                                                             const float* __restrict__ W, int64_t ldw, uint32_t Kx, const float* __restrict__ bias,
                                                             const float* __restrict__ gamma, int64_t gstride, int film,
                                                             float* __restrict__ dW, float* __restrict__ db, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta) {
+                                                            float* __restrict__ dbeta, const float* __restrict__ gscale) {
     __shared__ float red[4];
     const uint32_t j = blockIdx.x;
+    const float inv_s = gscale ? __ldg(gscale + 1) : 1.f;      // G carries the loss scale of the fp16 gradients
     float dbj = 0.f;
     for (uint32_t k = threadIdx.x; k < Kx; k += blockDim.x) {
         float acc = 0.f;
@@ -219,10 +325,10 @@ __global__ void __launch_bounds__(128) wgrad_finish_kernel(const float* __restri
             const float g = film ? __ldg(gamma + (int64_t)b * gstride + j) : 1.f;
             acc = fmaf(g, __ldg(G + ((size_t)b * 256 + j) * ldg + k), acc);
         }
-        dW[(int64_t)j * ldw + k] += acc;
+        dW[(int64_t)j * ldw + k] += inv_s * acc;
     }
     for (uint32_t b = 0; b < B; b++) {
-        const float ones = __ldg(G + ((size_t)b * 256 + j) * ldg + ones_col);
+        const float ones = inv_s * __ldg(G + ((size_t)b * 256 + j) * ldg + ones_col);
         if (film) {
             float part = 0.f;
             for (uint32_t k = threadIdx.x; k < Kx; k += blockDim.x) part = fmaf(__ldg(W + (int64_t)j * ldw + k), __ldg(G + ((size_t)b * 256 + j) * ldg + k), part);
@@ -232,7 +338,7 @@ __global__ void __launch_bounds__(128) wgrad_finish_kernel(const float* __restri
             __syncthreads();
             if (threadIdx.x == 0) {
                 const float tot = red[0] + red[1] + red[2] + red[3];
-                dgamma[(int64_t)b * gstride + j] += fmaf(__ldg(bias + j), ones, tot);
+                dgamma[(int64_t)b * gstride + j] += fmaf(__ldg(bias + j), ones, inv_s * tot);
                 dbeta[(int64_t)b * gstride + j] += ones;
             }
             dbj = fmaf(__ldg(gamma + (int64_t)b * gstride + j), ones, dbj);
@@ -268,6 +374,41 @@ __global__ void __launch_bounds__(256) head_wgrad16_kernel(const float* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// loss scale of the fp16 gradients: s = 2^floor(log2(64 / max|output gradient|)), computed on the device (no host sync)
+
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ a, uint64_t na, const float* __restrict__ b, uint64_t nb,
+                                                      const float* __restrict__ c, uint64_t nc, uint32_t* __restrict__ out_bits) {
+    float m = 0.f;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, t0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a) for (uint64_t i = t0; i < na; i += stride) m = fmaxf(m, fabsf(__ldg(a + i)));
+    if (b) for (uint64_t i = t0; i < nb; i += stride) m = fmaxf(m, fabsf(__ldg(b + i)));
+    if (c) for (uint64_t i = t0 * 4; i + 3 < nc; i += stride * 4) {
+        const float4 v = ldg_stream4(reinterpret_cast<const float4*>(c + i));
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));     // non-negative floats order like their bit patterns
+}
+__global__ void loss_scale_kernel(const uint32_t* __restrict__ bits, float* __restrict__ gscale) {
+    const float m = __uint_as_float(*bits);
+    float e = 0.f;
+    if (m > 0.f && m < 3.0e38f) e = fminf(fmaxf(floorf(log2f(64.f / m)), -100.f), 100.f);
+    gscale[0] = exp2f(e);
+    gscale[1] = exp2f(-e);
+}
+static int compute_loss_scale(const float* a, uint64_t na, const float* b, uint64_t nb, const float* c, uint64_t nc, uint32_t* bits,
+                              float* gscale, cudaStream_t st) {
+    if (cudaMemsetAsync(bits, 0, 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");
+    const uint64_t work = std::max<uint64_t>(a ? na : 0, std::max<uint64_t>(b ? nb : 0, c ? nc / 4 : 0));
+    const unsigned grid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(ceil_div<uint64_t>(work, 256 * 8), 1), 148 * 8);
+    absmax_kernel<<<grid, 256, 0, st>>>(a, na, b, nb, c, nc, bits);
+    if (int e = check_launch("absmax_kernel")) return e;
+    loss_scale_kernel<<<1, 1, 0, st>>>(bits, gscale);
+    return check_launch("loss_scale_kernel");
+}
+
 static int launch_wgrad(const h16* dz, const h16* x, uint32_t Kx, int64_t ldx, uint64_t N, uint32_t rows_per_image, float* G, uint32_t* ldg_out,
                         uint32_t* ones_out, cudaStream_t st, uint32_t x_fmt = tc::FMT_F16) {
     tc::WgradParams P = {};
@@ -287,7 +428,7 @@ static int launch_wgrad(const h16* dz, const h16* x, uint32_t Kx, int64_t ldx, u
     P.stages_per_pair = ceil_div<uint32_t>(P.n_stage_total, pairs);
     const uint32_t grid = 2 * ceil_div<uint32_t>(P.n_stage_total, P.stages_per_pair);
     CUtensorMap tmDZ, tmX;
-    if (int e = make_tensor_map_16(&tmDZ, dz, N, 256, 256, tc::WG_ROWS, 64, tc::FMT_BF16)) return e;
+    if (int e = make_tensor_map_16(&tmDZ, dz, N, 256, 256, tc::WG_ROWS, 64, x_fmt)) return e;
     if (int e = make_tensor_map_16(&tmX, x, N, (uint64_t)ldx, (uint64_t)ldx, tc::WG_ROWS, 64, x_fmt)) return e;
     const uint32_t smem = tc::wgrad_smem_bytes(P.n_xbox);
     static thread_local uint32_t configured = 0;
@@ -301,8 +442,8 @@ static int launch_wgrad(const h16* dz, const h16* x, uint32_t Kx, int64_t ldx, u
     return check_launch("tc_wgrad_kernel<gemm>");
 }
 
-// scratch: DZ [N,256] bf16 | DH [N,256] bf16 | WgT [B, 256, 256] bf16 | G [B, 256, 336] fp32
-struct TcScratch { uint64_t off_dz, off_dh, off_wgt, off_g, total; };
+// scratch: DZ [N,256] fp16 | DH [N,256] fp16 | WgT [B, 256, 256] fp16 | G [B, 256, 336] fp32 | loss scale {bits, s, 1/s}
+struct TcScratch { uint64_t off_dz, off_dh, off_wgt, off_g, off_scale, total; };
 static TcScratch tc_scratch(const sdfg_field_params* p, uint64_t N) {
     TcScratch s = {};
     const uint64_t B = ceil_div<uint64_t>(N, p->samples_per_image);
@@ -312,6 +453,7 @@ static TcScratch tc_scratch(const sdfg_field_params* p, uint64_t N) {
     s.off_dh = take(N * 256 * 2);
     s.off_wgt = take(B * 256 * 256 * 2);
     s.off_g = take(B * 256 * 336 * 4);
+    s.off_scale = take(256);
     s.total = off;
     return s;
 }
@@ -331,11 +473,12 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
     uint8_t* sc = (uint8_t*)scratch;
     auto Wb = [&](uint32_t i) { return (const h16*)(ws + L.off_w[i]); };
     auto A = [&](uint32_t l) { return (const h16*)(ws + L.off_a[l]); };
-    auto Ab = [&](uint32_t l) { return (const h16*)(ws + L.off_ab[l]); };
     h16* DZ = (h16*)(sc + SC.off_dz);
     h16* DH = (h16*)(sc + SC.off_dh);
     h16* WGT = (h16*)(sc + SC.off_wgt);
     float* G = (float*)(sc + SC.off_g);
+    float* gscale = (float*)(sc + SC.off_scale) + 2;      // {s, 1/s}; [0] of the slot holds the absmax bits
+    if (int e = compute_loss_scale(d_sdf, N, d_rgb, N * 3, d_feat, N * 256, (uint32_t*)(sc + SC.off_scale), gscale, st)) return e;
     const uint32_t W = L.W, nf = L.n_film;
     const uint32_t B = (uint32_t)ceil_div<uint64_t>(N, p->samples_per_image);
     const int64_t gstride = (int64_t)(nf + 1) * W;
@@ -349,8 +492,8 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         LayerParams P = {};
         P.M_total = (uint32_t)N; P.N_out = W; P.rows_per_image = spi; P.bias = p->film_b[l];
         P.gamma = p->gamma + (size_t)l * W; P.beta = p->beta + (size_t)l * W; P.gstride = gstride;
-        P.ab_fmt = tc::FMT_F16; P.out_fmt = tc::FMT_BF16; P.out16 = DZ; P.ld_out = W;
-        P.dh_bf16 = reinterpret_cast<const __nv_bfloat16*>(dh16); P.ld_dh = W; P.dh_f32 = dh32; P.ld_dh_f32 = W;
+        P.ab_fmt = tc::FMT_F16; P.out_fmt = tc::FMT_F16; P.out16 = DZ; P.ld_out = W; P.gscale = gscale;
+        P.dh16 = dh16; P.ld_dh = W; P.dh_f32 = dh32; P.ld_dh_f32 = W;
         P.rank = rank; P.rank_s = rs; P.rank_v = rv;
         return launch_layer<tc::MODE_R>(A(l), N, layer_K(l), layer_K(l), Wb(1 + l), W, layer_K(l), P, st, "tc_layer_kernel<R,gemm>");
     };
@@ -359,9 +502,9 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         if (!g || !g->film_w[l]) return SDFG_OK;
         if (cudaMemsetAsync(G, 0, (size_t)B * 256 * 336 * 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");
         uint32_t ldg, ones;
-        if (int e = launch_wgrad(DZ, Ab(l), layer_Kx(l), layer_K(l), N, spi, G, &ldg, &ones, st, tc::FMT_BF16)) return e;
+        if (int e = launch_wgrad(DZ, A(l), layer_Kx(l), layer_K(l), N, spi, G, &ldg, &ones, st, tc::FMT_F16)) return e;
         wgrad_finish_kernel<<<256, 128, 0, st>>>(G, ldg, ones, B, p->film_w[l], layer_Kx(l), layer_Kx(l), p->film_b[l], p->gamma + (size_t)l * W,
-                                                 gstride, 1, g->film_w[l], g->film_b[l], g->gamma + (size_t)l * W, g->beta + (size_t)l * W);
+                                                 gstride, 1, g->film_w[l], g->film_b[l], g->gamma + (size_t)l * W, g->beta + (size_t)l * W, gscale);
         return check_launch("wgrad_finish_kernel");
     };
     // D: DH = DZ * (gamma o W_l)[:, :Kout]  (+ rank-1)
@@ -370,7 +513,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         if (int e = check_launch("wgt_kernel")) return e;
         LayerParams P = {};
         P.M_total = (uint32_t)N; P.N_out = Kout; P.rows_per_image = spi; P.b_rows_per_image = Kout;
-        P.ab_fmt = tc::FMT_BF16; P.out_fmt = tc::FMT_BF16; P.out16 = DH; P.ld_out = W;
+        P.ab_fmt = tc::FMT_F16; P.out_fmt = tc::FMT_F16; P.out16 = DH; P.ld_out = W; P.gscale = gscale;
         P.rank = rs ? 1 : 0; P.rank_s = rs; P.rank_v = rv;
         return launch_layer<tc::MODE_D>(DZ, N, W, W, WGT, (uint64_t)B * Kout, W, P, st, "tc_layer_kernel<D,gemm>");
     };
@@ -407,9 +550,9 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         if (g && g->input_w) {
             if (cudaMemsetAsync(G, 0, (size_t)B * 256 * 336 * 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");
             uint32_t ldg, ones;
-            if (int e = launch_wgrad(DH, (const h16*)(ws + L.off_x0b), p->in_dim, L.Kp_in, N, spi, G, &ldg, &ones, st, tc::FMT_BF16)) return e;
+            if (int e = launch_wgrad(DH, (const h16*)(ws + L.off_x0), p->in_dim, L.Kp_in, N, spi, G, &ldg, &ones, st, tc::FMT_F16)) return e;
             wgrad_finish_kernel<<<256, 128, 0, st>>>(G, ldg, ones, B, p->input_w, p->in_dim, p->in_dim, p->input_b, nullptr, 0, 0, g->input_w,
-                                                     g->input_b, nullptr, nullptr);
+                                                     g->input_b, nullptr, nullptr, gscale);
             if (int e = check_launch("wgrad_finish_kernel")) return e;
         }
         if (d_x_in) {
@@ -417,7 +560,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
             if (int e = check_launch("wgt_kernel")) return e;
             LayerParams P = {};
             P.M_total = (uint32_t)N; P.N_out = p->in_dim; P.rows_per_image = spi; P.b_rows_per_image = 0;
-            P.ab_fmt = tc::FMT_BF16; P.out_f32 = d_x_in; P.ld_out_f32 = p->in_dim;
+            P.ab_fmt = tc::FMT_F16; P.out_f32 = d_x_in; P.ld_out_f32 = p->in_dim; P.gscale = gscale;
             if (int e = launch_layer<tc::MODE_D>(DH, N, W, W, WGT, p->in_dim, W, P, st, "tc_layer_kernel<D,gemm,in>")) return e;
         }
     }
@@ -444,7 +587,7 @@ int tc_wgrad_probe(const float* dz, const float* x, float* G, uint32_t N, uint32
     const uint32_t Kp = round_up(Kx, 8);
     h16* dzb = (h16*)workspace;
     h16* xb = dzb + align256((uint64_t)N * 256 * 2) / 2;
-    if (int e = cast_pad(dz, 256, 1, dzb, 256, N, 256, 256, st, tc::FMT_BF16)) return e;
+    if (int e = cast_pad(dz, 256, 1, dzb, 256, N, 256, 256, st, x_fmt)) return e;
     if (int e = cast_pad(x, Kx, 1, xb, Kp, N, Kx, Kp, st, x_fmt)) return e;
     return launch_wgrad(dzb, xb, Kx, Kp, N, rows_per_image, G, ldg, ones, st, x_fmt);
 }

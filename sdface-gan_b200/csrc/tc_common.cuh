@@ -166,6 +166,16 @@ __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// fp16 with saturation to +-65504 (gradients: an overflow must not become inf)
+__device__ __forceinline__ uint32_t pack_f16_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_f16(uint32_t v) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&v);
+    return __half22float2(h);
+}
 __device__ __forceinline__ uint32_t pack16(float lo, float hi, uint32_t fmt) { return fmt == FMT_BF16 ? pack_bf16(lo, hi) : pack_f16(lo, hi); }
 
 }  // namespace tc

@@ -3,6 +3,8 @@
 // with the layer's elementwise work fused into the TMEM -> register epilogue.  Three epilogues share the pipeline:
 //   MODE_F  forward:    h = sin(gamma*(acc + bias) + beta) (or acc + bias), optional sdf / rgb head dot products
 //   MODE_R  backward 1: recompute z from the saved input, dz = dh * cos(z)           (dh from memory and / or a rank-r term)
+//           gradients are fp16 carrying a power-of-two loss scale s (P.gscale): fp32 sources are multiplied by s on the way
+//           in, fp32 results by 1/s on the way out, 16-bit stores saturate
 //   MODE_D  backward 2: dh_in = dz * (gamma o W)  (+ rank-1 term d_sdf * w_sigma)    B = per-image (gamma o W)^T
 //
 // Structure (one CTA per SM, 320 threads):
@@ -48,7 +50,8 @@ struct LayerParams {
     const float* head_w;
     const float* head_b;
     float* out_head;
-    const __nv_bfloat16* dh_bf16;   // MODE_R: upstream gradient sources (each optional)
+    const float* gscale;            // MODE_R / MODE_D: device pointer to {s, 1/s}: the power-of-two loss scale every fp16 gradient carries (NULL = 1)
+    const uint16_t* dh16;           // MODE_R: upstream gradient sources (each optional); dh16 is fp16 and already carries the scale
     int64_t ld_dh;
     const float* dh_f32;
     int64_t ld_dh_f32;
@@ -197,8 +200,10 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint64_t row = (uint64_t)t * TILE_M + row_in_tile;
             const bool valid = row < P.M_total;
             float rs[3] = {0.f, 0.f, 0.f};
+            const float gs = (MODE != MODE_F && P.gscale) ? __ldg(P.gscale) : 1.f;
+            const float gs_inv = (MODE != MODE_F && P.gscale) ? __ldg(P.gscale + 1) : 1.f;
             if (MODE != MODE_F && valid)
-                for (int r = 0; r < P.rank; r++) rs[r] = __ldg(P.rank_s + row * P.rank + r);
+                for (int r = 0; r < P.rank; r++) rs[r] = gs * __ldg(P.rank_s + row * P.rank + r);
             float hacc[3] = {0.f, 0.f, 0.f};
 
             mbar_wait(&S.tmem_full[wg], acc_phase);
@@ -235,16 +240,17 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     float dh[32];
 #pragma unroll
                     for (int i = 0; i < 32; i++) dh[i] = 0.f;
-                    if (P.dh_bf16 && valid) {
-                        const uint4* src = reinterpret_cast<const uint4*>(P.dh_bf16 + row * P.ld_dh + c);
+                    if (P.dh16 && valid) {
+                        const uint4* src = reinterpret_cast<const uint4*>(P.dh16 + row * P.ld_dh + c);
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             const uint4 u = __ldg(src + j);
                             const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                             for (int k = 0; k < 4; k++) {
-                                dh[j * 8 + 2 * k] = __uint_as_float(w[k] << 16);
-                                dh[j * 8 + 2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+                                const float2 f = unpack_f16(w[k]);
+                                dh[j * 8 + 2 * k] = f.x;
+                                dh[j * 8 + 2 * k + 1] = f.y;
                             }
                         }
                     }
@@ -253,7 +259,8 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
                             const float4 u = ldg_stream4(src + j);
-                            dh[j * 4] += u.x; dh[j * 4 + 1] += u.y; dh[j * 4 + 2] += u.z; dh[j * 4 + 3] += u.w;
+                            dh[j * 4] = fmaf(gs, u.x, dh[j * 4]); dh[j * 4 + 1] = fmaf(gs, u.y, dh[j * 4 + 1]);
+                            dh[j * 4 + 2] = fmaf(gs, u.z, dh[j * 4 + 2]); dh[j * 4 + 3] = fmaf(gs, u.w, dh[j * 4 + 3]);
                         }
                     }
                     for (int r = 0; r < P.rank; r++) {
@@ -280,9 +287,14 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         uint4* dst = reinterpret_cast<uint4*>(P.out16 + row * P.ld_out + c);
                         const uint32_t f = P.out_fmt;
 #pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            dst[j] = make_uint4(pack16(v[j * 8], v[j * 8 + 1], f), pack16(v[j * 8 + 2], v[j * 8 + 3], f),
-                                                pack16(v[j * 8 + 4], v[j * 8 + 5], f), pack16(v[j * 8 + 6], v[j * 8 + 7], f));
+                        for (int j = 0; j < 4; j++) {
+                            if (MODE == MODE_F)
+                                dst[j] = make_uint4(pack16(v[j * 8], v[j * 8 + 1], f), pack16(v[j * 8 + 2], v[j * 8 + 3], f),
+                                                    pack16(v[j * 8 + 4], v[j * 8 + 5], f), pack16(v[j * 8 + 6], v[j * 8 + 7], f));
+                            else
+                                dst[j] = make_uint4(pack_f16_sat(v[j * 8], v[j * 8 + 1]), pack_f16_sat(v[j * 8 + 2], v[j * 8 + 3]),
+                                                    pack_f16_sat(v[j * 8 + 4], v[j * 8 + 5]), pack_f16_sat(v[j * 8 + 6], v[j * 8 + 7]));
+                        }
                     }
                     if (MODE == MODE_F && P.out16b) {
                         uint4* dst = reinterpret_cast<uint4*>(P.out16b + row * P.ld_out_b + c);
@@ -294,7 +306,8 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (P.out_f32) {
                         float4* dst = reinterpret_cast<float4*>(P.out_f32 + row * P.ld_out_f32 + c);
 #pragma unroll
-                        for (int j = 0; j < 8; j++) dst[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+                        for (int j = 0; j < 8; j++)
+                            dst[j] = make_float4(gs_inv * v[j * 4], gs_inv * v[j * 4 + 1], gs_inv * v[j * 4 + 2], gs_inv * v[j * 4 + 3]);
                     }
                 }
             }

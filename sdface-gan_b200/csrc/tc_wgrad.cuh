@@ -3,7 +3,7 @@
 //     G_b[j, ones] = sum_{n in image b} dz[n, j]                    (an extra all-ones B operand: the bias / beta gradient)
 // Both operands are read exactly as they sit in HBM ([samples, features] row-major): with the sample axis as the MMA's K
 // dimension they are MN-major, which tcgen05 consumes directly from the 128B-swizzled TMA boxes (no transposes anywhere).
-// dz is bf16 (gradient), x is fp16 (activation): the instruction descriptor carries the two formats separately.
+// dz (gradient, loss-scaled) and x (activation) are both fp16.
 //
 // Work split: the 256 output neurons do not fit one CTA's TMEM together with the ones column (2 x 272 > 512 columns), so CTAs
 // work in PAIRS on the same range of samples, CTA h of a pair owning neurons [128h, 128h+128) -- the partner's reads of x hit L2.
@@ -32,7 +32,7 @@ struct WgradParams {
     uint32_t n_extra;           // 0 or 64: second x block for Kx > 256
     uint32_t ones_col;          // n_main + n_extra: TMEM / G column of the ones accumulator
     uint32_t ldg;               // pitch of G rows (floats) >= ones_col + 16
-    uint32_t x_fmt;             // FMT_F16 / FMT_BF16 of x
+    uint32_t x_fmt;             // FMT_F16 / FMT_BF16 of x and dz (tcgen05.mma .kind::f16 rejects mixed 16-bit operand types)
     float* G;                   // [B, 256, ldg] fp32, pre-zeroed
 };
 
@@ -99,9 +99,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant_
     } else if (warp == 1) {
         // ===================================================== MMA issuer
         if (lane == 0 && s_begin < s_end) {
-            const uint32_t id_main = idesc_f16(128, P.n_main, FMT_BF16, P.x_fmt, 1, 1);
-            const uint32_t id_extra = idesc_f16(128, 64, FMT_BF16, P.x_fmt, 1, 1);
-            const uint32_t id_ones = idesc_f16(128, 16, FMT_BF16, P.x_fmt, 1, 0);
+            const uint32_t id_main = idesc_f16(128, P.n_main, P.x_fmt, P.x_fmt, 1, 1);
+            const uint32_t id_extra = idesc_f16(128, 64, P.x_fmt, P.x_fmt, 1, 1);
+            const uint32_t id_ones = idesc_f16(128, 16, P.x_fmt, P.x_fmt, 1, 0);
             const uint64_t d_ones = smem_desc_sw128(smem_u32(ones), 16, 1024);
             uint32_t stage = 0, phase = 0, flushes = 0;
             bool fresh = true;                                       // next MMA starts a new accumulation

@@ -86,7 +86,7 @@ class _field(Function):
         beta = beta.contiguous()
         wts = tuple(w.contiguous() for w in wts)
         weights = _unpack_weights(spec, wts)
-        need_bwd = any(ctx.needs_input_grad[2:]) or meta["want_dsdf"]
+        need_bwd = (meta.get("grad", True) and any(ctx.needs_input_grad[2:])) or meta["want_dsdf"]
         sdf, rgb, feat, ws = ops.field_forward(spec, x_in, view_feat, gamma, beta, weights, meta["spi"], meta["spr"],
                                                want_rgb=meta["want_rgb"], want_feat=meta["want_feat"],
                                                save_for_backward=need_bwd, precision=meta["precision"])
@@ -185,7 +185,8 @@ class _FieldNetwork(nn.Module):
         spec = self._spec
         gamma, beta = self._modulation(styles)
         meta = dict(spi=int(samples_per_image), spr=int(samples_per_ray), want_rgb=bool(want_rgb), want_feat=bool(want_feat),
-                    want_dsdf=bool(want_dsdf), precision=self._pick_precision(int(samples_per_image)))
+                    want_dsdf=bool(want_dsdf), precision=self._pick_precision(int(samples_per_image)),
+                    grad=torch.is_grad_enabled())   # Function.forward itself always runs with grad mode off
         sdf, rgb, feat, dsdf = _field.apply(spec, meta, x_in, view_feat, gamma, beta, *_pack_weights(spec, self))
         return sdf, (rgb if rgb.numel() else None), (feat if feat.numel() else None), (dsdf if dsdf.numel() else None)
 
