@@ -7,3 +7,5 @@ tail -15 gpurun_out/pytest_chain.log
 SDFG_ONLY=tc16 timeout 300 python scripts/bench_field.py 32 > gpurun_out/bench_chain_on.log 2>&1; tail -2 gpurun_out/bench_chain_on.log
 SDFG_TC_CHAIN=0 SDFG_ONLY=tc16 timeout 300 python scripts/bench_field.py 32 > gpurun_out/bench_chain_off.log 2>&1; tail -2 gpurun_out/bench_chain_off.log
 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.log 2>&1; tail -1 gpurun_out/bench_quick.log | cut -c1-1200
+SDFG_CHAIN_DBG=1 SDFG_ONLY=tc16 timeout 300 python scripts/bench_field.py 8 > gpurun_out/chain_dbg.log 2>&1
+grep -c CHDBG gpurun_out/chain_dbg.log

@@ -17,8 +17,10 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
 
 #include "field.cuh"
+#include "tc_bchain.cuh"
 #include "tc_chain.cuh"
 #include "tc_layer.cuh"
 #include "tc_wgrad.cuh"
@@ -140,6 +142,13 @@ static bool chain_eligible(const sdfg_field_params* p, bool want_views) {
     return n_main <= tc::CH_MAX_MAPS;
 }
 
+static bool bchain_eligible(const sdfg_field_params* p, const float* d_x_in) {
+    if (p->width != 256 || p->n_film < 1 || p->n_film + 1 > tc::BC_MAX_LAYERS) return false;
+    if (p->has_input_linear && (p->in_dim % 16 != 0 || p->in_dim > 256)) return false;
+    if (d_x_in && !p->has_input_linear) return false;
+    return true;
+}
+
 static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, const float* x_in, const float* view_feat, uint64_t N,
                                float* out_sdf, float* out_rgb, float* out_feat, uint8_t* ws, int save, cudaStream_t st) {
     const bool want_views = out_rgb || out_feat;
@@ -150,6 +159,7 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
     SDFG_REQUIRE(!out_rgb || (p->rgb_w && p->rgb_b), SDFG_ERR_INVALID, "field_forward: rgb head missing");
 
     tc::ChainMaps maps;
+    tc::ChainStoreMaps stores;
     tc::ChainParams P = {};
     P.M_total = (uint32_t)N; P.rows_per_image = p->samples_per_image; P.rows_per_ray = p->samples_per_ray;
     P.in_dim = p->in_dim; P.view_dim = p->view_dim;
@@ -168,53 +178,61 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
     auto add_main_map = [&](uint32_t wi, uint32_t ldw) -> int {
         return make_tensor_map_16(&maps.m[nm], Wb(wi), W, W, ldw, 256, 64, tc::FMT_F16);
     };
+    // SAVE: the layer's output tile is TMA-stored chunk by chunk to dst [N, 256] (pitch ld)
+    auto store_to = [&](uint32_t layer, h16* dst, uint64_t ld) -> int {
+        P.layer[layer].store = 1;
+        return make_tensor_map_16(&stores.m[layer], dst, N, W, ld, tc::CH_TILE_M, 64, tc::FMT_F16);
+    };
+    auto trunk_outputs = [&](uint32_t layer, uint32_t l) -> int {     // output of trunk layer l = A(l+1)
+        const bool last = l + 1 == nf;
+        if (last && out_sdf) { tc::ChainLayer& Y = P.layer[layer]; Y.nh = 1; Y.head_w = p->sigma_w; Y.head_b = p->sigma_b; Y.out_head = out_sdf; }
+        return save ? store_to(layer, A(l + 1), last ? L.Kp_v : W) : SDFG_OK;
+    };
     // layer 0: input_linear (ngp) or the first FiLM layer on the raw x part (siren)
     {
-        tc::ChainLayer& Y = P.layer[nl++];
+        tc::ChainLayer& Y = P.layer[nl];
         Y.small_k0 = 0; Y.small_nk = P.x_nk;
         if (p->has_input_linear) {
             Y.act = 0; Y.bias = p->input_b;
-            if (save) { Y.out16 = A(0); Y.ld_out = W; }
+            if (save) if (int e = store_to(nl, A(0), W)) return e;
         } else {
             Y.act = 1; Y.film = 0; Y.bias = p->film_b[0];
+            if (int e = trunk_outputs(nl, 0)) return e;
         }
+        nl++;
     }
-    const uint32_t first_trunk = p->has_input_linear ? 0u : 1u;
-    auto trunk_outputs = [&](tc::ChainLayer& Y, uint32_t l) {       // output of trunk layer l = A(l+1)
-        const bool last = l + 1 == nf;
-        if (save) { Y.out16 = A(l + 1); Y.ld_out = last ? L.Kp_v : W; }
-        if (last && out_sdf) { Y.nh = 1; Y.head_w = p->sigma_w; Y.head_b = p->sigma_b; Y.out_head = out_sdf; }
-    };
-    if (!p->has_input_linear) trunk_outputs(P.layer[0], 0);
-    for (uint32_t l = first_trunk; l < nf; l++) {
-        tc::ChainLayer& Y = P.layer[nl++];
+    for (uint32_t l = p->has_input_linear ? 0u : 1u; l < nf; l++) {
+        tc::ChainLayer& Y = P.layer[nl];
         Y.has_main = 1; Y.tm = nm; Y.act = 1; Y.film = l; Y.bias = p->film_b[l];
         if (int e = add_main_map(1 + l, W)) return e;
         nm++;
-        trunk_outputs(Y, l);
+        if (int e = trunk_outputs(nl, l)) return e;
+        nl++;
     }
     if (want_views) {
-        tc::ChainLayer& Y = P.layer[nl++];
+        tc::ChainLayer& Y = P.layer[nl];
         Y.has_main = 1; Y.tm = nm; Y.act = 1; Y.film = nf; Y.bias = p->film_b[nf];
         Y.small_k0 = P.x_nk; Y.small_nk = P.v_nk;
         if (int e = add_main_map(1 + nf, L.Kp_v)) return e;
         nm++;
-        if (save) { Y.out16 = (h16*)(ws + L.off_hv); Y.ld_out = W; }
+        if (save) if (int e = store_to(nl, (h16*)(ws + L.off_hv), W)) return e;
         if (out_feat) { Y.out_f32 = out_feat; Y.ld_out_f32 = W; }
         if (out_rgb) { Y.nh = 3; Y.head_w = p->rgb_w; Y.head_b = p->rgb_b; Y.out_head = out_rgb; }
+        nl++;
     }
     P.n_layers = nl;
-    for (uint32_t i = 0; i + 1 < nl; i++) P.layer[i].to_act = 1;
+    for (uint32_t i = 0; i < nl; i++) P.layer[i].to_act = (i + 1 < nl || P.layer[i].store) ? 1 : 0;
     P.n_tiles = (uint32_t)ceil_div<uint64_t>(N, tc::CH_TILE_M);
     const uint32_t ctas = std::min<uint32_t>((uint32_t)sm_count(), P.n_tiles);
     P.tiles_per_cta = ceil_div<uint32_t>(P.n_tiles, ctas);
     const uint32_t grid = ceil_div<uint32_t>(P.n_tiles, P.tiles_per_cta);
     const uint32_t smem = tc::chain_smem_bytes();
-    static thread_local bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(tc::tc_chain_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    auto kern = save ? tc::tc_chain_fwd_kernel<true> : tc::tc_chain_fwd_kernel<false>;
+    static thread_local bool configured[2] = {false, false};
+    if (!configured[save ? 1 : 0]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return set_error(SDFG_ERR_CUDA, "tc_chain_fwd_kernel: cannot opt in to %u bytes of shared memory", smem);
-        configured = true;
+        configured[save ? 1 : 0] = true;
     }
     static const bool dbg_on = getenv("SDFG_CHAIN_DBG") != nullptr;     // debugging aid: event log of CTA 0 to stderr
     if (dbg_on) {
@@ -222,7 +240,7 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
         if (!dbuf) cudaMalloc(&dbuf, 4 * 2048 * 8);
         cudaMemsetAsync(dbuf, 0, 4 * 2048 * 8, st);
         P.dbg = dbuf;
-        tc::tc_chain_fwd_kernel<<<grid, tc::CH_THREADS, smem, st>>>(maps, P);
+        kern<<<grid, tc::CH_THREADS, smem, st>>>(maps, stores, P);
         cudaStreamSynchronize(st);
         static unsigned long long host[4 * 2048];
         cudaMemcpy(host, dbuf, sizeof(host), cudaMemcpyDeviceToHost);
@@ -234,7 +252,7 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
         return check_launch("tc_chain_fwd_kernel<gemm>");
     }
     ProfScope prof("tc_chain_fwd_kernel<gemm>", st);
-    tc::tc_chain_fwd_kernel<<<grid, tc::CH_THREADS, smem, st>>>(maps, P);
+    kern<<<grid, tc::CH_THREADS, smem, st>>>(maps, stores, P);
     return check_launch("tc_chain_fwd_kernel<gemm>");
 }
 
@@ -442,16 +460,18 @@ static int launch_wgrad(const h16* dz, const h16* x, uint32_t Kx, int64_t ldx, u
     return check_launch("tc_wgrad_kernel<gemm>");
 }
 
-// scratch: DZ [N,256] fp16 | DH [N,256] fp16 | WgT [B, 256, 256] fp16 | G [B, 256, 336] fp32 | loss scale {bits, s, 1/s}
-struct TcScratch { uint64_t off_dz, off_dh, off_wgt, off_g, off_scale, total; };
+// scratch: DZ_l [N,256] fp16 per FiLM layer | DH [N,256] fp16 | WgT_l [B, 256, 256] fp16 per layer | W_in^T [in_dim, 256] |
+//          G [B, 256, 336] fp32 | loss scale {bits, s, 1/s}
+struct TcScratch { uint64_t off_dz[SDFG_MAX_FILM], off_dh, off_wgt[SDFG_MAX_FILM], off_wgt_in, off_g, off_scale, total; };
 static TcScratch tc_scratch(const sdfg_field_params* p, uint64_t N) {
     TcScratch s = {};
     const uint64_t B = ceil_div<uint64_t>(N, p->samples_per_image);
     uint64_t off = 0;
     auto take = [&](uint64_t bytes) { const uint64_t o = off; off = align256(off + bytes); return o; };
-    s.off_dz = take(N * 256 * 2);
+    for (uint32_t l = 0; l <= p->n_film; l++) s.off_dz[l] = take(N * 256 * 2);
     s.off_dh = take(N * 256 * 2);
-    s.off_wgt = take(B * 256 * 256 * 2);
+    for (uint32_t l = 0; l <= p->n_film; l++) s.off_wgt[l] = take(B * 256 * 256 * 2);
+    s.off_wgt_in = take((uint64_t)round_up(p->in_dim, 16) * 256 * 2);
     s.off_g = take(B * 256 * 336 * 4);
     s.off_scale = take(256);
     s.total = off;
@@ -473,9 +493,9 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
     uint8_t* sc = (uint8_t*)scratch;
     auto Wb = [&](uint32_t i) { return (const h16*)(ws + L.off_w[i]); };
     auto A = [&](uint32_t l) { return (const h16*)(ws + L.off_a[l]); };
-    h16* DZ = (h16*)(sc + SC.off_dz);
+    h16* DZ = (h16*)(sc + SC.off_dz[0]);
     h16* DH = (h16*)(sc + SC.off_dh);
-    h16* WGT = (h16*)(sc + SC.off_wgt);
+    h16* WGT = (h16*)(sc + SC.off_wgt[0]);
     float* G = (float*)(sc + SC.off_g);
     float* gscale = (float*)(sc + SC.off_scale) + 2;      // {s, 1/s}; [0] of the slot holds the absmax bits
     if (int e = compute_loss_scale(d_sdf, N, d_rgb, N * 3, d_feat, N * 256, (uint32_t*)(sc + SC.off_scale), gscale, st)) return e;
@@ -486,6 +506,108 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
 
     auto layer_K = [&](uint32_t l) { return l == nf ? L.Kp_v : ((l == 0 && !p->has_input_linear) ? L.Kp_in : W); };      // padded
     auto layer_Kx = [&](uint32_t l) { return l == nf ? W + p->view_dim : ((l == 0 && !p->has_input_linear) ? p->in_dim : W); };
+
+    if (chain_enabled() && bchain_eligible(p, d_x_in)) {
+        // ---------------------------------------------------------------- fused backward chain (tc_bchain.cuh)
+        const bool views = d_rgb || d_feat;
+        const bool store = g != nullptr;
+        const bool need_dh0 = p->has_input_linear && (d_x_in || (g && g->input_w));
+        tc::BChainMaps* maps = new tc::BChainMaps;                     // 5 KB of tensor maps: off the stack
+        std::unique_ptr<tc::BChainMaps> maps_guard(maps);
+        tc::BChainParams P = {};
+        P.M_total = (uint32_t)N; P.rows_per_image = spi;
+        P.gamma = p->gamma; P.beta = p->beta; P.gstride = gstride; P.gscale = gscale;
+        P.vecs[0] = p->sigma_w;
+        if (p->rgb_w) { P.vecs[1] = p->rgb_w; P.vecs[2] = p->rgb_w + W; P.vecs[3] = p->rgb_w + 2 * W; }
+        uint32_t nl = 0;
+        auto add_layer = [&](uint32_t l) -> int {                      // FiLM layer l (nf = views) becomes chain layer nl
+            tc::BLayer& Y = P.layer[nl];
+            const uint32_t Kp = layer_K(l);
+            Y.nk = ceil_div<uint32_t>(Kp, 64);
+            Y.last_ksteps = ceil_div<uint32_t>(Kp - (Y.nk - 1) * 64, 16);
+            Y.film = l; Y.bias = p->film_b[l];
+            Y.do_D = l == nf ? 1u : ((l > 0 || need_dh0) ? 1u : 0u);
+            if (int e = make_tensor_map_16(&maps->a[nl], A(l), N, Kp, Kp, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
+            if (int e = make_tensor_map_16(&maps->w[nl], Wb(1 + l), W, Kp, Kp, 256, 64, tc::FMT_F16)) return e;
+            if (Y.do_D) {
+                h16* wgt = (h16*)(sc + SC.off_wgt[l]);
+                wgt_kernel<<<dim3(W, B), 256, 0, st>>>(p->film_w[l], layer_Kx(l), p->gamma + (size_t)l * W, gstride, wgt, W, B);
+                if (int e = check_launch("wgt_kernel")) return e;
+                if (int e = make_tensor_map_16(&maps->wgt[nl], wgt, (uint64_t)B * W, W, W, 256, 64, tc::FMT_F16)) return e;
+            }
+            if (store)
+                if (int e = make_tensor_map_16(&maps->dz[nl], (h16*)(sc + SC.off_dz[l]), N, W, W, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
+            nl++;
+            return SDFG_OK;
+        };
+        if (views) {
+            if (int e = add_layer(nf)) return e;
+            tc::BLayer& Y = P.layer[0];
+            Y.r_src_g = 0; Y.r_rank = d_rgb ? 3 : 0; Y.r_vec0 = 1; Y.r_rank_s = d_rgb; Y.r_dfeat = d_feat;
+            Y.d_rank = d_sdf ? 1 : 0; Y.d_vec0 = 0; Y.d_rank_s = d_sdf;
+        }
+        for (int l = (int)nf - 1; l >= 0; l--) {
+            if (int e = add_layer((uint32_t)l)) return e;
+            tc::BLayer& Y = P.layer[nl - 1];
+            if (!views && l == (int)nf - 1) { Y.r_src_g = 0; Y.r_rank = 1; Y.r_vec0 = 0; Y.r_rank_s = d_sdf; }
+            else Y.r_src_g = 1;
+        }
+        P.n_layers = nl;
+        if (need_dh0) {
+            P.has_in = 1; P.in_dim = p->in_dim; P.d_x_in = d_x_in;
+            h16* wgt_in = (h16*)(sc + SC.off_wgt_in);
+            wgt_kernel<<<dim3(p->in_dim, 1), 256, 0, st>>>(p->input_w, p->in_dim, nullptr, 0, wgt_in, p->in_dim, 1);
+            if (int e = check_launch("wgt_kernel")) return e;
+            if (int e = make_tensor_map_16(&maps->wgt_in, wgt_in, p->in_dim, W, W, p->in_dim, 64, tc::FMT_F16)) return e;
+            if (store)
+                if (int e = make_tensor_map_16(&maps->dh0, DH, N, W, W, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
+        }
+        P.n_tiles = (uint32_t)(N / tc::CH_TILE_M);
+        const uint32_t ctas = std::min<uint32_t>((uint32_t)sm_count(), P.n_tiles);
+        P.tiles_per_cta = ceil_div<uint32_t>(P.n_tiles, ctas);
+        const uint32_t grid = ceil_div<uint32_t>(P.n_tiles, P.tiles_per_cta);
+        const uint32_t smem = tc::bchain_smem_bytes();
+        auto kern = store ? tc::tc_chain_bwd_kernel<true> : tc::tc_chain_bwd_kernel<false>;
+        static thread_local bool configured[2] = {false, false};
+        if (!configured[store ? 1 : 0]) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return set_error(SDFG_ERR_CUDA, "tc_chain_bwd_kernel: cannot opt in to %u bytes of shared memory", smem);
+            configured[store ? 1 : 0] = true;
+        }
+        {
+            ProfScope prof("tc_chain_bwd_kernel<gemm>", st);
+            kern<<<grid, tc::CH_THREADS, smem, st>>>(*maps, P);
+            if (int e = check_launch("tc_chain_bwd_kernel<gemm>")) return e;
+        }
+        if (!g) return SDFG_OK;
+        // ---- parameter gradients from the stored du tiles (sample-axis contractions) and the fp32 head gradients
+        if (views && g->rgb_w && d_rgb) {
+            head_wgrad16_kernel<3><<<(unsigned)ceil_div<uint64_t>(N, 512), 256, 0, st>>>(d_rgb, (const h16*)(ws + L.off_hv), W, g->rgb_w, g->rgb_b, N, 512);
+            if (int e = check_launch("head_wgrad16_kernel<3>")) return e;
+        }
+        if (g->sigma_w && d_sdf) {
+            head_wgrad16_kernel<1><<<(unsigned)ceil_div<uint64_t>(N, 512), 256, 0, st>>>(d_sdf, A(nf), L.Kp_v, g->sigma_w, g->sigma_b, N, 512);
+            if (int e = check_launch("head_wgrad16_kernel<1>")) return e;
+        }
+        for (int l = views ? (int)nf : (int)nf - 1; l >= 0; l--) {
+            if (!g->film_w[l]) continue;
+            if (cudaMemsetAsync(G, 0, (size_t)B * 256 * 336 * 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");
+            uint32_t ldg, ones;
+            if (int e = launch_wgrad((const h16*)(sc + SC.off_dz[l]), A(l), layer_Kx(l), layer_K(l), N, spi, G, &ldg, &ones, st, tc::FMT_F16)) return e;
+            wgrad_finish_kernel<<<256, 128, 0, st>>>(G, ldg, ones, B, p->film_w[l], layer_Kx(l), layer_Kx(l), p->film_b[l], p->gamma + (size_t)l * W,
+                                                     gstride, 1, g->film_w[l], g->film_b[l], g->gamma + (size_t)l * W, g->beta + (size_t)l * W, gscale);
+            if (int e = check_launch("wgrad_finish_kernel")) return e;
+        }
+        if (p->has_input_linear && g->input_w) {
+            if (cudaMemsetAsync(G, 0, (size_t)B * 256 * 336 * 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");
+            uint32_t ldg, ones;
+            if (int e = launch_wgrad(DH, (const h16*)(ws + L.off_x0), p->in_dim, L.Kp_in, N, spi, G, &ldg, &ones, st, tc::FMT_F16)) return e;
+            wgrad_finish_kernel<<<256, 128, 0, st>>>(G, ldg, ones, B, p->input_w, p->in_dim, p->in_dim, p->input_b, nullptr, 0, 0, g->input_w,
+                                                     g->input_b, nullptr, nullptr, gscale);
+            if (int e = check_launch("wgrad_finish_kernel")) return e;
+        }
+        return SDFG_OK;
+    }
 
     // R: DZ = dh * cos(z_l), z recomputed from A_l
     auto run_R = [&](uint32_t l, const h16* dh16, const float* dh32, int rank, const float* rs, const float* rv) -> int {

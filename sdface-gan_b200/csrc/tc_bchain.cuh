@@ -1,0 +1,427 @@
+// The backward pass through the FiLM-SIREN layers as ONE persistent tcgen05 kernel: for a 128-sample tile the gradient flows from
+// the top layer to the input without leaving the SM (ref: autograd of FiLMSiren.forward sdf_model.py:61-69 chained through
+// NGPSIRENGenerator.forward :1566-1592; the same kernel runs the eikonal chain d sdf / d x of get_eikonal_term :224-229).
+//
+// Per layer l (top -> bottom), two GEMMs share the tile:
+//   R_l   u  = A_l W_l^T                 recompute of the pre-activation from the SAVED layer input A_l (fp16, HBM -> TMA ring)
+//   epi_R du = dh * cos(gamma u + c)     dh: fp16 gradient tile G in shared memory (+ rank-r head terms / fp32 d_feat for the
+//                                        top layer); du overwrites G in place, chunk by chunk           [MUFU.COS bound]
+//   D_l   dh' = du (gamma o W_l)         A = G (K-major as written by the epilogue), B = per-image (gamma o W_l)^T chunks
+//   epi_D G = fp16(dh' [+ d_sdf w_sigma])  -> input gradient of the layer below
+// and a final N = in_dim GEMM gives d x_in = dh_0 W_in (fp32 out).  R_{l-1} is issued right behind D_l, so its MMAs overlap epi_D.
+// Gradients are fp16 with the power-of-two loss scale of field_tc.cu (gscale = {s, 1/s}); stores saturate.
+// With STORE the du tiles (and dh_0) are TMA-stored to HBM for the sample-axis weight-gradient kernels (tc_wgrad.cuh) that run
+// afterwards; G chunks are only overwritten once the store has read them (st_done).
+// Algorithmic HBM traffic per sample and layer: 512 B (A_l) in, 512 B (du) out -- the per-layer kernels moved 2.5 KB.
+#pragma once
+#include "tc_chain.cuh"
+
+namespace sdfg {
+namespace tc {
+
+constexpr uint32_t BC_MAX_LAYERS = SDFG_MAX_FILM;            // FiLM layers incl. views
+constexpr uint32_t BC_STAGE_BYTES = 48 * 1024;               // [B chunk 32 KB | A chunk 16 KB]
+constexpr uint32_t BC_STAGES = 3;
+constexpr uint32_t BC_G_BYTES = 4 * CH_CHUNK_BYTES;          // gradient tile [128 x 256] fp16
+
+struct BLayer {
+    uint32_t nk, last_ksteps;   // recompute GEMM: K chunks of 64 and K-steps (of 16) in the last chunk
+    uint32_t film;              // row of gamma / beta
+    uint32_t r_src_g;           // epi_R: dh comes from G
+    uint32_t r_rank, r_vec0;    // epi_R: + sum_r gs * r_rank_s[row*r_rank + r] * vecs[r_vec0 + r][col]
+    uint32_t do_D;              // run D (the layer below needs its gradient)
+    uint32_t d_rank, d_vec0;    // epi_D: + gs * d_rank_s[row] * vecs[d_vec0][col]
+    uint32_t pad;
+    const float* r_rank_s;
+    const float* r_dfeat;       // fp32 [M, 256] added to dh (times gs), or NULL
+    const float* d_rank_s;
+    const float* bias;
+};
+
+struct BChainParams {
+    uint32_t M_total, rows_per_image, n_tiles, tiles_per_cta, n_layers;
+    uint32_t has_in, in_dim;    // final stage: d_x_in[M, in_dim] = gs_inv * dh_0 W_in
+    uint32_t pad;
+    float* d_x_in;
+    const float* gamma;         // + img * gstride + film * 256 + n
+    const float* beta;
+    int64_t gstride;
+    const float* gscale;        // {s, 1/s}
+    const float* vecs[4];       // rank vectors [256] each: 0 = w_sigma, 1..3 = w_rgb rows
+    BLayer layer[BC_MAX_LAYERS];   // index 0 = TOP layer
+};
+
+struct alignas(64) BChainMaps {
+    CUtensorMap a[BC_MAX_LAYERS];      // saved layer input A_l      [M, K_l]      box 128 x 64
+    CUtensorMap w[BC_MAX_LAYERS];      // W_l fp16                    [256, K_l]    box 256 x 64
+    CUtensorMap wgt[BC_MAX_LAYERS];    // (gamma o W_l)^T per image   [B*256, 256]  box 256 x 64
+    CUtensorMap dz[BC_MAX_LAYERS];     // du store                    [M, 256]      box 128 x 64
+    CUtensorMap wgt_in;                // W_in^T                      [in_dim, 256] box in_dim x 64
+    CUtensorMap dh0;                   // dh_0 store                  [M, 256]      box 128 x 64
+};
+
+struct BChainSmem {
+    uint64_t full[BC_STAGES], empty[BC_STAGES];
+    uint64_t dz_ready[4], dh0_ready[4], st_done[4];
+    uint64_t accR_full, accR_empty, accD_full, accD_empty;
+    uint32_t tmem_base;
+    uint32_t pad[3];
+    alignas(16) float gam[2][256];
+    float cst[2][256];
+    float vecs[4][256];
+};
+
+__host__ __device__ inline uint32_t bchain_smem_bytes() { return 1024 + BC_G_BYTES + BC_STAGES * BC_STAGE_BYTES + (uint32_t)sizeof(BChainSmem); }
+
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+
+template <bool STORE>
+__global__ void __launch_bounds__(CH_THREADS, 1)
+tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_constant__ BChainParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smG = smem;
+    uint8_t* smRING = smG + BC_G_BYTES;
+    BChainSmem& S = *reinterpret_cast<BChainSmem*>(smRING + BC_STAGES * BC_STAGE_BYTES);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t_begin = blockIdx.x * P.tiles_per_cta;
+    const uint32_t t_end = min(P.n_tiles, t_begin + P.tiles_per_cta);
+    const uint32_t nL = P.n_layers;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < BC_STAGES; i++) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
+        for (uint32_t i = 0; i < 4; i++) { mbar_init(&S.dz_ready[i], CH_EPI_WARPS); mbar_init(&S.dh0_ready[i], CH_EPI_WARPS); mbar_init(&S.st_done[i], 1); }
+        mbar_init(&S.accR_full, 1); mbar_init(&S.accR_empty, CH_EPI_WARPS);
+        mbar_init(&S.accD_full, 1); mbar_init(&S.accD_empty, CH_EPI_WARPS);
+        fence_barrier_init();
+    }
+    if (warp == CH_WARP_TMA && lane == 0) {
+        for (uint32_t i = 0; i < nL; i++) {
+            tma_prefetch_desc(&maps.a[i]); tma_prefetch_desc(&maps.w[i]);
+            if (P.layer[i].do_D) tma_prefetch_desc(&maps.wgt[i]);
+            if (STORE) tma_prefetch_desc(&maps.dz[i]);
+        }
+        if (P.has_in) tma_prefetch_desc(&maps.wgt_in);
+    }
+    if (warp == CH_WARP_MMA) tmem_alloc(&S.tmem_base, 512);
+    for (uint32_t i = threadIdx.x; i < 4 * 256; i += blockDim.x) S.vecs[i >> 8][i & 255] = P.vecs[i >> 8] ? __ldg(P.vecs[i >> 8] + (i & 255)) : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = S.tmem_base;
+    const uint32_t in_box_bytes = P.in_dim * 128;
+
+    if (warp == CH_WARP_TMA) {
+        // ===================================================== TMA producer: operands of R_l, D_l (and the input stage), in issue order
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            auto next = [&]() { if (++stage == BC_STAGES) { stage = 0; phase ^= 1; } };
+            for (uint32_t t = t_begin; t < t_end; t++) {
+                const int32_t row0 = (int32_t)(t * CH_TILE_M);
+                const int32_t img = (int32_t)((t * CH_TILE_M) / P.rows_per_image);
+                for (uint32_t i = 0; i < nL; i++) {
+                    const uint32_t nk = P.layer[i].nk;
+                    for (uint32_t kc = 0; kc < nk; kc++) {
+                        mbar_wait(&S.empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&S.full[stage], BC_STAGE_BYTES);
+                        uint8_t* st = smRING + stage * BC_STAGE_BYTES;
+                        tma_load_2d(st, &maps.w[i], &S.full[stage], (int32_t)(kc * 64), 0);
+                        tma_load_2d(st + 32768, &maps.a[i], &S.full[stage], (int32_t)(kc * 64), row0);
+                        next();
+                    }
+                    if (P.layer[i].do_D)
+                        for (uint32_t kc = 0; kc < 4; kc++) {
+                            mbar_wait(&S.empty[stage], phase ^ 1);
+                            mbar_arrive_expect_tx(&S.full[stage], 32768);
+                            tma_load_2d(smRING + stage * BC_STAGE_BYTES, &maps.wgt[i], &S.full[stage], (int32_t)(kc * 64), img * 256);
+                            next();
+                        }
+                }
+                if (P.has_in)
+                    for (uint32_t kc = 0; kc < 4; kc++) {
+                        mbar_wait(&S.empty[stage], phase ^ 1);
+                        mbar_arrive_expect_tx(&S.full[stage], in_box_bytes);
+                        tma_load_2d(smRING + stage * BC_STAGE_BYTES, &maps.wgt_in, &S.full[stage], (int32_t)(kc * 64), 0);
+                        next();
+                    }
+            }
+        }
+    } else if (warp == CH_WARP_MMA) {
+        // ===================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = idesc_f16(CH_TILE_M, 256, FMT_F16, FMT_F16, 0, 0);
+            const uint32_t idesc_in = idesc_f16(CH_TILE_M, P.in_dim, FMT_F16, FMT_F16, 0, 0);
+            const uint32_t g_addr = smem_u32(smG);
+            uint32_t stage = 0, phase = 0, nR = 0, nD = 0, dzgen = 0, it = 0;
+            auto next = [&]() { if (++stage == BC_STAGES) { stage = 0; phase ^= 1; } };
+            for (uint32_t t = t_begin; t < t_end; t++, it++) {
+                for (uint32_t i = 0; i < nL; i++) {
+                    const uint32_t nk = P.layer[i].nk, lks = P.layer[i].last_ksteps;
+                    // ---- R_l -> accumulator 0
+                    mbar_wait(&S.accR_empty, (nR & 1) ^ 1);
+                    tc_fence_after();
+                    uint32_t accumulate = 0;
+                    for (uint32_t kc = 0; kc < nk; kc++) {
+                        mbar_wait(&S.full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(smRING + stage * BC_STAGE_BYTES), a_addr = b_addr + 32768;
+                        const uint32_t ks = kc + 1 == nk ? lks : 4;
+                        for (uint32_t s = 0; s < ks; s++, accumulate = 1)
+                            umma_bf16(tmem_base, smem_desc_sw128(a_addr + s * 32, 16, 1024), smem_desc_sw128(b_addr + s * 32, 16, 1024), idesc, accumulate);
+                        umma_commit(&S.empty[stage]);
+                        next();
+                    }
+                    umma_commit(&S.accR_full);
+                    nR++;
+                    // ---- D_l -> accumulator 1, chunk by chunk behind the epilogue
+                    if (P.layer[i].do_D) {
+                        mbar_wait(&S.accD_empty, (nD & 1) ^ 1);
+                        tc_fence_after();
+                        for (uint32_t kc = 0; kc < 4; kc++) {
+                            mbar_wait(&S.dz_ready[kc], dzgen & 1);
+                            mbar_wait(&S.full[stage], phase);
+                            tc_fence_after();
+                            const uint32_t b_addr = smem_u32(smRING + stage * BC_STAGE_BYTES), a_addr = g_addr + kc * CH_CHUNK_BYTES;
+                            for (uint32_t s = 0; s < 4; s++)
+                                umma_bf16(tmem_base + 256, smem_desc_sw128(a_addr + s * 32, 16, 1024), smem_desc_sw128(b_addr + s * 32, 16, 1024), idesc, (kc | s) != 0);
+                            umma_commit(&S.empty[stage]);
+                            next();
+                        }
+                        umma_commit(&S.accD_full);
+                        nD++;
+                    } else {
+                        for (uint32_t kc = 0; kc < 4; kc++) mbar_wait(&S.dz_ready[kc], dzgen & 1);   // keep the phase parity in step
+                    }
+                    dzgen++;
+                }
+                if (P.has_in) {
+                    mbar_wait(&S.accD_empty, (nD & 1) ^ 1);
+                    tc_fence_after();
+                    for (uint32_t kc = 0; kc < 4; kc++) {
+                        mbar_wait(&S.dh0_ready[kc], it & 1);
+                        mbar_wait(&S.full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t b_addr = smem_u32(smRING + stage * BC_STAGE_BYTES), a_addr = g_addr + kc * CH_CHUNK_BYTES;
+                        for (uint32_t s = 0; s < 4; s++)
+                            umma_bf16(tmem_base + 256, smem_desc_sw128(a_addr + s * 32, 16, 1024), smem_desc_sw128(b_addr + s * 32, 16, 1024), idesc_in, (kc | s) != 0);
+                        umma_commit(&S.empty[stage]);
+                        next();
+                    }
+                    umma_commit(&S.accD_full);
+                    nD++;
+                }
+            }
+        }
+    } else if (warp == CH_WARP_STORE) {
+        // ===================================================== storer (STORE): du tiles and dh_0 -> HBM for the weight-gradient kernels
+        if (STORE && lane == 0) {
+            uint32_t dzgen = 0, it = 0;
+            for (uint32_t t = t_begin; t < t_end; t++, it++) {
+                const int32_t row0 = (int32_t)(t * CH_TILE_M);
+                for (uint32_t i = 0; i < nL; i++, dzgen++)
+                    for (uint32_t c = 0; c < 4; c++) {
+                        mbar_wait(&S.dz_ready[c], dzgen & 1);
+                        tma_store_2d(&maps.dz[i], smG + c * CH_CHUNK_BYTES, (int32_t)(c * 64), row0);
+                        tma_store_commit();
+                        tma_store_wait_read();
+                        mbar_arrive(&S.st_done[c]);
+                    }
+                if (P.has_in)
+                    for (uint32_t c = 0; c < 4; c++) {
+                        mbar_wait(&S.dh0_ready[c], it & 1);
+                        tma_store_2d(&maps.dh0, smG + c * CH_CHUNK_BYTES, (int32_t)(c * 64), row0);
+                        tma_store_commit();
+                        tma_store_wait_read();
+                        mbar_arrive(&S.st_done[c]);
+                    }
+            }
+            tma_store_wait_all();
+        }
+    } else if (warp < CH_EPI_WARPS) {
+        // ===================================================== epilogue: 16 warps, 4 per TMEM lane quarter, 16 columns of every chunk each
+        const uint32_t q = warp & 3, sb = warp >> 2;
+        const uint32_t etid = threadIdx.x;
+        const uint32_t r = q * 32 + lane;
+        const uint32_t g_row = smem_u32(smG) + r * 128;
+        const uint32_t u0 = ((2 * sb) ^ (r & 7)) << 4, u1 = ((2 * sb + 1) ^ (r & 7)) << 4;
+        const float gs = __ldg(P.gscale), gs_inv = __ldg(P.gscale + 1);
+        const uint32_t lane_base = (q * 32) << 16;
+        uint32_t nR = 0, nD = 0, stgen = 0, n = 0;
+        bool stored_dh0 = false;                                        // G holds a dh_0 tile the storer is (or was) reading
+        for (uint32_t t = t_begin; t < t_end; t++) {
+            const uint64_t row = (uint64_t)t * CH_TILE_M + r;
+            const uint32_t img = (t * CH_TILE_M) / P.rows_per_image;
+            for (uint32_t i = 0; i < nL; i++, n++) {
+                const uint32_t L_film = P.layer[i].film, r_src_g = P.layer[i].r_src_g, r_rank = P.layer[i].r_rank, r_vec0 = P.layer[i].r_vec0;
+                const uint32_t do_D = P.layer[i].do_D, d_rank = P.layer[i].d_rank, d_vec0 = P.layer[i].d_vec0;
+                const float* const dfeat = P.layer[i].r_dfeat;
+                const uint32_t tb = n & 1;
+                const uint32_t gam_s = smem_u32(&S.gam[tb][0]), cst_s = smem_u32(&S.cst[tb][0]);
+                {   // FiLM constants of this layer: threads 0..255 gamma, 256..511 gamma*bias + beta
+                    const uint32_t col = etid & 255;
+                    const float gm = __ldg(P.gamma + (int64_t)img * P.gstride + L_film * 256 + col);
+                    if (etid < 256) sts32(gam_s + col * 4, gm);
+                    else sts32(cst_s + col * 4, fmaf(gm, __ldg(P.layer[i].bias + col), __ldg(P.beta + (int64_t)img * P.gstride + L_film * 256 + col)));
+                    named_bar_sync(1, CH_EPI_THREADS);
+                }
+                float rs[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    if ((uint32_t)k < r_rank) rs[k] = gs * __ldg(P.layer[i].r_rank_s + row * r_rank + k);
+                const float ds = d_rank ? gs * __ldg(P.layer[i].d_rank_s + row) : 0.f;
+                const uint32_t rvec_s = smem_u32(&S.vecs[r_vec0][0]), dvec_s = smem_u32(&S.vecs[d_vec0][0]);
+
+                // ---------------- epi_R: du = dh * cos(gamma u + c), in place in G
+                mbar_wait(&S.accR_full, nR & 1);
+                tc_fence_after();
+                {
+                    const uint32_t taddr = tmem_base + lane_base + sb * 16;
+                    uint32_t raw[2][16];
+                    tmem_ld16_issue(taddr, raw[0]);
+#pragma unroll
+                    for (uint32_t c = 0; c < 4; c++) {
+                        const uint32_t col = c * 64 + sb * 16;
+                        const uint32_t chunk = g_row + c * CH_CHUNK_BYTES;
+                        float dh[16];
+                        if (r_src_g) {
+                            const uint4 a = lds128u(chunk + u0), b = lds128u(chunk + u1);
+                            const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                            for (int k = 0; k < 8; k++) { const float2 f = unpack_f16(w[k]); dh[2 * k] = f.x; dh[2 * k + 1] = f.y; }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 16; k++) dh[k] = 0.f;
+                        }
+                        if (dfeat) {
+                            const float4* src = reinterpret_cast<const float4*>(dfeat + row * 256 + col);
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const float4 f = ldg_stream4(src + j);
+                                dh[4 * j] = fmaf(gs, f.x, dh[4 * j]); dh[4 * j + 1] = fmaf(gs, f.y, dh[4 * j + 1]);
+                                dh[4 * j + 2] = fmaf(gs, f.z, dh[4 * j + 2]); dh[4 * j + 3] = fmaf(gs, f.w, dh[4 * j + 3]);
+                            }
+                        }
+                        if (r_rank) {
+#pragma unroll
+                            for (int rr = 0; rr < 3; rr++) {
+                                if ((uint32_t)rr < r_rank) {
+#pragma unroll
+                                    for (int k = 0; k < 16; k += 4) {
+                                        const float4 w4 = lds128(rvec_s + (rr * 256 + col + k) * 4);
+                                        dh[k] = fmaf(rs[rr], w4.x, dh[k]); dh[k + 1] = fmaf(rs[rr], w4.y, dh[k + 1]);
+                                        dh[k + 2] = fmaf(rs[rr], w4.z, dh[k + 2]); dh[k + 3] = fmaf(rs[rr], w4.w, dh[k + 3]);
+                                    }
+                                }
+                            }
+                        }
+                        tmem_ld_wait16(raw[c & 1]);
+                        if (c < 3) tmem_ld16_issue(taddr + (c + 1) * 64, raw[(c + 1) & 1]);
+                        float v[16];
+#pragma unroll
+                        for (int k = 0; k < 16; k += 4) {
+                            const float4 g4 = lds128(gam_s + (col + k) * 4);
+                            const float4 c4 = lds128(cst_s + (col + k) * 4);
+                            v[k] = dh[k] * __cosf(fmaf(__uint_as_float(raw[c & 1][k]), g4.x, c4.x));
+                            v[k + 1] = dh[k + 1] * __cosf(fmaf(__uint_as_float(raw[c & 1][k + 1]), g4.y, c4.y));
+                            v[k + 2] = dh[k + 2] * __cosf(fmaf(__uint_as_float(raw[c & 1][k + 2]), g4.z, c4.z));
+                            v[k + 3] = dh[k + 3] * __cosf(fmaf(__uint_as_float(raw[c & 1][k + 3]), g4.w, c4.w));
+                        }
+                        const uint4 h0 = make_uint4(pack_f16_sat(v[0], v[1]), pack_f16_sat(v[2], v[3]), pack_f16_sat(v[4], v[5]), pack_f16_sat(v[6], v[7]));
+                        const uint4 h1 = make_uint4(pack_f16_sat(v[8], v[9]), pack_f16_sat(v[10], v[11]), pack_f16_sat(v[12], v[13]), pack_f16_sat(v[14], v[15]));
+                        if (STORE && stored_dh0 && i == 0) mbar_wait(&S.st_done[c], stgen & 1);   // the previous tile's dh_0 store has read the chunk
+                        sts128(chunk + u0, h0);
+                        sts128(chunk + u1, h1);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&S.dz_ready[c]);
+                    }
+                    if (STORE && stored_dh0 && i == 0) { stgen++; stored_dh0 = false; }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.accR_empty);
+                nR++;
+
+                // ---------------- epi_D: G = fp16(dh' + rank-1 term)
+                if (do_D) {
+                    mbar_wait(&S.accD_full, nD & 1);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + lane_base + 256 + sb * 16;
+                    const bool to_in = P.has_in && i + 1 == nL;
+                    uint32_t raw[2][16];
+                    tmem_ld16_issue(taddr, raw[0]);
+#pragma unroll
+                    for (uint32_t c = 0; c < 4; c++) {
+                        const uint32_t col = c * 64 + sb * 16;
+                        const uint32_t chunk = g_row + c * CH_CHUNK_BYTES;
+                        tmem_ld_wait16(raw[c & 1]);
+                        if (c < 3) tmem_ld16_issue(taddr + (c + 1) * 64, raw[(c + 1) & 1]);
+                        float v[16];
+#pragma unroll
+                        for (int k = 0; k < 16; k++) v[k] = __uint_as_float(raw[c & 1][k]);
+                        if (d_rank) {
+#pragma unroll
+                            for (int k = 0; k < 16; k += 4) {
+                                const float4 w4 = lds128(dvec_s + (col + k) * 4);
+                                v[k] = fmaf(ds, w4.x, v[k]); v[k + 1] = fmaf(ds, w4.y, v[k + 1]);
+                                v[k + 2] = fmaf(ds, w4.z, v[k + 2]); v[k + 3] = fmaf(ds, w4.w, v[k + 3]);
+                            }
+                        }
+                        const uint4 h0 = make_uint4(pack_f16_sat(v[0], v[1]), pack_f16_sat(v[2], v[3]), pack_f16_sat(v[4], v[5]), pack_f16_sat(v[6], v[7]));
+                        const uint4 h1 = make_uint4(pack_f16_sat(v[8], v[9]), pack_f16_sat(v[10], v[11]), pack_f16_sat(v[12], v[13]), pack_f16_sat(v[14], v[15]));
+                        if (STORE) mbar_wait(&S.st_done[c], stgen & 1);     // the du store of this layer has read the chunk
+                        sts128(chunk + u0, h0);
+                        sts128(chunk + u1, h1);
+                        if (to_in) {
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&S.dh0_ready[c]);
+                        }
+                    }
+                    if (STORE) stgen++;
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.accD_empty);
+                    nD++;
+                } else if (STORE) {
+                    // no D: the du store of this layer still owns G until the storer is done with it
+                    for (uint32_t c = 0; c < 4; c++) mbar_wait(&S.st_done[c], stgen & 1);
+                    stgen++;
+                }
+            }
+            // ---------------- input stage: d_x_in = gs_inv * acc
+            if (P.has_in) {
+                mbar_wait(&S.accD_full, nD & 1);
+                tc_fence_after();
+                if (sb * 16 < P.in_dim && P.d_x_in) {                   // warp-uniform: tcgen05.ld is a whole-warp instruction
+                    uint32_t raw[16];
+                    tmem_ld16(tmem_base + lane_base + 256 + sb * 16, raw);
+                    tmem_ld_wait();
+                    if (row < P.M_total) {
+                        float4* dst = reinterpret_cast<float4*>(P.d_x_in + row * P.in_dim + sb * 16);
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            dst[j] = make_float4(gs_inv * __uint_as_float(raw[4 * j]), gs_inv * __uint_as_float(raw[4 * j + 1]),
+                                                 gs_inv * __uint_as_float(raw[4 * j + 2]), gs_inv * __uint_as_float(raw[4 * j + 3]));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.accD_empty);
+                nD++;
+                if (STORE) stored_dh0 = true;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == CH_WARP_MMA) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace tc
+}  // namespace sdfg

@@ -10,14 +10,18 @@
 //   MMA thread    layer i accumulates into TMEM accumulator (i & 1); the K = 256 part is issued 64-column chunk by chunk as soon
 //                 as the epilogue of layer i-1 has produced that chunk (act_ready[kc]) -> the MMAs of layer i overlap the epilogue
 //                 of layer i-1 at chunk granularity, with only 2 x 256 TMEM columns
-//   epilogue      8 warps (2 per TMEM lane quarter): tcgen05.ld -> FiLM + sin.approx (+ sdf / rgb head dot products) -> fp16 ->
+//   epilogue      16 warps (4 per TMEM lane quarter = 4 per SM sub-partition, 16 columns of every 64-column chunk each):
+//                 tcgen05.ld (prefetched one chunk ahead) -> FiLM + sin.approx (+ sdf / rgb head dot products) -> fp16 ->
 //                 st.shared into ACT *in place* (every MMA that read the old contents has completed: acc_full) -> act_ready[kc]
 //   TMA producer  streams [256 x 64] fp16 weight chunks (32 KB) of the K = 256 layers through a 3-stage ring, in layer order,
 //                 tile after tile (weights live in L2: 0.5 MB per network)
+//   storer        (SAVE) TMA-stores each finished ACT chunk to the layer's saved-activation matrix in HBM; the epilogue waits for
+//                 the store to have read the chunk (st_done[kc]) before it overwrites it one layer later
+// The epilogue is the critical path: per layer and SM it has to push 32 768 sin.approx through the SFUs (16 / clk) and read
+// 128 KB of TMEM, each ~2 000 clk -- the same as the layer's 16 MMAs (128 clk each).  Role warps sit at the highest warp ids
+// because the issue arbiter favours them.
 // Algorithmic HBM traffic per sample (inference): in_dim*4 B in, 4 B (sdf) + 12 B (rgb) + 1 KB (features, if wanted) out --
 // against 1 KB per sample PER LAYER for the per-layer kernels (tc_layer.cuh), which stay as the fallback for odd shapes.
-// When the forward is saved for backward the epilogue also stores each layer's output to HBM (fp16 + bf16 copies, same
-// workspace layout as the per-layer path, so the backward kernels are unchanged).
 #pragma once
 #include "tc_common.cuh"
 
@@ -32,9 +36,10 @@ constexpr uint32_t CH_W_STAGE_BYTES = 256 * 128;            // one streamed weig
 constexpr uint32_t CH_W_STAGES = 3;
 constexpr uint32_t CH_MAX_LAYERS = SDFG_MAX_FILM + 1;
 constexpr uint32_t CH_MAX_MAPS = SDFG_MAX_FILM;
-constexpr uint32_t CH_THREADS = 384;                        // warp 0 TMA, 1 MMA, 2 loader, 3 spare, 4..11 epilogue
-constexpr uint32_t CH_EPI_WARP0 = 4;
-constexpr uint32_t CH_EPI_THREADS = 256;
+constexpr uint32_t CH_EPI_WARPS = 16;
+constexpr uint32_t CH_EPI_THREADS = CH_EPI_WARPS * 32;
+constexpr uint32_t CH_WARP_TMA = 16, CH_WARP_MMA = 17, CH_WARP_LOAD = 18, CH_WARP_STORE = 19;
+constexpr uint32_t CH_THREADS = 640;
 
 struct ChainLayer {
     uint32_t has_main;          // K = 256 part: A = ACT, B streamed through the ring with tensor map `tm`
@@ -42,17 +47,15 @@ struct ChainLayer {
     uint32_t small_k0, small_nk;   // K-steps [small_k0, small_k0 + small_nk) of SMALL / WSMALL (0 = none)
     uint32_t act;               // 1: FiLM + sin, 0: linear
     uint32_t film;              // row of gamma / beta
-    uint32_t to_act;            // write the fp16 output into ACT (input of the next layer)
+    uint32_t to_act;            // write the fp16 output into ACT (input of the next layer and / or source of the TMA store)
+    uint32_t store;             // SAVE: TMA-store the output with tensor map stores.m[layer]
     uint32_t nh;                // head rows: out_head[row*nh + c] = sum_n h[row,n] * head_w[c*256 + n] + head_b[c]
+    uint32_t pad;
     const float* bias;          // [256]
     const float* head_w;
     const float* head_b;
     float* out_head;
-    uint16_t* out16;            // optional copies of the output in HBM: fp16, bf16, fp32
-    int64_t ld_out;
-    uint16_t* out16b;
-    int64_t ld_out_b;
-    float* out_f32;
+    float* out_f32;             // optional fp32 copy of the output in HBM
     int64_t ld_out_f32;
 };
 
@@ -68,22 +71,20 @@ struct ChainParams {
     const float* gamma;         // + img * gstride + film * 256 + n
     const float* beta;
     int64_t gstride;
-    uint16_t* x16;              // save: fp16 / bf16 copies of x, [M, kp_x] zero padded (NULL ok)
-    uint16_t* x16b;
+    uint16_t* x16;              // SAVE: fp16 copy of x, [M, kp_x] zero padded (NULL ok)
     uint32_t kp_x, kp_v;
-    uint16_t* v16;              // save: view part expanded per sample, kp_v columns, fp16 / bf16 (NULL ok)
+    uint16_t* v16;              // SAVE: view part expanded per sample, kp_v columns (NULL ok)
     int64_t ld_v16;
-    uint16_t* v16b;
-    int64_t ld_v16b;
     unsigned long long* dbg;    // debugging: per-role (tag, clock) event log of CTA 0, 4 x 2048 entries (NULL = off)
     ChainLayer layer[CH_MAX_LAYERS];
 };
 
 struct alignas(64) ChainMaps { CUtensorMap m[CH_MAX_MAPS]; };
+struct alignas(64) ChainStoreMaps { CUtensorMap m[CH_MAX_LAYERS]; };
 
 struct ChainSmem {
     uint64_t w_full[CH_W_STAGES], w_empty[CH_W_STAGES];
-    uint64_t act_ready[4];
+    uint64_t act_ready[4], fin_ready[4], st_done[4];   // fin_ready: chunks of the LAST layer's output (consumed by the storer only)
     uint64_t acc_full[2], acc_empty[2];
     uint64_t x_full, x_free, v_full, v_free;
     uint32_t tmem_base;
@@ -91,7 +92,7 @@ struct ChainSmem {
     alignas(16) float gam[2][256];      // double-buffered per-layer FiLM constants: gamma, gamma*bias + beta
     float cst[2][256];
     float heads[4][256];                // row 0: first head layer (sdf), rows 1..3: second head layer (rgb)
-    float hx[CH_TILE_M][4];             // head partial sums of the second column group
+    float hx[3][CH_TILE_M][4];          // head partial sums of column sub-blocks 1..3
 };
 
 __host__ __device__ inline uint32_t chain_smem_bytes() {
@@ -111,10 +112,15 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
 }
 __device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
-// 8 consecutive fp32 (bounds-checked against n_valid) -> 8 fp16 / bf16 packed in a uint4
+// 8 consecutive fp32 (bounds-checked against n_valid) -> registers; fast path when all 8 are in range and 16-byte aligned
 __device__ __forceinline__ void load8(const float* src, uint32_t k0, uint32_t n_valid, float (&v)[8]) {
+    if (k0 + 8 <= n_valid && ((reinterpret_cast<uintptr_t>(src + k0) & 15) == 0)) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src + k0)), b = __ldg(reinterpret_cast<const float4*>(src + k0) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
 #pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = (k0 + i < n_valid) ? __ldg(src + k0 + i) : 0.f;
+        for (int i = 0; i < 8; i++) v[i] = (k0 + i < n_valid) ? __ldg(src + k0 + i) : 0.f;
+    }
 }
 __device__ __forceinline__ uint4 pack8(const float (&v)[8], uint32_t fmt) {
     return make_uint4(pack16(v[0], v[1], fmt), pack16(v[2], v[3], fmt), pack16(v[4], v[5], fmt), pack16(v[6], v[7], fmt));
@@ -129,8 +135,9 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8], uint32_t fmt) {
         }                                                                                                   \
     } while (0)
 
+template <bool SAVE>
 __global__ void __launch_bounds__(CH_THREADS, 1)
-tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainParams P) {
+tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainStoreMaps stores, const __grid_constant__ ChainParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smACT = smem;
@@ -147,15 +154,17 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
 
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < CH_W_STAGES; i++) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
-        for (uint32_t i = 0; i < 4; i++) mbar_init(&S.act_ready[i], CH_EPI_THREADS / 32);
-        for (uint32_t i = 0; i < 2; i++) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], CH_EPI_THREADS / 32); }
+        for (uint32_t i = 0; i < 4; i++) { mbar_init(&S.act_ready[i], CH_EPI_WARPS); mbar_init(&S.fin_ready[i], CH_EPI_WARPS); mbar_init(&S.st_done[i], 1); }
+        for (uint32_t i = 0; i < 2; i++) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], CH_EPI_WARPS); }
         mbar_init(&S.x_full, 1); mbar_init(&S.x_free, 1); mbar_init(&S.v_full, 1); mbar_init(&S.v_free, 1);
         fence_barrier_init();
     }
-    if (warp == 0 && lane == 0)
-        for (uint32_t i = 0; i < nL; i++)
+    if (warp == CH_WARP_TMA && lane == 0)
+        for (uint32_t i = 0; i < nL; i++) {
             if (P.layer[i].has_main) tma_prefetch_desc(&maps.m[P.layer[i].tm]);
-    if (warp == 1) tmem_alloc(&S.tmem_base, 512);
+            if (SAVE && P.layer[i].store) tma_prefetch_desc(&stores.m[i]);
+        }
+    if (warp == CH_WARP_MMA) tmem_alloc(&S.tmem_base, 512);
     // resident small weights: K-steps [0, x_nk) = layer 0, [x_nk, x_nk + v_nk) = view columns of the last layer; head vectors
     {
         const uint32_t units = 2 * (P.x_nk + P.v_nk);
@@ -168,9 +177,9 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
         }
         uint32_t hrow = 0;
         for (uint32_t i = 0; i < nL; i++) {
-            const ChainLayer& Ly = P.layer[i];
-            for (uint32_t k = threadIdx.x; k < Ly.nh * 256 && hrow + Ly.nh <= 4; k += blockDim.x) S.heads[hrow + k / 256][k % 256] = __ldg(Ly.head_w + k);
-            hrow += Ly.nh;
+            const uint32_t nh = P.layer[i].nh;
+            for (uint32_t k = threadIdx.x; k < nh * 256 && hrow + nh <= 4; k += blockDim.x) S.heads[hrow + k / 256][k % 256] = __ldg(P.layer[i].head_w + k);
+            hrow += nh;
         }
         // zero the activation-side small tile once (its padding columns are never written again)
         for (uint32_t i = threadIdx.x; i < CH_CHUNK_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(smSMALL)[i] = make_uint4(0, 0, 0, 0);
@@ -181,7 +190,7 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = S.tmem_base;
 
-    if (warp == 0) {
+    if (warp == CH_WARP_TMA) {
         // ===================================================== TMA producer: weight chunks of the K = 256 layers
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
@@ -198,7 +207,7 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                     }
                 }
         }
-    } else if (warp == 1) {
+    } else if (warp == CH_WARP_MMA) {
         // ===================================================== MMA issuer
         if (lane == 0) {
             const uint32_t idesc = idesc_f16(CH_TILE_M, 256, FMT_F16, FMT_F16, 0, 0);
@@ -206,20 +215,20 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
             uint32_t stage = 0, phase = 0, n = 0, actgen = 0, it = 0;
             for (uint32_t t = t_begin; t < t_end; t++, it++)
                 for (uint32_t i = 0; i < nL; i++, n++) {
-                    const ChainLayer& Ly = P.layer[i];
+                    const uint32_t has_main = P.layer[i].has_main, sk0 = P.layer[i].small_k0, snk = P.layer[i].small_nk;
                     const uint32_t acc = n & 1, use = n >> 1;
                     mbar_wait(&S.acc_empty[acc], (use & 1) ^ 1);          // the epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + acc * 256;
                     uint32_t accumulate = 0;
-                    if (Ly.small_nk && i == 0) {                          // x part
+                    if (snk && i == 0) {                                  // x part
                         mbar_wait(&S.x_full, it & 1);
                         tc_fence_after();
-                        for (uint32_t s = Ly.small_k0; s < Ly.small_k0 + Ly.small_nk; s++, accumulate = 1)
+                        for (uint32_t s = sk0; s < sk0 + snk; s++, accumulate = 1)
                             umma_bf16(tmem_d, smem_desc_sw128(a_small + s * 32, 16, 1024), smem_desc_sw128(b_small + s * 32, 16, 1024), idesc, accumulate);
                         umma_commit(&S.x_free);
                     }
-                    if (Ly.has_main) {
+                    if (has_main) {
                         for (uint32_t kc = 0; kc < 4; kc++) {
                             mbar_wait(&S.act_ready[kc], actgen & 1);      // chunk kc of the previous layer's output is in ACT
                             CH_DBG(0, 100 + i * 16 + kc);
@@ -235,124 +244,159 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                         }
                         actgen++;
                     }
-                    if (Ly.small_nk && i != 0) {                          // view part
+                    if (snk && i != 0) {                                  // view part
                         mbar_wait(&S.v_full, it & 1);
                         tc_fence_after();
-                        for (uint32_t s = Ly.small_k0; s < Ly.small_k0 + Ly.small_nk; s++, accumulate = 1)
+                        for (uint32_t s = sk0; s < sk0 + snk; s++, accumulate = 1)
                             umma_bf16(tmem_d, smem_desc_sw128(a_small + s * 32, 16, 1024), smem_desc_sw128(b_small + s * 32, 16, 1024), idesc, accumulate);
                         umma_commit(&S.v_free);
                     }
                     umma_commit(&S.acc_full[acc]);
                 }
         }
-    } else if (warp == 2) {
-        // ===================================================== loader: x / view parts of the tile -> SMALL (+ 16-bit copies in HBM)
+    } else if (warp == CH_WARP_LOAD) {
+        // ===================================================== loader: x / view parts of the tile -> SMALL (+ fp16 copies in HBM)
         const uint32_t xu = 2 * P.x_nk, vu = 2 * P.v_nk;               // 16-byte units per row
-        uint32_t it = 0;
-        for (uint32_t t = t_begin; t < t_end; t++, it++) {
-            const uint64_t row0 = (uint64_t)t * CH_TILE_M;
-            mbar_wait(&S.x_free, (it & 1) ^ 1);
-            if (lane == 0) CH_DBG(2, 1);
-            for (uint32_t i = lane; i < CH_TILE_M * xu; i += 32) {
-                const uint32_t r = i / xu, u = i % xu;
-                const uint64_t row = row0 + r;
-                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (row < P.M_total) load8(P.x_in + row * P.in_dim, u * 8, P.in_dim, v);
-                const uint4 h = pack8(v, FMT_F16);
-                *reinterpret_cast<uint4*>(smSMALL + sw128(r, u)) = h;
-                if (row < P.M_total && u * 8 < P.kp_x) {
-                    if (P.x16) *reinterpret_cast<uint4*>(P.x16 + row * P.kp_x + u * 8) = h;
-                    if (P.x16b) *reinterpret_cast<uint4*>(P.x16b + row * P.kp_x + u * 8) = pack8(v, FMT_BF16);
+        // fast path: every unit is 8 in-range, 16-byte aligned floats -> the loads of 4 units are issued before any is used
+        const bool x_fast = P.in_dim % 8 == 0 && (reinterpret_cast<uintptr_t>(P.x_in) & 15) == 0;
+        const bool v_fast = vu && P.view_dim % 8 == 0 && (reinterpret_cast<uintptr_t>(P.view_feat) & 15) == 0;
+        auto fill = [&](const float* src, uint32_t src_ld, uint32_t src_div, uint32_t n_valid, bool fast, uint32_t nu, uint32_t u_off,
+                        uint32_t row0, uint16_t* copy, uint64_t copy_ld, uint32_t copy_cols) {
+            const uint32_t total = CH_TILE_M * nu;
+            for (uint32_t base = 0; base < total; base += 128) {
+                float v[4][8];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t i = min(base + j * 32 + lane, total - 1);
+                    const uint32_t r = i / nu, u = i % nu;
+                    const uint32_t row = min(row0 + r, P.M_total - 1);
+                    const float* sp = src + (uint64_t)(row / src_div) * src_ld;
+                    if (fast) {
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(sp + u * 8)), b = __ldg(reinterpret_cast<const float4*>(sp + u * 8) + 1);
+                        v[j][0] = a.x; v[j][1] = a.y; v[j][2] = a.z; v[j][3] = a.w; v[j][4] = b.x; v[j][5] = b.y; v[j][6] = b.z; v[j][7] = b.w;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; k++) v[j][k] = (u * 8 + k < n_valid) ? __ldg(sp + u * 8 + k) : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t i = base + j * 32 + lane;
+                    if (i < total) {
+                        const uint32_t r = i / nu, u = i % nu;
+                        const uint32_t row = row0 + r;
+                        const uint4 h = pack8(v[j], FMT_F16);
+                        *reinterpret_cast<uint4*>(smSMALL + sw128(r, u_off + u)) = h;
+                        if (SAVE && copy && row < P.M_total && u * 8 < copy_cols) *reinterpret_cast<uint4*>(copy + (uint64_t)row * copy_ld + u * 8) = h;
+                    }
                 }
             }
+        };
+        uint32_t it = 0;
+        for (uint32_t t = t_begin; t < t_end; t++, it++) {
+            const uint32_t row0 = t * CH_TILE_M;
+            mbar_wait(&S.x_free, (it & 1) ^ 1);
+            if (lane == 0) CH_DBG(2, 1);
+            fill(P.x_in, P.in_dim, 1, P.in_dim, x_fast, xu, 0, row0, P.x16, P.kp_x, P.kp_x);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) { mbar_arrive(&S.x_full); CH_DBG(2, 2); }
             if (vu) {
                 mbar_wait(&S.v_free, (it & 1) ^ 1);
-                for (uint32_t i = lane; i < CH_TILE_M * vu; i += 32) {
-                    const uint32_t r = i / vu, u = i % vu;
-                    const uint64_t row = row0 + r;
-                    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (row < P.M_total) load8(P.view_feat + (row / P.rows_per_ray) * P.view_dim, u * 8, P.view_dim, v);
-                    const uint4 h = pack8(v, FMT_F16);
-                    *reinterpret_cast<uint4*>(smSMALL + sw128(r, xu + u)) = h;
-                    if (row < P.M_total && u * 8 < P.kp_v) {
-                        if (P.v16) *reinterpret_cast<uint4*>(P.v16 + row * P.ld_v16 + u * 8) = h;
-                        if (P.v16b) *reinterpret_cast<uint4*>(P.v16b + row * P.ld_v16b + u * 8) = pack8(v, FMT_BF16);
-                    }
-                }
+                fill(P.view_feat, P.view_dim, P.rows_per_ray, P.view_dim, v_fast, vu, xu, row0, P.v16, (uint64_t)P.ld_v16, P.kp_v);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(&S.v_full); CH_DBG(2, 3); }
             }
         }
-    } else if (warp >= CH_EPI_WARP0) {
-        // ===================================================== epilogue: 8 warps, 2 per TMEM lane quarter
+    } else if (warp == CH_WARP_STORE) {
+        // ===================================================== storer (SAVE): finished ACT chunks -> saved activations in HBM
+        if (SAVE && lane == 0) {
+            uint32_t actgen = 0, fingen = 0;
+            for (uint32_t t = t_begin; t < t_end; t++)
+                for (uint32_t i = 0; i < nL; i++) {
+                    if (!P.layer[i].to_act) continue;
+                    const bool st = P.layer[i].store != 0, fin = i + 1 == nL;
+                    for (uint32_t c = 0; c < 4; c++) {
+                        if (fin) mbar_wait(&S.fin_ready[c], fingen & 1);
+                        else mbar_wait(&S.act_ready[c], actgen & 1);
+                        if (st) {
+                            tma_store_2d(&stores.m[i], smACT + c * CH_CHUNK_BYTES, (int32_t)(c * 64), (int32_t)(t * CH_TILE_M));
+                            tma_store_commit();
+                            tma_store_wait_read();
+                        }
+                        mbar_arrive(&S.st_done[c]);                       // the chunk may be overwritten
+                    }
+                    if (fin) fingen++; else actgen++;
+                }
+            tma_store_wait_all();
+        }
+    } else {
+        // ===================================================== epilogue: 16 warps, 4 per TMEM lane quarter
         const uint32_t q = warp & 3;                                   // TMEM lane quarter this warp may access
-        const uint32_t g = (warp - CH_EPI_WARP0) >> 2;                 // column group: 32-column half of every 64-column chunk
-        const uint32_t etid = (warp - CH_EPI_WARP0) * 32 + lane;       // 0..255 = the column this thread prepares constants for
+        const uint32_t sb = warp >> 2;                                 // 16-column sub-block of every 64-column chunk
+        const uint32_t etid = threadIdx.x;                             // 0..511
         const uint32_t r = q * 32 + lane;                              // row of the tile = TMEM lane
-        uint32_t n = 0;
+        const uint32_t act_row = smem_u32(smACT) + r * 128;
+        const uint32_t u0 = ((2 * sb) ^ (r & 7)) << 4, u1 = ((2 * sb + 1) ^ (r & 7)) << 4;
+        uint32_t n = 0, stgen = 0;
         for (uint32_t t = t_begin; t < t_end; t++) {
             const uint64_t row = (uint64_t)t * CH_TILE_M + r;
             const bool valid = row < P.M_total;
-            const uint32_t img = (uint32_t)(((uint64_t)t * CH_TILE_M) / P.rows_per_image);
+            const uint32_t img = (t * CH_TILE_M) / P.rows_per_image;
             uint32_t hrow = 0;
             for (uint32_t i = 0; i < nL; i++, n++) {
                 // layer description -> registers (constant-bank reads with a dynamic index are slow inside the chunk loop)
                 const uint32_t L_act = P.layer[i].act, L_nh = P.layer[i].nh, L_to_act = P.layer[i].to_act, L_film = P.layer[i].film;
-                uint16_t* const o16 = P.layer[i].out16;
-                uint16_t* const o16b = P.layer[i].out16b;
                 float* const o32 = P.layer[i].out_f32;
-                const int64_t ld16 = P.layer[i].ld_out, ld16b = P.layer[i].ld_out_b, ld32 = P.layer[i].ld_out_f32;
+                const int64_t ld32 = P.layer[i].ld_out_f32;
                 const uint32_t acc = n & 1, use = n >> 1, tb = n & 1;
                 const uint32_t gam_s = smem_u32(&S.gam[tb][0]), cst_s = smem_u32(&S.cst[tb][0]);
-                {   // per-layer FiLM constants for column `etid` (overlaps the MMAs of this layer)
-                    const float b = __ldg(P.layer[i].bias + etid);
-                    float gm = 1.f, cs = b;
-                    if (L_act) {
-                        gm = __ldg(P.gamma + (int64_t)img * P.gstride + L_film * 256 + etid);
-                        cs = fmaf(gm, b, __ldg(P.beta + (int64_t)img * P.gstride + L_film * 256 + etid));
+                {   // per-layer FiLM constants (overlaps the MMAs of this layer): threads 0..255 gamma, 256..511 gamma*bias + beta
+                    const uint32_t col = etid & 255;
+                    float gm = 1.f;
+                    if (L_act) gm = __ldg(P.gamma + (int64_t)img * P.gstride + L_film * 256 + col);
+                    if (etid < 256) sts32(gam_s + col * 4, gm);
+                    else {
+                        const float b = __ldg(P.layer[i].bias + col);
+                        sts32(cst_s + col * 4, L_act ? fmaf(gm, b, __ldg(P.beta + (int64_t)img * P.gstride + L_film * 256 + col)) : b);
                     }
-                    sts32(gam_s + etid * 4, gm);
-                    sts32(cst_s + etid * 4, cs);
                     named_bar_sync(1, CH_EPI_THREADS);
                 }
                 const uint32_t heads_s = smem_u32(&S.heads[hrow][0]);
                 float hacc[3] = {0.f, 0.f, 0.f};
-                if (etid == 0) CH_DBG(1, 300 + i * 16);
+                if (threadIdx.x == 0) CH_DBG(1, 300 + i * 16);
                 mbar_wait(&S.acc_full[acc], use & 1);
                 tc_fence_after();
-                if (etid == 0) CH_DBG(1, 400 + i * 16);
-                const uint32_t taddr = tmem_base + ((q * 32) << 16) + acc * 256;
-                const uint32_t act_row = smem_u32(smACT) + r * 128;
-#pragma unroll 1
-                for (uint32_t c = 0; c < 4; c++) {
-                    const uint32_t col = c * 64 + g * 32;
-                    uint32_t raw[32];
-                    tmem_ld32(taddr + col, raw);
-                    tmem_ld_wait();
-                    float v[32];
+                if (threadIdx.x == 0) CH_DBG(1, 400 + i * 16);
+                const uint32_t taddr = tmem_base + ((q * 32) << 16) + acc * 256 + sb * 16;
+                uint32_t raw[2][16];
+                tmem_ld16_issue(taddr, raw[0]);
 #pragma unroll
-                    for (int k = 0; k < 32; k += 4) {
+                for (uint32_t c = 0; c < 4; c++) {
+                    const uint32_t col = c * 64 + sb * 16;
+                    tmem_ld_wait16(raw[c & 1]);
+                    if (c < 3) tmem_ld16_issue(taddr + (c + 1) * 64, raw[(c + 1) & 1]);
+                    float v[16];
+#pragma unroll
+                    for (int k = 0; k < 16; k += 4) {
                         const float4 g4 = lds128(gam_s + (col + k) * 4);
                         const float4 c4 = lds128(cst_s + (col + k) * 4);
-                        v[k] = fmaf(__uint_as_float(raw[k]), g4.x, c4.x);
-                        v[k + 1] = fmaf(__uint_as_float(raw[k + 1]), g4.y, c4.y);
-                        v[k + 2] = fmaf(__uint_as_float(raw[k + 2]), g4.z, c4.z);
-                        v[k + 3] = fmaf(__uint_as_float(raw[k + 3]), g4.w, c4.w);
+                        v[k] = fmaf(__uint_as_float(raw[c & 1][k]), g4.x, c4.x);
+                        v[k + 1] = fmaf(__uint_as_float(raw[c & 1][k + 1]), g4.y, c4.y);
+                        v[k + 2] = fmaf(__uint_as_float(raw[c & 1][k + 2]), g4.z, c4.z);
+                        v[k + 3] = fmaf(__uint_as_float(raw[c & 1][k + 3]), g4.w, c4.w);
                     }
                     if (L_act) {
 #pragma unroll
-                        for (int k = 0; k < 32; k++) v[k] = __sinf(v[k]);
+                        for (int k = 0; k < 16; k++) v[k] = __sinf(v[k]);
                     }
                     if (L_nh) {
 #pragma unroll
                         for (int hd = 0; hd < 3; hd++) {
                             if ((uint32_t)hd < L_nh) {
 #pragma unroll
-                                for (int k = 0; k < 32; k += 4) {
+                                for (int k = 0; k < 16; k += 4) {
                                     const float4 w4 = lds128(heads_s + (hd * 256 + col + k) * 4);
                                     hacc[hd] = fmaf(v[k], w4.x, hacc[hd]); hacc[hd] = fmaf(v[k + 1], w4.y, hacc[hd]);
                                     hacc[hd] = fmaf(v[k + 2], w4.z, hacc[hd]); hacc[hd] = fmaf(v[k + 3], w4.w, hacc[hd]);
@@ -360,56 +404,41 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                             }
                         }
                     }
-                    uint4 h16[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        h16[j] = make_uint4(pack_f16(v[j * 8], v[j * 8 + 1]), pack_f16(v[j * 8 + 2], v[j * 8 + 3]),
-                                            pack_f16(v[j * 8 + 4], v[j * 8 + 5]), pack_f16(v[j * 8 + 6], v[j * 8 + 7]));
                     if (L_to_act) {
+                        const uint4 h0 = make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
+                        const uint4 h1 = make_uint4(pack_f16(v[8], v[9]), pack_f16(v[10], v[11]), pack_f16(v[12], v[13]), pack_f16(v[14], v[15]));
+                        if (SAVE) mbar_wait(&S.st_done[c], (stgen & 1) ^ 1);   // the previous contents of the chunk have been stored
                         const uint32_t chunk = act_row + c * CH_CHUNK_BYTES;
-#pragma unroll
-                        for (int j = 0; j < 4; j++) sts128(chunk + (((g * 4 + j) ^ (r & 7)) << 4), h16[j]);
+                        sts128(chunk + u0, h0);
+                        sts128(chunk + u1, h1);
                         fence_proxy_async();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&S.act_ready[c]);
-                        if (etid == 0) CH_DBG(1, 500 + i * 16 + c);
+                        if (lane == 0) mbar_arrive(i + 1 == nL ? &S.fin_ready[c] : &S.act_ready[c]);
+                        if (threadIdx.x == 0) CH_DBG(1, 500 + i * 16 + c);
                     }
-                    if (valid) {
-                        if (o16) {
-                            uint4* dst = reinterpret_cast<uint4*>(o16 + row * ld16 + col);
+                    if (o32 && valid) {
+                        float4* dst = reinterpret_cast<float4*>(o32 + row * ld32 + col);
 #pragma unroll
-                            for (int j = 0; j < 4; j++) dst[j] = h16[j];
-                        }
-                        if (o16b) {
-                            uint4* dst = reinterpret_cast<uint4*>(o16b + row * ld16b + col);
-#pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                dst[j] = make_uint4(pack_bf16(v[j * 8], v[j * 8 + 1]), pack_bf16(v[j * 8 + 2], v[j * 8 + 3]),
-                                                    pack_bf16(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16(v[j * 8 + 6], v[j * 8 + 7]));
-                        }
-                        if (o32) {
-                            float4* dst = reinterpret_cast<float4*>(o32 + row * ld32 + col);
-#pragma unroll
-                            for (int j = 0; j < 8; j++) dst[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
-                        }
+                        for (int j = 0; j < 4; j++) dst[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
                     }
                 }
+                if (L_to_act) stgen++;
                 // every TMEM read of this layer has completed (wait::ld): hand the accumulator back to the MMA thread
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.acc_empty[acc]);
-                if (L_nh) {                                             // combine the two column groups' partial dot products
-                    if (g == 1) {
+                if (L_nh) {                                             // combine the four sub-blocks' partial dot products
+                    if (sb != 0) {
 #pragma unroll
-                        for (int hd = 0; hd < 3; hd++) S.hx[r][hd] = hacc[hd];
+                        for (int hd = 0; hd < 3; hd++) S.hx[sb - 1][r][hd] = hacc[hd];
                     }
                     named_bar_sync(2, CH_EPI_THREADS);
-                    if (g == 0 && valid) {
+                    if (sb == 0 && valid) {
                         float* oh = P.layer[i].out_head;
                         const float* hb = P.layer[i].head_b;
 #pragma unroll
                         for (int hd = 0; hd < 3; hd++)
-                            if ((uint32_t)hd < L_nh) oh[row * L_nh + hd] = hacc[hd] + S.hx[r][hd] + __ldg(hb + hd);
+                            if ((uint32_t)hd < L_nh) oh[row * L_nh + hd] = hacc[hd] + S.hx[0][r][hd] + S.hx[1][r][hd] + S.hx[2][r][hd] + __ldg(hb + hd);
                     }
                     hrow += L_nh;
                 }
@@ -419,7 +448,7 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
     // teardown: the epilogue consumed the last accumulator, so every MMA and TMA load issued has completed
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == CH_WARP_MMA) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace tc
