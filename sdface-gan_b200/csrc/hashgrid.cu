@@ -257,17 +257,20 @@ __global__ void __launch_bounds__(256) grid_backward_kernel(const float* __restr
                                                             uint32_t N, uint32_t L, float S, uint32_t H, float bound,
                                                             uint32_t gridtype, int align_corners, uint32_t interp,
                                                             int grad_layout) {
-    __shared__ LevelInfo li_s;
-    const uint32_t level = blockIdx.y;
-    if (threadIdx.x == 0) fill_level_info<D>(li_s, level, offsets, S, H, gridtype, align_corners);
+    // One thread per sample walks every level: the sample's gradient row (L*C floats, one or two cache lines) and its
+    // coordinates are fetched from HBM once -- with a thread per (sample, level) every level pass re-read whole sectors of the
+    // [N, L*C] gradient (16 x 400 MB at the benchmark size) and evicted the table gradient from L2.
+    __shared__ LevelInfo li_all[kMaxLevels];
+    if (threadIdx.x < L) fill_level_info<D>(li_all[threadIdx.x], threadIdx.x, offsets, S, H, gridtype, align_corners);
     __syncthreads();
-    const LevelInfo li = li_s;
     const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     float u[D];
 #pragma unroll
     for (uint32_t d = 0; d < D; d++) u[d] = 0.f;
     const bool active = n < N && load_unit<D>(inputs, n, bound, u);
+    for (uint32_t level = 0; level < L; level++) {
+    const LevelInfo li = li_all[level];
     Feat<C> g;
 #pragma unroll
     for (uint32_t c = 0; c < C; c++) g.v[c] = 0.f;
@@ -282,22 +285,22 @@ __global__ void __launch_bounds__(256) grid_backward_kernel(const float* __restr
     // Coarse levels: consecutive samples of a ray share cells, so a warp would hammer a handful of addresses (the L2 atomic
     // unit serialises per address).  Runs of adjacent lanes with the same row are summed with a segmented shuffle reduction and
     // only the run head issues the reduction.  Fine levels (about one sample per cell) scatter directly.
-    const bool aggregate = li.scale <= 1024.f;
+    const bool aggregate = li.scale <= 64.f;      // cell >= the sample spacing along a ray (1/48 of the unit cube at 24 samples per ray)
+    if (aggregate) {
 #pragma unroll
-    for (uint32_t idx = 0; idx < (1u << D); idx++) {
-        float w = 1.f;
-        uint32_t gl[D];
+        for (uint32_t idx = 0; idx < (1u << D); idx++) {
+            float w = 1.f;
+            uint32_t gl[D];
 #pragma unroll
-        for (uint32_t d = 0; d < D; d++) {
-            const uint32_t bit = (idx >> d) & 1u;
-            w *= bit ? f[d] : 1.f - f[d];
-            gl[d] = cell[d] + bit;
-        }
-        float v[C];
+            for (uint32_t d = 0; d < D; d++) {
+                const uint32_t bit = (idx >> d) & 1u;
+                w *= bit ? f[d] : 1.f - f[d];
+                gl[d] = cell[d] + bit;
+            }
+            float v[C];
 #pragma unroll
-        for (uint32_t c = 0; c < C; c++) v[c] = w * g.v[c];
-        const uint32_t row = active ? corner_row<D>(li, gl) : 0xFFFFFFFFu;
-        if (aggregate) {
+            for (uint32_t c = 0; c < C; c++) v[c] = w * g.v[c];
+            const uint32_t row = active ? corner_row<D>(li, gl) : 0xFFFFFFFFu;
             const uint32_t prev = __shfl_up_sync(0xffffffffu, row, 1);
             const bool head = lane == 0 || row != prev;
             const uint32_t heads = __ballot_sync(0xffffffffu, head);
@@ -312,10 +315,38 @@ __global__ void __launch_bounds__(256) grid_backward_kernel(const float* __restr
                 }
             }
             if (head && active) red_feat<C>(gt + (size_t)row * C, v);
-        } else if (active) {
-            red_feat<C>(gt + (size_t)row * C, v);
+        }
+    } else if (active) {
+        // Fine levels scatter directly.  The two corners along x of a pair are adjacent table rows whenever the lower one is even
+        // (dense: stride 1 in x; hashed: x enters the hash with prime 1, so x|1 only flips bit 0 of the row) -> one 16-byte
+        // reduction instead of two 8-byte ones: the LSU issues reductions per lane, not per byte.
+#pragma unroll
+        for (uint32_t idx = 0; idx < (1u << D); idx += 2) {
+            float w0 = 1.f - f[0], w1 = f[0];                      // same multiplication order as the reference (d = 0 first)
+            uint32_t gl[D];
+            gl[0] = cell[0];
+#pragma unroll
+            for (uint32_t d = 1; d < D; d++) {
+                const uint32_t bit = (idx >> d) & 1u;
+                const float wd = bit ? f[d] : 1.f - f[d];
+                w0 *= wd;
+                w1 *= wd;
+                gl[d] = cell[d] + bit;
+            }
+            const uint32_t r0 = corner_row<D>(li, gl);
+            gl[0] = cell[0] + 1;
+            const uint32_t r1 = corner_row<D>(li, gl);
+            float v0[C], v1[C];
+#pragma unroll
+            for (uint32_t c = 0; c < C; c++) { v0[c] = w0 * g.v[c]; v1[c] = w1 * g.v[c]; }
+            if constexpr (C == 2) {
+                if (r1 == r0 + 1 && (r0 & 1u) == 0) { red_add_v4(gt + (size_t)r0 * 2, v0[0], v0[1], v1[0], v1[1]); continue; }
+            }
+            red_feat<C>(gt + (size_t)r0 * C, v0);
+            red_feat<C>(gt + (size_t)r1 * C, v1);
         }
     }
+    }   // levels
 }
 
 // grad_inputs[n,d] = sum_{l,c} grad[n,l,c] * dy_dx[n,l,d,c]  (/ (2*bound) when the affine map was folded in)
@@ -449,7 +480,7 @@ static int launch_backward(const float* grad, const float* inputs, const int* of
                            float S, uint32_t H, float bound, const float* dy_dx, float* grad_inputs, uint32_t gridtype,
                            int align_corners, uint32_t interp, int grad_layout, cudaStream_t st) {
     if (grad_table) {
-        const dim3 grid(ceil_div<uint32_t>(N, 256), L);
+        const dim3 grid(ceil_div<uint32_t>(N, 256), 1);
         grid_backward_kernel<D, C><<<grid, 256, 0, st>>>(grad, inputs, offsets, grad_table, N, L, S, H, bound, gridtype,
                                                          align_corners, interp, grad_layout);
         if (int e = check_launch("grid_backward_kernel")) return e;
