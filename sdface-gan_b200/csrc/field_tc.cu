@@ -367,28 +367,44 @@ __global__ void __launch_bounds__(128) wgrad_finish_kernel(const float* __restri
     if (threadIdx.x == 0) db[j] += dbj;
 }
 
-// head weight gradient: dw[c, k] += sum_n dout[n, c] * h[n, k]   (h fp16, pitch ld), db[c] += sum_n dout[n, c];  block = 256 columns
+// head weight gradient: dw[c, k] += sum_n dout[n, c] * h[n, k]   (h fp16, pitch ld), db[c] += sum_n dout[n, c].
+// Block = 256 columns x 2 row groups: a thread owns a column PAIR (one 4-byte load per row) and every other row; 8 rows are in
+// flight per thread so the fp16 stream runs at HBM speed (512 B per sample).
 template <int NOUT>
 __global__ void __launch_bounds__(256) head_wgrad16_kernel(const float* __restrict__ dout, const h16* __restrict__ h, int64_t ld,
                                                             float* __restrict__ dw, float* __restrict__ db, uint64_t M, uint32_t rows_per_block) {
-    const uint32_t k = threadIdx.x;
+    const uint32_t cp = threadIdx.x & 127, rg = threadIdx.x >> 7;
     const uint64_t m0 = (uint64_t)blockIdx.x * rows_per_block, m1 = min(M, m0 + rows_per_block);
-    float gw[NOUT], gb[NOUT];
+    float gw0[NOUT], gw1[NOUT], gb[NOUT];
 #pragma unroll
-    for (int c = 0; c < NOUT; c++) { gw[c] = 0.f; gb[c] = 0.f; }
-    for (uint64_t m = m0; m < m1; m++) {
-        const float hv = __half2float(__ushort_as_half(h[m * ld + k]));
+    for (int c = 0; c < NOUT; c++) { gw0[c] = 0.f; gw1[c] = 0.f; gb[c] = 0.f; }
+    constexpr int U = 8;
+    for (uint64_t m = m0 + rg; m < m1; m += 2 * U) {
+        uint32_t hv[U];
+        float d[U][NOUT];
 #pragma unroll
-        for (int c = 0; c < NOUT; c++) {
-            const float d = __ldg(dout + m * NOUT + c);
-            gw[c] = fmaf(d, hv, gw[c]);
-            gb[c] += d;
+        for (int j = 0; j < U; j++) {
+            const uint64_t mm = m + 2 * j;
+            const bool ok = mm < m1;
+            hv[j] = ok ? __ldg(reinterpret_cast<const uint32_t*>(h + mm * ld) + cp) : 0u;
+#pragma unroll
+            for (int c = 0; c < NOUT; c++) d[j][c] = ok ? __ldg(dout + mm * NOUT + c) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const float2 f = tc::unpack_f16(hv[j]);
+#pragma unroll
+            for (int c = 0; c < NOUT; c++) {
+                gw0[c] = fmaf(d[j][c], f.x, gw0[c]);
+                gw1[c] = fmaf(d[j][c], f.y, gw1[c]);
+                gb[c] += d[j][c];
+            }
         }
     }
 #pragma unroll
     for (int c = 0; c < NOUT; c++) {
-        red_add_f32(dw + (size_t)c * 256 + k, gw[c]);
-        if (k == 0) red_add_f32(db + c, gb[c]);
+        red_add_v2(dw + (size_t)c * 256 + 2 * cp, gw0[c], gw1[c]);
+        if (cp == 0) red_add_f32(db + c, gb[c]);
     }
 }
 
@@ -582,11 +598,11 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         if (!g) return SDFG_OK;
         // ---- parameter gradients from the stored du tiles (sample-axis contractions) and the fp32 head gradients
         if (views && g->rgb_w && d_rgb) {
-            head_wgrad16_kernel<3><<<(unsigned)ceil_div<uint64_t>(N, 512), 256, 0, st>>>(d_rgb, (const h16*)(ws + L.off_hv), W, g->rgb_w, g->rgb_b, N, 512);
+            head_wgrad16_kernel<3><<<(unsigned)ceil_div<uint64_t>(N, 2048), 256, 0, st>>>(d_rgb, (const h16*)(ws + L.off_hv), W, g->rgb_w, g->rgb_b, N, 2048);
             if (int e = check_launch("head_wgrad16_kernel<3>")) return e;
         }
         if (g->sigma_w && d_sdf) {
-            head_wgrad16_kernel<1><<<(unsigned)ceil_div<uint64_t>(N, 512), 256, 0, st>>>(d_sdf, A(nf), L.Kp_v, g->sigma_w, g->sigma_b, N, 512);
+            head_wgrad16_kernel<1><<<(unsigned)ceil_div<uint64_t>(N, 2048), 256, 0, st>>>(d_sdf, A(nf), L.Kp_v, g->sigma_w, g->sigma_b, N, 2048);
             if (int e = check_launch("head_wgrad16_kernel<1>")) return e;
         }
         for (int l = views ? (int)nf : (int)nf - 1; l >= 0; l--) {
@@ -646,7 +662,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
     if (d_rgb || d_feat) {
         if (int e = run_R(nf, nullptr, d_feat, d_rgb ? 3 : 0, d_rgb, p->rgb_w)) return e;
         if (g && g->rgb_w && d_rgb) {
-            head_wgrad16_kernel<3><<<(unsigned)ceil_div<uint64_t>(N, 512), 256, 0, st>>>(d_rgb, (const h16*)(ws + L.off_hv), W, g->rgb_w, g->rgb_b, N, 512);
+            head_wgrad16_kernel<3><<<(unsigned)ceil_div<uint64_t>(N, 2048), 256, 0, st>>>(d_rgb, (const h16*)(ws + L.off_hv), W, g->rgb_w, g->rgb_b, N, 2048);
             if (int e = check_launch("head_wgrad16_kernel<3>")) return e;
         }
         if (int e = run_W(nf)) return e;
@@ -656,7 +672,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         rank1_sdf = true;
     }
     if (g && g->sigma_w && d_sdf) {
-        head_wgrad16_kernel<1><<<(unsigned)ceil_div<uint64_t>(N, 512), 256, 0, st>>>(d_sdf, h_last, L.Kp_v, g->sigma_w, g->sigma_b, N, 512);
+        head_wgrad16_kernel<1><<<(unsigned)ceil_div<uint64_t>(N, 2048), 256, 0, st>>>(d_sdf, h_last, L.Kp_v, g->sigma_w, g->sigma_b, N, 2048);
         if (int e = check_launch("head_wgrad16_kernel<1>")) return e;
     }
     for (int l = (int)nf - 1; l >= 0; l--) {
