@@ -173,6 +173,13 @@ int sdfg_field_forward(const sdfg_field_params* p, const float* x_in, const floa
                        float* out_sdf, float* out_rgb, float* out_feat, void* workspace, int save_for_backward,
                        int precision, void* stream);
 
+/* inference variant of the tensor-core path (SDFG_PRECISION_TC16 constraints apply): the [N,W] feature output leaves the chip
+ * as fp16 (written by TMA straight from the last layer's operand tile), half the HBM bytes of the fp32 copy; consumed by
+ * sdfg_composite_forward_h.  No save_for_backward.  Replaces the same torch op chain as sdfg_field_forward
+ * (sdf_model.py:1566-1592). */
+int sdfg_field_forward_h(const sdfg_field_params* p, const float* x_in, const float* view_feat, uint64_t N,
+                         float* out_sdf, float* out_rgb, uint16_t* out_feat16, void* workspace, void* stream);
+
 /* backward.  d_sdf [N], d_rgb [N,3], d_feat [N,W] (each NULL = zero; at least one given) -> parameter grads (g NULL =
  * none wanted, e.g. for the eikonal pass) + d_x_in [N,in_dim] (NULL ok).  Reads the workspace written by the matching
  * forward (save_for_backward = 1), `out_feat` = the pointer that forward was given (NULL if none) and uses `scratch`
@@ -207,6 +214,12 @@ int sdfg_composite_forward(const float* sdf, const float* rgb, const float* feat
                            const float* rays_d, const float* pts, const float* noise, const float* sigmoid_beta,
                            uint64_t NR, uint32_t S, uint32_t F, int with_sdf, int force_background,
                            float* rgb_map, float* feat_map, float* xyz_map, float* mask, float* weights, void* stream);
+
+/* same, with fp16 features [NR,S,F] as written by sdfg_field_forward_h (feat16 and feat_map required). */
+int sdfg_composite_forward_h(const float* sdf, const float* rgb, const uint16_t* feat16, const float* z_vals,
+                             const float* rays_d, const float* pts, const float* noise, const float* sigmoid_beta,
+                             uint64_t NR, uint32_t S, uint32_t F, int with_sdf, int force_background,
+                             float* rgb_map, float* feat_map, float* xyz_map, float* mask, float* weights, void* stream);
 
 /* backward of the above wrt sdf, rgb, feat, sigmoid_beta (accumulated into d_sigmoid_beta[0]) and pts (NULL ok).
  * d_* map gradients may be NULL (= zero). */

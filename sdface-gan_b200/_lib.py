@@ -55,12 +55,14 @@ PROTOTYPES = {
     "sdfg_field_workspace_bytes": (u64, [ctypes.POINTER(FieldParams), u64, i32, i32]),
     "sdfg_field_backward_scratch_bytes": (u64, [ctypes.POINTER(FieldParams), u64, i32]),
     "sdfg_field_forward": (i32, [ctypes.POINTER(FieldParams), vp, vp, u64, vp, vp, vp, vp, i32, i32, vp]),
+    "sdfg_field_forward_h": (i32, [ctypes.POINTER(FieldParams), vp, vp, u64, vp, vp, vp, vp, vp]),
     "sdfg_field_backward": (i32, [ctypes.POINTER(FieldParams), ctypes.POINTER(FieldGrads), vp, vp, u64, vp, vp, vp, vp, vp, vp,
                                   vp, i32, vp]),
     "sdfg_tc_linear_probe_workspace_bytes": (u64, [u32, u32, u32]),
     "sdfg_tc_linear_probe": (i32, [vp, vp, vp, u32, u32, u32, vp, vp]),
     "sdfg_tc_wgrad_probe": (i32, [vp, vp, vp, u32, u32, u32, u32, ctypes.POINTER(u32), ctypes.POINTER(u32), vp, vp]),
     "sdfg_composite_forward": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "sdfg_composite_forward_h": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "sdfg_composite_backward": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,
                                       vp, vp]),
 }

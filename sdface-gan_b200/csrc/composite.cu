@@ -76,7 +76,8 @@ __device__ __forceinline__ void ray_weights(const float* __restrict__ sdf, const
     }
 }
 
-template <int KS>
+// FEAT16: `feat` points at fp16 features (the tensor-core field's inference output), 8 bytes per lane and sample instead of 16
+template <int KS, bool FEAT16 = false>
 __global__ void __launch_bounds__(256) composite_forward_kernel(
     const float* __restrict__ sdf, const float* __restrict__ rgb, const float* __restrict__ feat, const float* __restrict__ z_vals,
     const float* __restrict__ rays_d, const float* __restrict__ pts, const float* __restrict__ noise,
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(256) composite_forward_kernel(
 #pragma unroll
         for (int j = 0; j < kMaxF4; j++) fa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4* frow = reinterpret_cast<const float4*>(feat + base * F);
+        const uint2* frow16 = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(feat) + base * F);
         for (uint32_t s = 0; s < S; s++) {
             float w = 0.f;
 #pragma unroll
@@ -139,7 +141,14 @@ __global__ void __launch_bounds__(256) composite_forward_kernel(
             for (int j = 0; j < kMaxF4; j++) {
                 const uint32_t f4 = lane + 32 * j;
                 if (f4 < F4) {
-                    const float4 v = ldg_stream4(frow + (size_t)s * F4 + f4);
+                    float4 v;
+                    if (FEAT16) {
+                        const uint2 h = __ldg(frow16 + (size_t)s * F4 + f4);
+                        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+                        v = make_float4(a.x, a.y, b.x, b.y);
+                    } else {
+                        v = ldg_stream4(frow + (size_t)s * F4 + f4);
+                    }
                     fa[j].x = fmaf(w, v.x, fa[j].x); fa[j].y = fmaf(w, v.y, fa[j].y);
                     fa[j].z = fmaf(w, v.z, fa[j].z); fa[j].w = fmaf(w, v.w, fa[j].w);
                 }
@@ -345,6 +354,29 @@ extern "C" int sdfg_composite_forward(const float* sdf, const float* rgb, const 
     else LAUNCH(4);
 #undef LAUNCH
     return check_launch("composite_forward_kernel");
+}
+
+extern "C" int sdfg_composite_forward_h(const float* sdf, const float* rgb, const uint16_t* feat16, const float* z_vals,
+                                        const float* rays_d, const float* pts, const float* noise, const float* sigmoid_beta,
+                                        uint64_t NR, uint32_t S, uint32_t F, int with_sdf, int force_background, float* rgb_map,
+                                        float* feat_map, float* xyz_map, float* mask, float* weights, void* stream) {
+    if (int e = check_composite(S, F, feat16)) return e;
+    if (NR == 0) return SDFG_OK;
+    SDFG_REQUIRE(sdf && rgb && z_vals && rays_d && rgb_map && feat16 && feat_map, SDFG_ERR_INVALID, "composite_forward_h: null pointer");
+    SDFG_REQUIRE(!with_sdf || sigmoid_beta, SDFG_ERR_INVALID, "composite_forward_h: sdf mode needs sigmoid_beta");
+    SDFG_REQUIRE(!xyz_map || pts, SDFG_ERR_INVALID, "composite_forward_h: xyz_map needs pts");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)ceil_div<uint64_t>(NR, 8);
+    const float* feat = reinterpret_cast<const float*>(feat16);
+#define LAUNCH(KS)                                                                                                          \
+    composite_forward_kernel<KS, true><<<blocks, 256, 0, st>>>(sdf, rgb, feat, z_vals, rays_d, pts, noise, sigmoid_beta, NR, \
+                                                               S, F, with_sdf, force_background, rgb_map, feat_map, xyz_map, \
+                                                               mask, weights)
+    if (S <= 32) LAUNCH(1);
+    else if (S <= 64) LAUNCH(2);
+    else LAUNCH(4);
+#undef LAUNCH
+    return check_launch("composite_forward_kernel<h>");
 }
 
 extern "C" int sdfg_composite_backward(const float* sdf, const float* rgb, const float* feat, const float* z_vals,

@@ -26,8 +26,16 @@ extern "C" int sdfg_field_forward(const sdfg_field_params* p, const float* x_in,
     if (precision == SDFG_PRECISION_FP32)
         return field_forward_f32(p, x_in, view_feat, N, out_sdf, out_rgb, out_feat, workspace, save_for_backward, (cudaStream_t)stream);
     if (precision == SDFG_PRECISION_TC16)
-        return field_forward_tc(p, x_in, view_feat, N, out_sdf, out_rgb, out_feat, workspace, save_for_backward, (cudaStream_t)stream);
+        return field_forward_tc(p, x_in, view_feat, N, out_sdf, out_rgb, out_feat, nullptr, workspace, save_for_backward, (cudaStream_t)stream);
     return set_error(SDFG_ERR_UNSUPPORTED, "field_forward: unknown precision %d", precision);
+}
+
+extern "C" int sdfg_field_forward_h(const sdfg_field_params* p, const float* x_in, const float* view_feat, uint64_t N,
+                                    float* out_sdf, float* out_rgb, uint16_t* out_feat16, void* workspace, void* stream) {
+    if (int e = field_check_params(p, N)) return e;
+    if (N == 0) return SDFG_OK;
+    SDFG_REQUIRE(x_in && workspace && out_feat16, SDFG_ERR_INVALID, "field_forward_h: null pointer");
+    return field_forward_tc(p, x_in, view_feat, N, out_sdf, out_rgb, nullptr, out_feat16, workspace, 0, (cudaStream_t)stream);
 }
 
 extern "C" int sdfg_field_backward(const sdfg_field_params* p, const sdfg_field_grads* g, const float* x_in, const float* view_feat,

@@ -17,7 +17,7 @@ int field_backward_f32(const sdfg_field_params* p, const sdfg_field_grads* g, co
 // tcgen05 path (field_tc.cu)
 uint64_t field_workspace_bytes_tc(const sdfg_field_params* p, uint64_t N, int save);
 int field_forward_tc(const sdfg_field_params* p, const float* x_in, const float* view_feat, uint64_t N, float* out_sdf, float* out_rgb,
-                     float* out_feat, void* workspace, int save, cudaStream_t st);
+                     float* out_feat, uint16_t* out_feat16, void* workspace, int save, cudaStream_t st);
 uint64_t field_backward_scratch_bytes_tc(const sdfg_field_params* p, uint64_t N);
 int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, const float* x_in, const float* view_feat, uint64_t N,
                       const float* d_sdf, const float* d_rgb, const float* d_feat, const void* workspace, void* scratch, float* d_x_in,

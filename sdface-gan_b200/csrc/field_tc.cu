@@ -150,8 +150,8 @@ static bool bchain_eligible(const sdfg_field_params* p, const float* d_x_in) {
 }
 
 static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, const float* x_in, const float* view_feat, uint64_t N,
-                               float* out_sdf, float* out_rgb, float* out_feat, uint8_t* ws, int save, cudaStream_t st) {
-    const bool want_views = out_rgb || out_feat;
+                               float* out_sdf, float* out_rgb, float* out_feat, uint16_t* out_feat16, uint8_t* ws, int save, cudaStream_t st) {
+    const bool want_views = out_rgb || out_feat || out_feat16;
     const uint32_t W = L.W, nf = L.n_film;
     auto Wb = [&](uint32_t i) { return (h16*)(ws + L.off_w[i]); };
     auto A = [&](uint32_t l) { return (h16*)(ws + L.off_a[l]); };
@@ -216,6 +216,7 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
         if (int e = add_main_map(1 + nf, L.Kp_v)) return e;
         nm++;
         if (save) if (int e = store_to(nl, (h16*)(ws + L.off_hv), W)) return e;
+        if (out_feat16) if (int e = store_to(nl, out_feat16, W)) return e;      // features leave the chip as fp16, by TMA
         if (out_feat) { Y.out_f32 = out_feat; Y.ld_out_f32 = W; }
         if (out_rgb) { Y.nh = 3; Y.head_w = p->rgb_w; Y.head_b = p->rgb_b; Y.out_head = out_rgb; }
         nl++;
@@ -227,12 +228,13 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
     P.tiles_per_cta = ceil_div<uint32_t>(P.n_tiles, ctas);
     const uint32_t grid = ceil_div<uint32_t>(P.n_tiles, P.tiles_per_cta);
     const uint32_t smem = tc::chain_smem_bytes();
-    auto kern = save ? tc::tc_chain_fwd_kernel<true> : tc::tc_chain_fwd_kernel<false>;
+    const bool storing = save || out_feat16;
+    auto kern = storing ? tc::tc_chain_fwd_kernel<true> : tc::tc_chain_fwd_kernel<false>;
     static thread_local bool configured[2] = {false, false};
-    if (!configured[save ? 1 : 0]) {
+    if (!configured[storing ? 1 : 0]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return set_error(SDFG_ERR_CUDA, "tc_chain_fwd_kernel: cannot opt in to %u bytes of shared memory", smem);
-        configured[save ? 1 : 0] = true;
+        configured[storing ? 1 : 0] = true;
     }
     static const bool dbg_on = getenv("SDFG_CHAIN_DBG") != nullptr;     // debugging aid: event log of CTA 0 to stderr
     if (dbg_on) {
@@ -257,15 +259,17 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
 }
 
 int field_forward_tc(const sdfg_field_params* p, const float* x_in, const float* view_feat, uint64_t N, float* out_sdf, float* out_rgb,
-                     float* out_feat, void* workspace, int save, cudaStream_t st) {
+                     float* out_feat, uint16_t* out_feat16, void* workspace, int save, cudaStream_t st) {
     if (int e = check_tc(p, N)) return e;
+    SDFG_REQUIRE(!(out_feat16 && (save || out_feat)), SDFG_ERR_INVALID,
+                 "field_forward: fp16 features are an inference output (no save_for_backward, no fp32 copy)");
     const TcLayout L = tc_layout(p, N, save);
     uint8_t* ws = (uint8_t*)workspace;
     auto Wb = [&](uint32_t i) { return (h16*)(ws + L.off_w[i]); };
     auto A = [&](uint32_t l) { return (h16*)(ws + L.off_a[l]); };
     const uint32_t W = L.W, nf = L.n_film;
     const int64_t gstride = (int64_t)(nf + 1) * W;
-    const bool want_views = out_rgb || out_feat;
+    const bool want_views = out_rgb || out_feat || out_feat16;
     // 1. weights -> fp16 (padded K)
     if (p->has_input_linear)
         if (int e = cast_pad(p->input_w, p->in_dim, 1, Wb(0), L.Kp_in, W, p->in_dim, L.Kp_in, st)) return e;
@@ -275,7 +279,7 @@ int field_forward_tc(const sdfg_field_params* p, const float* x_in, const float*
         if (int e = cast_pad(p->film_w[l], K, 1, Wb(1 + l), round_up(K, 8), W, K, round_up(K, 8), st)) return e;
     }
     if (chain_enabled() && chain_eligible(p, want_views))
-        return field_forward_chain(p, L, x_in, view_feat, N, out_sdf, out_rgb, out_feat, ws, save, st);
+        return field_forward_chain(p, L, x_in, view_feat, N, out_sdf, out_rgb, out_feat, out_feat16, ws, save, st);
     // 2. encoder features -> fp16
     h16* X0 = (h16*)(ws + L.off_x0);
     if (int e = cast_pad(x_in, p->in_dim, 1, X0, L.Kp_in, N, p->in_dim, L.Kp_in, st)) return e;
@@ -309,6 +313,7 @@ int field_forward_tc(const sdfg_field_params* p, const float* x_in, const float*
         P.gamma = p->gamma + (size_t)nf * W; P.beta = p->beta + (size_t)nf * W; P.gstride = gstride;
         if (save) { P.out16 = (h16*)(ws + L.off_hv); P.ld_out = W; }
         if (out_feat) { P.out_f32 = out_feat; P.ld_out_f32 = W; }
+        if (out_feat16) { P.out16 = out_feat16; P.ld_out = W; }
         if (out_rgb) { P.nh = 3; P.head_w = p->rgb_w; P.head_b = p->rgb_b; P.out_head = out_rgb; }
         if (int e = launch_layer<tc::MODE_F>(A(nf), N, L.Kp_v, L.Kp_v, Wb(1 + nf), W, L.Kp_v, P, st, "tc_layer_kernel<F,gemm,views>")) return e;
     }

@@ -189,8 +189,9 @@ def _field_params(spec, samples_per_image, samples_per_ray, gamma, beta, weights
 
 
 def field_forward(spec, x_in, view_feat, gamma, beta, weights, samples_per_image, samples_per_ray, want_rgb=True, want_feat=True,
-                  save_for_backward=False, precision=_lib.PRECISION_FP32):
-    """Returns (sdf [N], rgb [N,3]|None, feat [N,W]|None, workspace)."""
+                  save_for_backward=False, precision=_lib.PRECISION_FP32, feat_f16=False):
+    """Returns (sdf [N], rgb [N,3]|None, feat [N,W]|None, workspace).  feat_f16 (tensor-core path, inference only): the
+    features come back as a float16 tensor (sdfg_field_forward_h), to be consumed by composite_forward."""
     lib = _lib.load()
     _chk(x_in, "x_in"); _chk(view_feat, "view_feat")
     N = x_in.shape[0]
@@ -200,6 +201,14 @@ def field_forward(spec, x_in, view_feat, gamma, beta, weights, samples_per_image
     ws = torch.empty(max(nbytes, 16) // 4, device=dev, dtype=torch.float32)
     sdf = torch.empty(N, device=dev)
     rgb = torch.empty(N, 3, device=dev) if want_rgb else None
+    if feat_f16 and want_feat:
+        if save_for_backward or precision != _lib.PRECISION_TC16:
+            raise RuntimeError("fp16 features are an inference output of the tensor-core path")
+        feat = torch.empty(N, spec.width, device=dev, dtype=torch.float16)
+        with torch.cuda.device(dev):
+            _lib.check(lib.sdfg_field_forward_h(ctypes.byref(p), _ptr(x_in), _ptr(view_feat), N, _ptr(sdf), _ptr(rgb), _ptr(feat), _ptr(ws),
+                                                _stream()), "sdfg_field_forward_h")
+        return sdf, rgb, feat, ws
     feat = torch.empty(N, spec.width, device=dev) if want_feat else None
     with torch.cuda.device(dev):
         _lib.check(lib.sdfg_field_forward(ctypes.byref(p), _ptr(x_in), _ptr(view_feat), N, _ptr(sdf), _ptr(rgb), _ptr(feat), _ptr(ws),
@@ -286,6 +295,14 @@ def composite_forward(sdf, rgb, feat, z_vals, rays_d, pts, noise, sigmoid_beta, 
     feat_map = torch.empty(NR, F, device=dev) if feat is not None else None
     xyz = torch.empty(NR, 3, device=dev) if want_xyz else None
     mask = torch.empty(NR, device=dev) if want_xyz else None
+    if feat is not None and feat.dtype == torch.float16:
+        with torch.cuda.device(dev):
+            _lib.check(lib.sdfg_composite_forward_h(_ptr(_chk(sdf, "sdf")), _ptr(_chk(rgb, "rgb")), _ptr(_chk(feat, "feat", torch.float16)),
+                                                    _ptr(_chk(z_vals, "z_vals")), _ptr(_chk(rays_d, "rays_d")), _ptr(_chk(pts, "pts")),
+                                                    _ptr(_chk(noise, "noise")), _ptr(_chk(sigmoid_beta, "sigmoid_beta")), NR, int(S), int(F),
+                                                    int(bool(with_sdf)), int(bool(force_background)), _ptr(rgb_map), _ptr(feat_map), _ptr(xyz),
+                                                    _ptr(mask), None, _stream()), "sdfg_composite_forward_h")
+        return rgb_map, feat_map, xyz, mask
     with torch.cuda.device(dev):
         _lib.check(lib.sdfg_composite_forward(_ptr(_chk(sdf, "sdf")), _ptr(_chk(rgb, "rgb")), _ptr(_chk(feat, "feat")), _ptr(_chk(z_vals, "z_vals")),
                                               _ptr(_chk(rays_d, "rays_d")), _ptr(_chk(pts, "pts")), _ptr(_chk(noise, "noise")),

@@ -87,9 +87,11 @@ class _field(Function):
         wts = tuple(w.contiguous() for w in wts)
         weights = _unpack_weights(spec, wts)
         need_bwd = (meta.get("grad", True) and any(ctx.needs_input_grad[2:])) or meta["want_dsdf"]
+        # inference on the tensor-core path: features stay fp16 between the field and the compositing kernel (half the HBM bytes)
+        feat_f16 = bool(meta.get("feat_f16")) and not need_bwd and meta["precision"] == _lib.PRECISION_TC16
         sdf, rgb, feat, ws = ops.field_forward(spec, x_in, view_feat, gamma, beta, weights, meta["spi"], meta["spr"],
                                                want_rgb=meta["want_rgb"], want_feat=meta["want_feat"],
-                                               save_for_backward=need_bwd, precision=meta["precision"])
+                                               save_for_backward=need_bwd, precision=meta["precision"], feat_f16=feat_f16)
         dsdf = None
         if meta["want_dsdf"]:
             # d sdf / d x_in for the eikonal term (ref get_eikonal_term :224-229): a trunk-only backward with d_sdf = 1
@@ -181,12 +183,13 @@ class _FieldNetwork(nn.Module):
         beta = torch.stack([l.beta(styles) for l in layers], 1)
         return gamma, beta
 
-    def _run_field(self, x_in, view_feat, styles, samples_per_image, samples_per_ray, want_rgb=True, want_feat=True, want_dsdf=False):
+    def _run_field(self, x_in, view_feat, styles, samples_per_image, samples_per_ray, want_rgb=True, want_feat=True, want_dsdf=False,
+                   feat_f16=False):
         spec = self._spec
         gamma, beta = self._modulation(styles)
         meta = dict(spi=int(samples_per_image), spr=int(samples_per_ray), want_rgb=bool(want_rgb), want_feat=bool(want_feat),
                     want_dsdf=bool(want_dsdf), precision=self._pick_precision(int(samples_per_image)),
-                    grad=torch.is_grad_enabled())   # Function.forward itself always runs with grad mode off
+                    grad=torch.is_grad_enabled(), feat_f16=bool(feat_f16))   # Function.forward itself always runs with grad mode off
         sdf, rgb, feat, dsdf = _field.apply(spec, meta, x_in, view_feat, gamma, beta, *_pack_weights(spec, self))
         return sdf, (rgb if rgb.numel() else None), (feat if feat.numel() else None), (dsdf if dsdf.numel() else None)
 
@@ -203,12 +206,12 @@ class _FieldNetwork(nn.Module):
             out.append(feat)
         return torch.cat(out, -1).view(prefix + [-1])
 
-    def forward_rays(self, npts, viewdirs, styles, want_rgb=True, want_feat=True, want_dsdf=False):
+    def forward_rays(self, npts, viewdirs, styles, want_rgb=True, want_feat=True, want_dsdf=False, feat_f16=False):
         """Renderer entry: npts [B,R,R,S,3], viewdirs [B,R,R,3] (one per ray) -> (sdf [N], rgb [N,3], feat [N,W], dsdf_dnpts [N,3])."""
         B, R1, R2, S, _ = npts.shape
         flat = npts.reshape(-1, 3)
         x_in, view_feat, grid_ctx = self._encode_rays(flat, viewdirs.reshape(-1, 3), want_dsdf)
-        sdf, rgb, feat, dsdf = self._run_field(x_in, view_feat, styles, R1 * R2 * S, S, want_rgb, want_feat, want_dsdf)
+        sdf, rgb, feat, dsdf = self._run_field(x_in, view_feat, styles, R1 * R2 * S, S, want_rgb, want_feat, want_dsdf, feat_f16)
         if want_dsdf:
             dsdf = self._dsdf_to_points(dsdf, flat, grid_ctx)
         return sdf, rgb, feat, dsdf
@@ -457,7 +460,7 @@ class VolumeFeatureRenderer(nn.Module):
         smp, near, far = self._sample(c2w, focal, near, far, t_rand=t_rand)
         want_eik = bool(return_eikonal and self.with_sdf)
         sdf, rgb, feat, dsdf = self.network.forward_rays(smp["npts"], smp["viewdirs"], styles, want_rgb=True,
-                                                         want_feat=self.output_features, want_dsdf=want_eik)
+                                                         want_feat=self.output_features, want_dsdf=want_eik, feat_f16=True)
         noise = None
         if (not self.with_sdf) and self.raw_noise_std > 0.:
             noise = torch.randn_like(sdf) * self.raw_noise_std
