@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-SDFG_CHAIN_DBG=1 SDFG_ONLY=tc16 timeout 300 python scripts/bench_field.py 8 > gpurun_out/chain_dbg.log 2>&1
-grep -c CHDBG gpurun_out/chain_dbg.log; tail -1 gpurun_out/chain_dbg.log
+SDFG_BCHAIN_DBG=1 timeout 300 python bench.py --steps 1 --warmup 3 --batch 8 --no-cpu-baseline > gpurun_out/bchain_dbg.log 2>&1
+grep -c CHDBG gpurun_out/bchain_dbg.log

@@ -536,6 +536,9 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         tc::BChainMaps* maps = new tc::BChainMaps;                     // 5 KB of tensor maps: off the stack
         std::unique_ptr<tc::BChainMaps> maps_guard(maps);
         tc::BChainParams P = {};
+        static const bool exp_halfw = getenv("SDFG_EXP_HALFW") != nullptr;   // timing experiment only: stream half of every weight chunk (wrong results)
+        const uint32_t wrows = exp_halfw ? 128 : 256;
+        P.w_bytes = wrows * 128;
         P.M_total = (uint32_t)N; P.rows_per_image = spi;
         P.gamma = p->gamma; P.beta = p->beta; P.gstride = gstride; P.gscale = gscale;
         P.vecs[0] = p->sigma_w;
@@ -549,12 +552,12 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
             Y.film = l; Y.bias = p->film_b[l];
             Y.do_D = l == nf ? 1u : ((l > 0 || need_dh0) ? 1u : 0u);
             if (int e = make_tensor_map_16(&maps->a[nl], A(l), N, Kp, Kp, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
-            if (int e = make_tensor_map_16(&maps->w[nl], Wb(1 + l), W, Kp, Kp, 256, 64, tc::FMT_F16)) return e;
+            if (int e = make_tensor_map_16(&maps->w[nl], Wb(1 + l), W, Kp, Kp, wrows, 64, tc::FMT_F16)) return e;
             if (Y.do_D) {
                 h16* wgt = (h16*)(sc + SC.off_wgt[l]);
                 wgt_kernel<<<dim3(W, B), 256, 0, st>>>(p->film_w[l], layer_Kx(l), p->gamma + (size_t)l * W, gstride, wgt, W, B);
                 if (int e = check_launch("wgt_kernel")) return e;
-                if (int e = make_tensor_map_16(&maps->wgt[nl], wgt, (uint64_t)B * W, W, W, 256, 64, tc::FMT_F16)) return e;
+                if (int e = make_tensor_map_16(&maps->wgt[nl], wgt, (uint64_t)B * W, W, W, wrows, 64, tc::FMT_F16)) return e;
             }
             if (store)
                 if (int e = make_tensor_map_16(&maps->dz[nl], (h16*)(sc + SC.off_dz[l]), N, W, W, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
@@ -595,7 +598,23 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
                 return set_error(SDFG_ERR_CUDA, "tc_chain_bwd_kernel: cannot opt in to %u bytes of shared memory", smem);
             configured[store ? 1 : 0] = true;
         }
-        {
+        static const bool dbg_on = getenv("SDFG_BCHAIN_DBG") != nullptr;    // debugging aid: event log of CTA 0 to stderr
+        if (dbg_on && store) {
+            static unsigned long long* dbuf = nullptr;
+            if (!dbuf) cudaMalloc(&dbuf, 4 * 2048 * 8);
+            cudaMemsetAsync(dbuf, 0, 4 * 2048 * 8, st);
+            P.dbg = dbuf;
+            kern<<<grid, tc::CH_THREADS, smem, st>>>(*maps, P);
+            cudaStreamSynchronize(st);
+            static unsigned long long host[4 * 2048];
+            cudaMemcpy(host, dbuf, sizeof(host), cudaMemcpyDeviceToHost);
+            static int dumps = 0;
+            if (dumps++ == 2)
+                for (int role = 0; role < 4; role++)
+                    for (int k = 0; k < 1024 && host[role * 2048 + 2 * k + 1]; k++)
+                        fprintf(stderr, "CHDBG %d %llu %llu\n", role, host[role * 2048 + 2 * k], host[role * 2048 + 2 * k + 1]);
+            if (int e = check_launch("tc_chain_bwd_kernel<gemm>")) return e;
+        } else {
             ProfScope prof("tc_chain_bwd_kernel<gemm>", st);
             kern<<<grid, tc::CH_THREADS, smem, st>>>(*maps, P);
             if (int e = check_launch("tc_chain_bwd_kernel<gemm>")) return e;
@@ -603,11 +622,11 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         if (!g) return SDFG_OK;
         // ---- parameter gradients from the stored du tiles (sample-axis contractions) and the fp32 head gradients
         if (views && g->rgb_w && d_rgb) {
-            head_wgrad16_kernel<3><<<(unsigned)ceil_div<uint64_t>(N, 2048), 256, 0, st>>>(d_rgb, (const h16*)(ws + L.off_hv), W, g->rgb_w, g->rgb_b, N, 2048);
+            head_wgrad16_kernel<3><<<(unsigned)ceil_div<uint64_t>(N, 512), 256, 0, st>>>(d_rgb, (const h16*)(ws + L.off_hv), W, g->rgb_w, g->rgb_b, N, 512);
             if (int e = check_launch("head_wgrad16_kernel<3>")) return e;
         }
         if (g->sigma_w && d_sdf) {
-            head_wgrad16_kernel<1><<<(unsigned)ceil_div<uint64_t>(N, 2048), 256, 0, st>>>(d_sdf, A(nf), L.Kp_v, g->sigma_w, g->sigma_b, N, 2048);
+            head_wgrad16_kernel<1><<<(unsigned)ceil_div<uint64_t>(N, 512), 256, 0, st>>>(d_sdf, A(nf), L.Kp_v, g->sigma_w, g->sigma_b, N, 512);
             if (int e = check_launch("head_wgrad16_kernel<1>")) return e;
         }
         for (int l = views ? (int)nf : (int)nf - 1; l >= 0; l--) {
@@ -667,7 +686,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
     if (d_rgb || d_feat) {
         if (int e = run_R(nf, nullptr, d_feat, d_rgb ? 3 : 0, d_rgb, p->rgb_w)) return e;
         if (g && g->rgb_w && d_rgb) {
-            head_wgrad16_kernel<3><<<(unsigned)ceil_div<uint64_t>(N, 2048), 256, 0, st>>>(d_rgb, (const h16*)(ws + L.off_hv), W, g->rgb_w, g->rgb_b, N, 2048);
+            head_wgrad16_kernel<3><<<(unsigned)ceil_div<uint64_t>(N, 512), 256, 0, st>>>(d_rgb, (const h16*)(ws + L.off_hv), W, g->rgb_w, g->rgb_b, N, 512);
             if (int e = check_launch("head_wgrad16_kernel<3>")) return e;
         }
         if (int e = run_W(nf)) return e;
@@ -677,7 +696,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         rank1_sdf = true;
     }
     if (g && g->sigma_w && d_sdf) {
-        head_wgrad16_kernel<1><<<(unsigned)ceil_div<uint64_t>(N, 2048), 256, 0, st>>>(d_sdf, h_last, L.Kp_v, g->sigma_w, g->sigma_b, N, 2048);
+        head_wgrad16_kernel<1><<<(unsigned)ceil_div<uint64_t>(N, 512), 256, 0, st>>>(d_sdf, h_last, L.Kp_v, g->sigma_w, g->sigma_b, N, 512);
         if (int e = check_launch("head_wgrad16_kernel<1>")) return e;
     }
     for (int l = (int)nf - 1; l >= 0; l--) {

@@ -41,13 +41,14 @@ struct BLayer {
 struct BChainParams {
     uint32_t M_total, rows_per_image, n_tiles, tiles_per_cta, n_layers;
     uint32_t has_in, in_dim;    // final stage: d_x_in[M, in_dim] = gs_inv * dh_0 W_in
-    uint32_t pad;
+    uint32_t w_bytes;           // bytes of one streamed weight chunk (32768; an experiment knob)
     float* d_x_in;
     const float* gamma;         // + img * gstride + film * 256 + n
     const float* beta;
     int64_t gstride;
     const float* gscale;        // {s, 1/s}
     const float* vecs[4];       // rank vectors [256] each: 0 = w_sigma, 1..3 = w_rgb rows
+    unsigned long long* dbg;    // debugging: event log of CTA 0 (see tc_chain.cuh)
     BLayer layer[BC_MAX_LAYERS];   // index 0 = TOP layer
 };
 
@@ -92,6 +93,7 @@ tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_consta
     const uint32_t t_begin = blockIdx.x * P.tiles_per_cta;
     const uint32_t t_end = min(P.n_tiles, t_begin + P.tiles_per_cta);
     const uint32_t nL = P.n_layers;
+    uint32_t dbg_n = 0;
 
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < BC_STAGES; i++) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
@@ -128,7 +130,7 @@ tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_consta
                     const uint32_t nk = P.layer[i].nk;
                     for (uint32_t kc = 0; kc < nk; kc++) {
                         mbar_wait(&S.empty[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&S.full[stage], BC_STAGE_BYTES);
+                        mbar_arrive_expect_tx(&S.full[stage], 16384 + P.w_bytes);
                         uint8_t* st = smRING + stage * BC_STAGE_BYTES;
                         tma_load_2d(st, &maps.w[i], &S.full[stage], (int32_t)(kc * 64), 0);
                         tma_load_2d(st + 32768, &maps.a[i], &S.full[stage], (int32_t)(kc * 64), row0);
@@ -137,7 +139,7 @@ tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_consta
                     if (P.layer[i].do_D)
                         for (uint32_t kc = 0; kc < 4; kc++) {
                             mbar_wait(&S.empty[stage], phase ^ 1);
-                            mbar_arrive_expect_tx(&S.full[stage], 32768);
+                            mbar_arrive_expect_tx(&S.full[stage], P.w_bytes);
                             tma_load_2d(smRING + stage * BC_STAGE_BYTES, &maps.wgt[i], &S.full[stage], (int32_t)(kc * 64), img * 256);
                             next();
                         }
@@ -165,6 +167,7 @@ tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_consta
                     // ---- R_l -> accumulator 0
                     mbar_wait(&S.accR_empty, (nR & 1) ^ 1);
                     tc_fence_after();
+                    CH_DBG(0, 50 + i);
                     uint32_t accumulate = 0;
                     for (uint32_t kc = 0; kc < nk; kc++) {
                         mbar_wait(&S.full[stage], phase);
@@ -177,6 +180,7 @@ tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_consta
                         next();
                     }
                     umma_commit(&S.accR_full);
+                    CH_DBG(0, 100 + i);
                     nR++;
                     // ---- D_l -> accumulator 1, chunk by chunk behind the epilogue
                     if (P.layer[i].do_D) {
@@ -190,6 +194,7 @@ tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_consta
                             for (uint32_t s = 0; s < 4; s++)
                                 umma_bf16(tmem_base + 256, smem_desc_sw128(a_addr + s * 32, 16, 1024), smem_desc_sw128(b_addr + s * 32, 16, 1024), idesc, (kc | s) != 0);
                             umma_commit(&S.empty[stage]);
+                            CH_DBG(0, 200 + i * 16 + kc);
                             next();
                         }
                         umma_commit(&S.accD_full);
@@ -277,8 +282,10 @@ tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_consta
                 const uint32_t rvec_s = smem_u32(&S.vecs[r_vec0][0]), dvec_s = smem_u32(&S.vecs[d_vec0][0]);
 
                 // ---------------- epi_R: du = dh * cos(gamma u + c), in place in G
+                if (threadIdx.x == 0) CH_DBG(1, 300 + i);
                 mbar_wait(&S.accR_full, nR & 1);
                 tc_fence_after();
+                if (threadIdx.x == 0) CH_DBG(1, 400 + i);
                 {
                     const uint32_t taddr = tmem_base + lane_base + sb * 16;
                     uint32_t raw[2][16];
@@ -339,6 +346,7 @@ tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_consta
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&S.dz_ready[c]);
+                        if (threadIdx.x == 0) CH_DBG(1, 500 + i * 16 + c);
                     }
                     if (STORE && stored_dh0 && i == 0) { stgen++; stored_dh0 = false; }
                 }
@@ -349,8 +357,10 @@ tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_consta
 
                 // ---------------- epi_D: G = fp16(dh' + rank-1 term)
                 if (do_D) {
+                    if (threadIdx.x == 0) CH_DBG(1, 600 + i);
                     mbar_wait(&S.accD_full, nD & 1);
                     tc_fence_after();
+                    if (threadIdx.x == 0) CH_DBG(1, 700 + i);
                     const uint32_t taddr = tmem_base + lane_base + 256 + sb * 16;
                     const bool to_in = P.has_in && i + 1 == nL;
                     uint32_t raw[2][16];
@@ -387,6 +397,7 @@ tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_consta
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S.accD_empty);
+                    if (threadIdx.x == 0) CH_DBG(1, 800 + i);
                     nD++;
                 } else if (STORE) {
                     // no D: the du store of this layer still owns G until the storer is done with it
