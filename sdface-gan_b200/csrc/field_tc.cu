@@ -536,9 +536,10 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         tc::BChainMaps* maps = new tc::BChainMaps;                     // 5 KB of tensor maps: off the stack
         std::unique_ptr<tc::BChainMaps> maps_guard(maps);
         tc::BChainParams P = {};
-        static const bool exp_halfw = getenv("SDFG_EXP_HALFW") != nullptr;   // timing experiment only: stream half of every weight chunk (wrong results)
-        const uint32_t wrows = exp_halfw ? 128 : 256;
-        P.w_bytes = wrows * 128;
+        // CTA pairs (cta_group::2) when two adjacent tiles always belong to one image and the input stage splits evenly
+        static const int cg_env = []() { const char* e = getenv("SDFG_TC_CG"); return e ? atoi(e) : 2; }();
+        const int cg = (cg_env == 2 && spi % 256 == 0 && (N / tc::CH_TILE_M) % 2 == 0 && (!p->has_input_linear || p->in_dim % 32 == 0)) ? 2 : 1;
+        const uint32_t wrows = 256 / cg;
         P.M_total = (uint32_t)N; P.rows_per_image = spi;
         P.gamma = p->gamma; P.beta = p->beta; P.gstride = gstride; P.gscale = gscale;
         P.vecs[0] = p->sigma_w;
@@ -582,29 +583,42 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
             h16* wgt_in = (h16*)(sc + SC.off_wgt_in);
             wgt_kernel<<<dim3(p->in_dim, 1), 256, 0, st>>>(p->input_w, p->in_dim, nullptr, 0, wgt_in, p->in_dim, 1);
             if (int e = check_launch("wgt_kernel")) return e;
-            if (int e = make_tensor_map_16(&maps->wgt_in, wgt_in, p->in_dim, W, W, p->in_dim, 64, tc::FMT_F16)) return e;
+            if (int e = make_tensor_map_16(&maps->wgt_in, wgt_in, p->in_dim, W, W, p->in_dim / cg, 64, tc::FMT_F16)) return e;
             if (store)
                 if (int e = make_tensor_map_16(&maps->dh0, DH, N, W, W, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
         }
-        P.n_tiles = (uint32_t)(N / tc::CH_TILE_M);
-        const uint32_t ctas = std::min<uint32_t>((uint32_t)sm_count(), P.n_tiles);
-        P.tiles_per_cta = ceil_div<uint32_t>(P.n_tiles, ctas);
-        const uint32_t grid = ceil_div<uint32_t>(P.n_tiles, P.tiles_per_cta);
-        const uint32_t smem = tc::bchain_smem_bytes();
-        auto kern = store ? tc::tc_chain_bwd_kernel<true> : tc::tc_chain_bwd_kernel<false>;
-        static thread_local bool configured[2] = {false, false};
-        if (!configured[store ? 1 : 0]) {
+        P.n_units = (uint32_t)(N / (tc::CH_TILE_M * cg));
+        const uint32_t groups = std::min<uint32_t>((uint32_t)sm_count() / cg, P.n_units);      // CTAs (CG = 1) or CTA pairs
+        P.units_per_cta = ceil_div<uint32_t>(P.n_units, groups);
+        const uint32_t grid = cg * ceil_div<uint32_t>(P.n_units, P.units_per_cta);
+        const uint32_t smem = tc::bchain_smem_bytes(cg);
+        typedef void (*bkern_t)(const tc::BChainMaps, const tc::BChainParams);
+        const bkern_t kern = cg == 2 ? (store ? (bkern_t)tc::tc_chain_bwd_kernel<true, 2> : (bkern_t)tc::tc_chain_bwd_kernel<false, 2>)
+                                     : (store ? (bkern_t)tc::tc_chain_bwd_kernel<true, 1> : (bkern_t)tc::tc_chain_bwd_kernel<false, 1>);
+        static thread_local bool configured[4] = {false, false, false, false};
+        const int ki = (cg == 2 ? 2 : 0) + (store ? 1 : 0);
+        if (!configured[ki]) {
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
                 return set_error(SDFG_ERR_CUDA, "tc_chain_bwd_kernel: cannot opt in to %u bytes of shared memory", smem);
-            configured[store ? 1 : 0] = true;
+            configured[ki] = true;
         }
+        auto launch = [&]() -> int {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            if (cudaLaunchKernelEx(&cfg, kern, *maps, P) != cudaSuccess) { (void)check_launch("tc_chain_bwd_kernel<gemm>"); return SDFG_ERR_CUDA; }
+            return check_launch("tc_chain_bwd_kernel<gemm>");
+        };
         static const bool dbg_on = getenv("SDFG_BCHAIN_DBG") != nullptr;    // debugging aid: event log of CTA 0 to stderr
         if (dbg_on && store) {
             static unsigned long long* dbuf = nullptr;
             if (!dbuf) cudaMalloc(&dbuf, 4 * 2048 * 8);
             cudaMemsetAsync(dbuf, 0, 4 * 2048 * 8, st);
             P.dbg = dbuf;
-            kern<<<grid, tc::CH_THREADS, smem, st>>>(*maps, P);
+            if (int e = launch()) return e;
             cudaStreamSynchronize(st);
             static unsigned long long host[4 * 2048];
             cudaMemcpy(host, dbuf, sizeof(host), cudaMemcpyDeviceToHost);
@@ -613,11 +627,9 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
                 for (int role = 0; role < 4; role++)
                     for (int k = 0; k < 1024 && host[role * 2048 + 2 * k + 1]; k++)
                         fprintf(stderr, "CHDBG %d %llu %llu\n", role, host[role * 2048 + 2 * k], host[role * 2048 + 2 * k + 1]);
-            if (int e = check_launch("tc_chain_bwd_kernel<gemm>")) return e;
         } else {
             ProfScope prof("tc_chain_bwd_kernel<gemm>", st);
-            kern<<<grid, tc::CH_THREADS, smem, st>>>(*maps, P);
-            if (int e = check_launch("tc_chain_bwd_kernel<gemm>")) return e;
+            if (int e = launch()) return e;
         }
         if (!g) return SDFG_OK;
         // ---- parameter gradients from the stored du tiles (sample-axis contractions) and the fp32 head gradients

@@ -12,6 +12,10 @@
 // Gradients are fp16 with the power-of-two loss scale of field_tc.cu (gscale = {s, 1/s}); stores saturate.
 // With STORE the du tiles (and dh_0) are TMA-stored to HBM for the sample-axis weight-gradient kernels (tc_wgrad.cuh) that run
 // afterwards; G chunks are only overwritten once the store has read them (st_done).
+// CG = 2: two CTAs of a cluster run one tcgen05.mma.cta_group::2 (M = 256) per K-step: each stages its own 128 rows of A / G
+// and HALF of every weight chunk, so the L2 -> SM weight stream (the measured bound of the CG = 1 kernel: ~1.3 MB per tile,
+// 6.9 TB/s over the chip) is halved.  The leader CTA's MMA thread issues for the pair; the peer's epilogue warps arrive on
+// the leader's barriers through the cluster (mapa + mbarrier.arrive.release.cluster), commits are multicast to both CTAs.
 // Algorithmic HBM traffic per sample and layer: 512 B (A_l) in, 512 B (du) out -- the per-layer kernels moved 2.5 KB.
 #pragma once
 #include "tc_chain.cuh"
@@ -20,8 +24,13 @@ namespace sdfg {
 namespace tc {
 
 constexpr uint32_t BC_MAX_LAYERS = SDFG_MAX_FILM;            // FiLM layers incl. views
-constexpr uint32_t BC_STAGE_BYTES = 48 * 1024;               // [B chunk 32 KB | A chunk 16 KB]
-constexpr uint32_t BC_STAGES = 3;
+// Two operand rings.  A ring: 4 x 16 KB = one whole saved-activation tile [128 x 256] -- the HBM loads of the NEXT layer's recompute
+// are in flight while this layer's epilogue runs.  W ring: weight chunks ([256 / CG rows] x 64) of R_l, D_l, R_{l-1}, ... in issue
+// order (L2 hits); a CTA pair (CG = 2) stages half of every chunk per CTA.
+constexpr uint32_t BC_A_STAGES = 4;
+__host__ __device__ constexpr uint32_t bc_w_bytes(int cg) { return 32768u / (uint32_t)cg; }
+__host__ __device__ constexpr uint32_t bc_w_stages(int cg) { return cg == 2 ? 5u : 2u; }
+constexpr uint32_t BC_MAX_W_STAGES = 5;
 constexpr uint32_t BC_G_BYTES = 4 * CH_CHUNK_BYTES;          // gradient tile [128 x 256] fp16
 
 struct BLayer {
@@ -39,9 +48,9 @@ struct BLayer {
 };
 
 struct BChainParams {
-    uint32_t M_total, rows_per_image, n_tiles, tiles_per_cta, n_layers;
+    uint32_t M_total, rows_per_image, n_units, units_per_cta, n_layers;   // unit = CG adjacent 128-row tiles (one per CTA of the pair)
     uint32_t has_in, in_dim;    // final stage: d_x_in[M, in_dim] = gs_inv * dh_0 W_in
-    uint32_t w_bytes;           // bytes of one streamed weight chunk (32768; an experiment knob)
+    uint32_t pad;
     float* d_x_in;
     const float* gamma;         // + img * gstride + film * 256 + n
     const float* beta;
@@ -62,8 +71,11 @@ struct alignas(64) BChainMaps {
 };
 
 struct BChainSmem {
-    uint64_t full[BC_STAGES], empty[BC_STAGES];
-    uint64_t dz_ready[4], dh0_ready[4], st_done[4];
+    uint64_t a_full[BC_A_STAGES], a_empty;      // one buffer = one tile: per-chunk arrival, released once per layer
+    uint64_t w_full[BC_MAX_W_STAGES], w_empty[BC_MAX_W_STAGES];
+    uint64_t dz_ready[4], dh0_ready[4];          // MMA side (on the leader CTA: every epilogue warp of the pair arrives)
+    uint64_t dz_ready_st[4], dh0_ready_st[4];    // storer side (local)
+    uint64_t st_done[4];
     uint64_t accR_full, accR_empty, accD_full, accD_empty;
     uint32_t tmem_base;
     uint32_t pad[3];
@@ -72,7 +84,9 @@ struct BChainSmem {
     float vecs[4][256];
 };
 
-__host__ __device__ inline uint32_t bchain_smem_bytes() { return 1024 + BC_G_BYTES + BC_STAGES * BC_STAGE_BYTES + (uint32_t)sizeof(BChainSmem); }
+__host__ __device__ inline uint32_t bchain_smem_bytes(int cg) {
+    return 1024 + BC_G_BYTES + BC_A_STAGES * CH_CHUNK_BYTES + bc_w_stages(cg) * bc_w_bytes(cg) + (uint32_t)sizeof(BChainSmem);
+}
 
 __device__ __forceinline__ uint4 lds128u(uint32_t addr) {
     uint4 r;
@@ -80,26 +94,38 @@ __device__ __forceinline__ uint4 lds128u(uint32_t addr) {
     return r;
 }
 
-template <bool STORE>
+template <bool STORE, int CG>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_constant__ BChainParams P) {
+    constexpr bool PAIR = CG == 2;
+    constexpr uint32_t W_BYTES = bc_w_bytes(CG), NW = bc_w_stages(CG), NA = BC_A_STAGES;
+    constexpr uint32_t W_ROWS = 256 / CG;                              // weight rows (output neurons) staged per CTA
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smG = smem;
-    uint8_t* smRING = smG + BC_G_BYTES;
-    BChainSmem& S = *reinterpret_cast<BChainSmem*>(smRING + BC_STAGES * BC_STAGE_BYTES);
+    uint8_t* smA = smG + BC_G_BYTES;
+    uint8_t* smW = smA + NA * CH_CHUNK_BYTES;
+    BChainSmem& S = *reinterpret_cast<BChainSmem*>(smW + NW * W_BYTES);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t t_begin = blockIdx.x * P.tiles_per_cta;
-    const uint32_t t_end = min(P.n_tiles, t_begin + P.tiles_per_cta);
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;               // 0 = leader (issues the MMAs of the pair)
+    const bool leader = rank == 0;
+    const uint32_t u_begin = (blockIdx.x / CG) * P.units_per_cta;
+    const uint32_t u_end = min(P.n_units, u_begin + P.units_per_cta);
     const uint32_t nL = P.n_layers;
     uint32_t dbg_n = 0;
 
     if (threadIdx.x == 0) {
-        for (uint32_t i = 0; i < BC_STAGES; i++) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
-        for (uint32_t i = 0; i < 4; i++) { mbar_init(&S.dz_ready[i], CH_EPI_WARPS); mbar_init(&S.dh0_ready[i], CH_EPI_WARPS); mbar_init(&S.st_done[i], 1); }
-        mbar_init(&S.accR_full, 1); mbar_init(&S.accR_empty, CH_EPI_WARPS);
-        mbar_init(&S.accD_full, 1); mbar_init(&S.accD_empty, CH_EPI_WARPS);
+        for (uint32_t i = 0; i < NA; i++) mbar_init(&S.a_full[i], 1);
+        mbar_init(&S.a_empty, 1);
+        for (uint32_t i = 0; i < NW; i++) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
+        for (uint32_t i = 0; i < 4; i++) {
+            mbar_init(&S.dz_ready[i], CH_EPI_WARPS * CG); mbar_init(&S.dh0_ready[i], CH_EPI_WARPS * CG);
+            mbar_init(&S.dz_ready_st[i], CH_EPI_WARPS); mbar_init(&S.dh0_ready_st[i], CH_EPI_WARPS);
+            mbar_init(&S.st_done[i], 1);
+        }
+        mbar_init(&S.accR_full, 1); mbar_init(&S.accR_empty, CH_EPI_WARPS * CG);
+        mbar_init(&S.accD_full, 1); mbar_init(&S.accD_empty, CH_EPI_WARPS * CG);
         fence_barrier_init();
     }
     if (warp == CH_WARP_TMA && lane == 0) {
@@ -110,114 +136,146 @@ tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_consta
         }
         if (P.has_in) tma_prefetch_desc(&maps.wgt_in);
     }
-    if (warp == CH_WARP_MMA) tmem_alloc(&S.tmem_base, 512);
+    if (warp == CH_WARP_MMA) { if (PAIR) tmem_alloc_2cta(&S.tmem_base, 512); else tmem_alloc(&S.tmem_base, 512); }
     for (uint32_t i = threadIdx.x; i < 4 * 256; i += blockDim.x) S.vecs[i >> 8][i & 255] = P.vecs[i >> 8] ? __ldg(P.vecs[i >> 8] + (i & 255)) : 0.f;
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();              // the peer's barriers exist before anything remote touches them
     tc_fence_after();
     const uint32_t tmem_base = S.tmem_base;
-    const uint32_t in_box_bytes = P.in_dim * 128;
+    const uint32_t in_rows = P.in_dim / CG, in_box_bytes = in_rows * 128;
 
     if (warp == CH_WARP_TMA) {
-        // ===================================================== TMA producer: operands of R_l, D_l (and the input stage), in issue order
+        // ===================================================== weight producer (both CTAs): own half of every chunk, in MMA issue order
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            auto next = [&]() { if (++stage == BC_STAGES) { stage = 0; phase ^= 1; } };
-            for (uint32_t t = t_begin; t < t_end; t++) {
-                const int32_t row0 = (int32_t)(t * CH_TILE_M);
+            auto put = [&](const CUtensorMap* m, uint32_t bytes, int32_t c0, int32_t c1) {
+                mbar_wait(&S.w_empty[stage], phase ^ 1);
+                if (leader) mbar_arrive_expect_tx(&S.w_full[stage], CG * bytes);
+                if (PAIR) tma_load_2d_2cta(smW + stage * W_BYTES, m, &S.w_full[stage], c0, c1);
+                else tma_load_2d(smW + stage * W_BYTES, m, &S.w_full[stage], c0, c1);
+                if (++stage == NW) { stage = 0; phase ^= 1; }
+            };
+            for (uint32_t u = u_begin; u < u_end; u++) {
+                const uint32_t t = u * CG + rank;
                 const int32_t img = (int32_t)((t * CH_TILE_M) / P.rows_per_image);
                 for (uint32_t i = 0; i < nL; i++) {
                     const uint32_t nk = P.layer[i].nk;
                     for (uint32_t kc = 0; kc < nk; kc++) {
-                        mbar_wait(&S.empty[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&S.full[stage], 16384 + P.w_bytes);
-                        uint8_t* st = smRING + stage * BC_STAGE_BYTES;
-                        tma_load_2d(st, &maps.w[i], &S.full[stage], (int32_t)(kc * 64), 0);
-                        tma_load_2d(st + 32768, &maps.a[i], &S.full[stage], (int32_t)(kc * 64), row0);
-                        next();
+                        // a 5th K chunk (view tail) does not fit the A buffer: its activation half travels through this ring too
+                        if (kc >= NA) put(&maps.a[i], CH_CHUNK_BYTES, (int32_t)(kc * 64), (int32_t)(t * CH_TILE_M));
+                        put(&maps.w[i], W_BYTES, (int32_t)(kc * 64), (int32_t)(rank * W_ROWS));
                     }
                     if (P.layer[i].do_D)
-                        for (uint32_t kc = 0; kc < 4; kc++) {
-                            mbar_wait(&S.empty[stage], phase ^ 1);
-                            mbar_arrive_expect_tx(&S.full[stage], P.w_bytes);
-                            tma_load_2d(smRING + stage * BC_STAGE_BYTES, &maps.wgt[i], &S.full[stage], (int32_t)(kc * 64), img * 256);
-                            next();
-                        }
+                        for (uint32_t kc = 0; kc < 4; kc++) put(&maps.wgt[i], W_BYTES, (int32_t)(kc * 64), img * 256 + (int32_t)(rank * W_ROWS));
                 }
                 if (P.has_in)
-                    for (uint32_t kc = 0; kc < 4; kc++) {
-                        mbar_wait(&S.empty[stage], phase ^ 1);
-                        mbar_arrive_expect_tx(&S.full[stage], in_box_bytes);
-                        tma_load_2d(smRING + stage * BC_STAGE_BYTES, &maps.wgt_in, &S.full[stage], (int32_t)(kc * 64), 0);
-                        next();
+                    for (uint32_t kc = 0; kc < 4; kc++) put(&maps.wgt_in, in_box_bytes, (int32_t)(kc * 64), (int32_t)(rank * in_rows));
+            }
+        }
+    } else if (warp == CH_WARP_LOAD) {
+        // ===================================================== activation producer (both CTAs): saved layer inputs of the own tile
+        if (lane == 0) {
+            uint32_t agen = 0;
+            for (uint32_t u = u_begin; u < u_end; u++) {
+                const int32_t row0 = (int32_t)((u * CG + rank) * CH_TILE_M);
+                for (uint32_t i = 0; i < nL; i++, agen++) {
+                    const uint32_t nk = min(P.layer[i].nk, NA);
+                    mbar_wait(&S.a_empty, (agen & 1) ^ 1);            // every MMA that read the previous tile has completed
+                    for (uint32_t kc = 0; kc < nk; kc++) {
+                        if (leader) mbar_arrive_expect_tx(&S.a_full[kc], CG * CH_CHUNK_BYTES);
+                        if (PAIR) tma_load_2d_2cta(smA + kc * CH_CHUNK_BYTES, &maps.a[i], &S.a_full[kc], (int32_t)(kc * 64), row0);
+                        else tma_load_2d(smA + kc * CH_CHUNK_BYTES, &maps.a[i], &S.a_full[kc], (int32_t)(kc * 64), row0);
                     }
+                }
             }
         }
     } else if (warp == CH_WARP_MMA) {
-        // ===================================================== MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = idesc_f16(CH_TILE_M, 256, FMT_F16, FMT_F16, 0, 0);
-            const uint32_t idesc_in = idesc_f16(CH_TILE_M, P.in_dim, FMT_F16, FMT_F16, 0, 0);
+        // ===================================================== MMA issuer (leader CTA only)
+        if (lane == 0 && leader) {
+            const uint32_t idesc = idesc_f16(CH_TILE_M * CG, 256, FMT_F16, FMT_F16, 0, 0);
+            const uint32_t idesc_in = idesc_f16(CH_TILE_M * CG, P.in_dim, FMT_F16, FMT_F16, 0, 0);
             const uint32_t g_addr = smem_u32(smG);
             uint32_t stage = 0, phase = 0, nR = 0, nD = 0, dzgen = 0, it = 0;
-            auto next = [&]() { if (++stage == BC_STAGES) { stage = 0; phase ^= 1; } };
-            for (uint32_t t = t_begin; t < t_end; t++, it++) {
+            auto next = [&]() { if (++stage == NW) { stage = 0; phase ^= 1; } };
+            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t accum) {
+                if (PAIR) umma_f16_2cta(d, da, db, id, accum); else umma_bf16(d, da, db, id, accum);
+            };
+            auto commit = [&](uint64_t* bar) { if (PAIR) umma_commit_2cta(bar, 3); else umma_commit(bar); };
+            auto wait_x = [&](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };
+            for (uint32_t u = u_begin; u < u_end; u++, it++) {
                 for (uint32_t i = 0; i < nL; i++) {
                     const uint32_t nk = P.layer[i].nk, lks = P.layer[i].last_ksteps;
                     // ---- R_l -> accumulator 0
-                    mbar_wait(&S.accR_empty, (nR & 1) ^ 1);
+                    wait_x(&S.accR_empty, (nR & 1) ^ 1);
                     tc_fence_after();
                     CH_DBG(0, 50 + i);
                     uint32_t accumulate = 0;
                     for (uint32_t kc = 0; kc < nk; kc++) {
-                        mbar_wait(&S.full[stage], phase);
+                        uint32_t a_addr;
+                        uint64_t* tail_bar = nullptr;
+                        if (kc < NA) {
+                            mbar_wait(&S.a_full[kc], nR & 1);
+                            a_addr = smem_u32(smA + kc * CH_CHUNK_BYTES);
+                        } else {                                          // view tail: the activation chunk sits in the W ring
+                            mbar_wait(&S.w_full[stage], phase);
+                            a_addr = smem_u32(smW + stage * W_BYTES);
+                            tail_bar = &S.w_empty[stage];
+                            next();
+                        }
+                        CH_DBG(0, 3000 + i * 16 + kc);
+                        mbar_wait(&S.w_full[stage], phase);
                         tc_fence_after();
-                        const uint32_t b_addr = smem_u32(smRING + stage * BC_STAGE_BYTES), a_addr = b_addr + 32768;
+                        CH_DBG(0, 4000 + i * 16 + kc);
+                        const uint32_t b_addr = smem_u32(smW + stage * W_BYTES);
                         const uint32_t ks = kc + 1 == nk ? lks : 4;
                         for (uint32_t s = 0; s < ks; s++, accumulate = 1)
-                            umma_bf16(tmem_base, smem_desc_sw128(a_addr + s * 32, 16, 1024), smem_desc_sw128(b_addr + s * 32, 16, 1024), idesc, accumulate);
-                        umma_commit(&S.empty[stage]);
+                            mma(tmem_base, smem_desc_sw128(a_addr + s * 32, 16, 1024), smem_desc_sw128(b_addr + s * 32, 16, 1024), idesc, accumulate);
+                        if (tail_bar) commit(tail_bar);
+                        commit(&S.w_empty[stage]);
                         next();
                     }
-                    umma_commit(&S.accR_full);
+                    commit(&S.a_empty);
+                    commit(&S.accR_full);
                     CH_DBG(0, 100 + i);
                     nR++;
-                    // ---- D_l -> accumulator 1, chunk by chunk behind the epilogue
+                    // ---- D_l -> accumulator 1, chunk by chunk behind the epilogue(s)
                     if (P.layer[i].do_D) {
-                        mbar_wait(&S.accD_empty, (nD & 1) ^ 1);
+                        wait_x(&S.accD_empty, (nD & 1) ^ 1);
                         tc_fence_after();
                         for (uint32_t kc = 0; kc < 4; kc++) {
-                            mbar_wait(&S.dz_ready[kc], dzgen & 1);
-                            mbar_wait(&S.full[stage], phase);
+                            wait_x(&S.dz_ready[kc], dzgen & 1);
+                            CH_DBG(0, 1000 + i * 16 + kc);
+                            mbar_wait(&S.w_full[stage], phase);
                             tc_fence_after();
-                            const uint32_t b_addr = smem_u32(smRING + stage * BC_STAGE_BYTES), a_addr = g_addr + kc * CH_CHUNK_BYTES;
+                            CH_DBG(0, 2000 + i * 16 + kc);
+                            const uint32_t b_addr = smem_u32(smW + stage * W_BYTES), a_addr = g_addr + kc * CH_CHUNK_BYTES;
                             for (uint32_t s = 0; s < 4; s++)
-                                umma_bf16(tmem_base + 256, smem_desc_sw128(a_addr + s * 32, 16, 1024), smem_desc_sw128(b_addr + s * 32, 16, 1024), idesc, (kc | s) != 0);
-                            umma_commit(&S.empty[stage]);
+                                mma(tmem_base + 256, smem_desc_sw128(a_addr + s * 32, 16, 1024), smem_desc_sw128(b_addr + s * 32, 16, 1024), idesc, (kc | s) != 0);
+                            commit(&S.w_empty[stage]);
                             CH_DBG(0, 200 + i * 16 + kc);
                             next();
                         }
-                        umma_commit(&S.accD_full);
+                        commit(&S.accD_full);
                         nD++;
                     } else {
-                        for (uint32_t kc = 0; kc < 4; kc++) mbar_wait(&S.dz_ready[kc], dzgen & 1);   // keep the phase parity in step
+                        for (uint32_t kc = 0; kc < 4; kc++) wait_x(&S.dz_ready[kc], dzgen & 1);   // keep the phase parity in step
                     }
                     dzgen++;
                 }
                 if (P.has_in) {
-                    mbar_wait(&S.accD_empty, (nD & 1) ^ 1);
+                    wait_x(&S.accD_empty, (nD & 1) ^ 1);
                     tc_fence_after();
                     for (uint32_t kc = 0; kc < 4; kc++) {
-                        mbar_wait(&S.dh0_ready[kc], it & 1);
-                        mbar_wait(&S.full[stage], phase);
+                        wait_x(&S.dh0_ready[kc], it & 1);
+                        mbar_wait(&S.w_full[stage], phase);
                         tc_fence_after();
-                        const uint32_t b_addr = smem_u32(smRING + stage * BC_STAGE_BYTES), a_addr = g_addr + kc * CH_CHUNK_BYTES;
+                        const uint32_t b_addr = smem_u32(smW + stage * W_BYTES), a_addr = g_addr + kc * CH_CHUNK_BYTES;
                         for (uint32_t s = 0; s < 4; s++)
-                            umma_bf16(tmem_base + 256, smem_desc_sw128(a_addr + s * 32, 16, 1024), smem_desc_sw128(b_addr + s * 32, 16, 1024), idesc_in, (kc | s) != 0);
-                        umma_commit(&S.empty[stage]);
+                            mma(tmem_base + 256, smem_desc_sw128(a_addr + s * 32, 16, 1024), smem_desc_sw128(b_addr + s * 32, 16, 1024), idesc_in, (kc | s) != 0);
+                        commit(&S.w_empty[stage]);
                         next();
                     }
-                    umma_commit(&S.accD_full);
+                    commit(&S.accD_full);
                     nD++;
                 }
             }
@@ -226,11 +284,11 @@ tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_consta
         // ===================================================== storer (STORE): du tiles and dh_0 -> HBM for the weight-gradient kernels
         if (STORE && lane == 0) {
             uint32_t dzgen = 0, it = 0;
-            for (uint32_t t = t_begin; t < t_end; t++, it++) {
-                const int32_t row0 = (int32_t)(t * CH_TILE_M);
+            for (uint32_t u = u_begin; u < u_end; u++, it++) {
+                const int32_t row0 = (int32_t)((u * CG + rank) * CH_TILE_M);
                 for (uint32_t i = 0; i < nL; i++, dzgen++)
                     for (uint32_t c = 0; c < 4; c++) {
-                        mbar_wait(&S.dz_ready[c], dzgen & 1);
+                        mbar_wait(&S.dz_ready_st[c], dzgen & 1);
                         tma_store_2d(&maps.dz[i], smG + c * CH_CHUNK_BYTES, (int32_t)(c * 64), row0);
                         tma_store_commit();
                         tma_store_wait_read();
@@ -238,7 +296,7 @@ tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_consta
                     }
                 if (P.has_in)
                     for (uint32_t c = 0; c < 4; c++) {
-                        mbar_wait(&S.dh0_ready[c], it & 1);
+                        mbar_wait(&S.dh0_ready_st[c], it & 1);
                         tma_store_2d(&maps.dh0, smG + c * CH_CHUNK_BYTES, (int32_t)(c * 64), row0);
                         tma_store_commit();
                         tma_store_wait_read();
@@ -256,9 +314,12 @@ tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_consta
         const uint32_t u0 = ((2 * sb) ^ (r & 7)) << 4, u1 = ((2 * sb + 1) ^ (r & 7)) << 4;
         const float gs = __ldg(P.gscale), gs_inv = __ldg(P.gscale + 1);
         const uint32_t lane_base = (q * 32) << 16;
+        // arrive on a barrier the leader's MMA thread waits on
+        auto arrive_mma = [&](uint64_t* bar) { if (PAIR && !leader) mbar_arrive_remote(bar, 0); else mbar_arrive(bar); };
         uint32_t nR = 0, nD = 0, stgen = 0, n = 0;
         bool stored_dh0 = false;                                        // G holds a dh_0 tile the storer is (or was) reading
-        for (uint32_t t = t_begin; t < t_end; t++) {
+        for (uint32_t u = u_begin; u < u_end; u++) {
+            const uint32_t t = u * CG + rank;
             const uint64_t row = (uint64_t)t * CH_TILE_M + r;
             const uint32_t img = (t * CH_TILE_M) / P.rows_per_image;
             for (uint32_t i = 0; i < nL; i++, n++) {
@@ -345,14 +406,18 @@ tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_consta
                         sts128(chunk + u1, h1);
                         fence_proxy_async();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&S.dz_ready[c]);
+                        if (lane == 0) {
+                            arrive_mma(&S.dz_ready[c]);
+                            if (STORE) mbar_arrive(&S.dz_ready_st[c]);
+                        }
                         if (threadIdx.x == 0) CH_DBG(1, 500 + i * 16 + c);
+                        if (threadIdx.x == 0 && P.dbg && blockIdx.x == 1 && dbg_n < 1023) { P.dbg[2 * 2048 + 2 * dbg_n] = 500 + i * 16 + c; P.dbg[2 * 2048 + 2 * dbg_n + 1] = clock64(); dbg_n++; }
                     }
                     if (STORE && stored_dh0 && i == 0) { stgen++; stored_dh0 = false; }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&S.accR_empty);
+                if (lane == 0) arrive_mma(&S.accR_empty);
                 nR++;
 
                 // ---------------- epi_D: G = fp16(dh' + rank-1 term)
@@ -390,13 +455,16 @@ tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_consta
                         if (to_in) {
                             fence_proxy_async();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(&S.dh0_ready[c]);
+                            if (lane == 0) {
+                                arrive_mma(&S.dh0_ready[c]);
+                                if (STORE) mbar_arrive(&S.dh0_ready_st[c]);
+                            }
                         }
                     }
                     if (STORE) stgen++;
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&S.accD_empty);
+                    if (lane == 0) arrive_mma(&S.accD_empty);
                     if (threadIdx.x == 0) CH_DBG(1, 800 + i);
                     nD++;
                 } else if (STORE) {
@@ -423,15 +491,15 @@ tc_chain_bwd_kernel(const __grid_constant__ BChainMaps maps, const __grid_consta
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&S.accD_empty);
+                if (lane == 0) arrive_mma(&S.accD_empty);
                 nD++;
                 if (STORE) stored_dh0 = true;
             }
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == CH_WARP_MMA) tmem_dealloc(tmem_base, 512);
+    if (PAIR) cluster_sync_all(); else __syncthreads();              // nobody may exit while the pair can still touch its shared / tensor memory
+    if (warp == CH_WARP_MMA) { if (PAIR) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
 }
 
 }  // namespace tc
