@@ -103,6 +103,10 @@ int sdfg_grid_corner_indices(const float* inputs, const int* offsets, uint32_t* 
                              uint32_t N, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, float bound,
                              uint32_t gridtype, int align_corners, void* stream);
 
+/* roofline probe (measurement aid, not part of the reference interface): `threads` threads each issue 8*rounds random 8-byte
+ * gathers from buf[n_rows][2]; time it with events to get the device's random-gather rate over a table-sized buffer. */
+int sdfg_l2_gather_probe(const float* buf, uint32_t n_rows, uint32_t threads, uint32_t rounds, float* sink, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Spherical harmonics of the view direction.
  * ref: sh_encode_forward shencoder/src/shencoder.h:9, shencoder.cu:400-416 (kernel_sh :27-355);

@@ -1,0 +1,99 @@
+"""Per-kernel roofline measurements of the non-GEMM kernels of the path (encoder, compositing) plus the inference forward,
+at the BASELINE config sizes.  Device-timed with CUDA events after warm-up; prints one JSON object.
+
+    python scripts/bench_kernels.py [B]      # B = images per pass (default 32; configs[2] uses 64 / n_gpus)
+"""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import sdface_gan_b200 as sg
+from sdface_gan_b200 import ops
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+dev = "cuda"
+R, S = 64, 24
+N = B * R * R * S
+peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+hbm_peak = next((v for k, v in peaks.items() if "hbm" in k.lower() and isinstance(v, (int, float))), 6547.0)
+
+
+def timed(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+torch.manual_seed(0)
+mo, ro = sg.default_options("ngp", renderer_res=R, n_samples=S, perturb=0.)
+g = sg.Generator(mo, ro, full_pipeline=False, ema=True).to(dev).eval()
+net = g.renderer.network
+enc = net.encoder
+cam, focal, near, far, _ = sg.generate_camera_params(R, dev, batch=B)
+z = torch.randn(B, 256, device=dev)
+out = {"B": B, "samples": N, "hbm_peak_GBps": hbm_peak}
+
+# --- L2 random-gather roofline: table-sized buffer (50.6 MB), 8 B per gather
+tab = enc.embeddings.detach()
+threads, rounds = 148 * 2048 * 4, 64
+ms = timed(lambda: ops.l2_gather_probe(tab, threads, rounds))
+gathers = threads * 8 * rounds
+out["l2_gather_probe"] = {"table_MB": tab.numel() * 4 / 1e6, "Ggathers_per_s": gathers / ms / 1e6, "GBps_8B": gathers * 8 / ms / 1e6}
+
+# --- encoder on the real ray samples (the points are NOT uniform: SURVEY 8d)
+with torch.no_grad():
+    smp, _, _ = g.renderer._sample(cam, focal, near, far, t_rand=None)
+pts = smp["npts"].reshape(-1, 3).contiguous()
+Sg, H = ops.log2_scale(enc.per_level_scale), enc.base_resolution
+feats = torch.empty(N, 32, device=dev)
+dy = torch.empty(96, N, device=dev)
+ms_f = timed(lambda: ops.grid_encode_forward(pts, tab, enc.offsets, Sg, H, bound=2.0, outputs=feats))
+ms_fd = timed(lambda: ops.grid_encode_forward(pts, tab, enc.offsets, Sg, H, bound=2.0, calc_dy_dx=True, outputs=feats, dy_dx=dy))
+grad = torch.randn(N, 32, device=dev)
+gt = torch.zeros_like(tab)
+ms_b = timed(lambda: ops.grid_encode_backward(grad, pts, tab, enc.offsets, Sg, H, bound=2.0, grad_embeddings=gt))
+probe = out["l2_gather_probe"]["Ggathers_per_s"]
+out["grid_forward"] = {"ms": ms_f, "hbm_GBps": N * 140 / ms_f / 1e6, "Ggathers_per_s": N * 128 / ms_f / 1e6,
+                       "frac_of_l2_gather_probe": N * 128 / ms_f / 1e6 / probe}
+out["grid_forward_dydx"] = {"ms": ms_fd, "hbm_GBps": N * (140 + 384) / ms_fd / 1e6, "frac_of_hbm": N * (140 + 384) / ms_fd / 1e6 / hbm_peak,
+                            "frac_of_l2_gather_probe": N * 128 / ms_fd / 1e6 / probe}
+out["grid_backward"] = {"ms": ms_b, "Greductions_8B_per_s": N * 128 / ms_b / 1e6, "frac_of_l2_gather_probe": N * 128 / ms_b / 1e6 / probe}
+
+# --- compositing: full-feature inference variant (fp16 features from the field chain) and the stage-1 variant (no features)
+sdf = torch.randn(N, device=dev) * 0.05
+rgb = torch.randn(N, 3, device=dev)
+f16 = torch.randn(N, 256, device=dev).half()
+zv = smp["z_vals"].reshape(-1).contiguous()
+rd = smp["rays_d"].reshape(-1, 3).contiguous()
+ptsw = smp["pts"].reshape(-1, 3).contiguous()
+sb = g.renderer.sigmoid_beta.detach()
+ms_c = timed(lambda: ops.composite_forward(sdf, rgb, f16, zv, rd, ptsw, None, sb, S, True, False, False))
+bytes_c = N * (4 + 12 + 512 + 4) + (N // S) * (12 + 1024 + 12)
+out["composite_forward_feat16"] = {"ms": ms_c, "hbm_GBps": bytes_c / ms_c / 1e6, "frac_of_hbm": bytes_c / ms_c / 1e6 / hbm_peak}
+f32 = f16.float()
+ms_c32 = timed(lambda: ops.composite_forward(sdf, rgb, f32, zv, rd, ptsw, None, sb, S, True, False, False))
+bytes_c32 = N * (4 + 12 + 1024 + 4) + (N // S) * (12 + 1024 + 12)
+out["composite_forward_feat32"] = {"ms": ms_c32, "hbm_GBps": bytes_c32 / ms_c32 / 1e6, "frac_of_hbm": bytes_c32 / ms_c32 / 1e6 / hbm_peak}
+ms_c0 = timed(lambda: ops.composite_forward(sdf, rgb, None, zv, rd, ptsw, None, sb, S, True, False, False))
+bytes_c0 = N * (4 + 12 + 4) + (N // S) * 24
+out["composite_forward_nofeat"] = {"ms": ms_c0, "hbm_GBps": bytes_c0 / ms_c0 / 1e6, "frac_of_hbm": bytes_c0 / ms_c0 / 1e6 / hbm_peak}
+
+# --- inference forward of the renderer (configs[2] field part): rays -> encoder -> field chain -> compositing
+sg._lib.prof_enable(True, "gemm")
+with torch.no_grad():
+    ms_fw = timed(lambda: g([z], cam, focal, near, far), reps=5)
+sg._lib.prof_enable(False, "")
+kms, kn = sg._lib.prof_collect()
+flop = N * 2 * (32 * 256 + 3 * 256 * 256 + 256 + 272 * 256 + 768)
+tc_peak = peaks.get("bf16_tflops_sustained", 1393.1)
+out["inference_forward"] = {"ms": ms_fw, "images_per_s": B / ms_fw * 1e3, "Msamples_per_s": N / ms_fw / 1e3,
+                            "field_chain_ms": kms / max(kn, 1), "field_chain_TFLOPs": flop / (kms / max(kn, 1) * 1e-3) / 1e12,
+                            "field_chain_frac_of_tensor_peak": flop / (kms / max(kn, 1) * 1e-3) / 1e12 / tc_peak}
+print(json.dumps(out))

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "sdfg_grad_total_variation": (i32, [vp, vp, vp, vp, f32, u32, u32, u32, u32, f32, u32, u32, i32, vp]),
     "sdfg_grid_level_scales": (i32, [vp, u32, f32, u32, vp]),
     "sdfg_grid_corner_indices": (i32, [vp, vp, vp, vp, u32, u32, u32, u32, f32, u32, f32, u32, i32, vp]),
+    "sdfg_l2_gather_probe": (i32, [vp, u32, u32, u32, vp, vp]),
     "sdfg_sh_encode_forward": (i32, [vp, vp, u32, u32, vp, vp]),
     "sdfg_sh_encode_backward": (i32, [vp, vp, vp, u32, u32, vp]),
     "sdfg_field_workspace_bytes": (u64, [ctypes.POINTER(FieldParams), u64, i32, i32]),

@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256) grid_forward_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// backward scatter: thread per (sample, level); the level is blockIdx.y so a warp's reductions hit one level's table
+// backward scatter: thread per sample, loop over levels (a warp's reductions of one iteration hit one level's table)
 template <uint32_t D, uint32_t C>
 __global__ void __launch_bounds__(256) grid_backward_kernel(const float* __restrict__ grad, const float* __restrict__ inputs,
                                                             const int* __restrict__ offsets, float* __restrict__ grad_table,
@@ -527,6 +527,27 @@ static int check_shape(uint32_t D, uint32_t C, uint32_t L) {
         }                                                              \
     } while (0)
 
+// ---------------------------------------------------------------------------------------------------------------
+// Roofline probe: random 8-byte gathers from a table-sized buffer (what the encoder's corner fetches look like to L2), 8
+// independent gathers in flight per thread, indices from an integer hash (no index traffic).  Gives the denominator of the
+// encoder's "L2 gather" roofline fraction on the GPU at hand (MEASURED_PEAKS.json has no such figure).
+__global__ void __launch_bounds__(256) l2_gather_probe_kernel(const float2* __restrict__ buf, uint32_t n_rows, uint32_t rounds,
+                                                              float* __restrict__ sink) {
+    uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    float acc = 0.f;
+    for (uint32_t r = 0; r < rounds; r++) {
+        float2 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            x ^= x << 13; x ^= x >> 17; x ^= x << 5;                  // xorshift32
+            v[j] = __ldg(buf + (x % n_rows));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc += v[j].x + v[j].y;
+    }
+    if (acc == 123.456f) sink[0] = acc;                             // keep the loads alive
+}
+
 }  // namespace sdfg
 
 using namespace sdfg;
@@ -590,4 +611,10 @@ extern "C" int sdfg_grid_corner_indices(const float* inputs, const int* offsets,
     if (D == 3) grid_corner_kernel<3><<<blocks, 256, 0, st>>>(inputs, offsets, corner_idx, corner_w, N, L, S, H, bound, gridtype, align_corners);
     else grid_corner_kernel<2><<<blocks, 256, 0, st>>>(inputs, offsets, corner_idx, corner_w, N, L, S, H, bound, gridtype, align_corners);
     return check_launch("grid_corner_kernel");
+}
+
+extern "C" int sdfg_l2_gather_probe(const float* buf, uint32_t n_rows, uint32_t threads, uint32_t rounds, float* sink, void* stream) {
+    SDFG_REQUIRE(buf && sink && n_rows > 0, SDFG_ERR_INVALID, "l2_gather_probe: null pointer");
+    l2_gather_probe_kernel<<<ceil_div<uint32_t>(threads, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(buf), n_rows, rounds, sink);
+    return check_launch("l2_gather_probe_kernel");
 }

@@ -132,6 +132,16 @@ def grid_corner_indices(inputs, offsets, C, S, H, bound=0.0, gridtype=0, align_c
     return idx, w
 
 
+def l2_gather_probe(buf, threads, rounds):
+    """Issue threads*8*rounds random 8-byte gathers from buf [rows, 2] (roofline probe; time it with CUDA events)."""
+    lib = _lib.load()
+    _chk(buf, "buf")
+    sink = torch.zeros(1, device=buf.device)
+    with torch.cuda.device(buf.device):
+        _lib.check(lib.sdfg_l2_gather_probe(_ptr(buf), buf.shape[0], int(threads), int(rounds), _ptr(sink), _stream()), "sdfg_l2_gather_probe")
+    return threads * 8 * rounds
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # spherical harmonics
 
