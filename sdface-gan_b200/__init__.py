@@ -6,6 +6,6 @@ Import through the alias module at the repo root (``import sdface_gan_b200``) or
 from . import _lib, distributed, ops  # noqa: F401
 from .gridencoder import GridEncoder, grid_encode  # noqa: F401
 from .shencoder import SHEncoder, sh_encode  # noqa: F401
-from .sdf_model import (FiLMSiren, Generator, LinearLayer, MappingLinear, NGPSIRENGenerator, SirenGenerator,  # noqa: F401
+from .sdf_model import (FCGenerator, FiLMSiren, Generator, LinearLayer, MappingLinear, NGPSIRENGenerator, SirenGenerator,  # noqa: F401
                         VolumeFeatureRenderer, get_encoder, register_decoder)
 from .sdf_utils import Munch, default_options, generate_camera_params  # noqa: F401

@@ -330,6 +330,62 @@ class _grid_encode_keep(Function):
         return None, ge, None, None, None, None, None, None, None
 
 
+class FCGenerator(nn.Module):
+    """`--fc 1` ablation (ref :1599-1670): positional encoding -> ReLU MLP with the style added after the first layer.  Kept
+    for drop-in completeness: it runs on the GPU through cuBLAS (torch) between this package's ray-sampling and compositing
+    kernels; it is NOT one of the fused tensor-core kernels (the north-star configuration is `--ngp 1 --fc 0`)."""
+
+    def __init__(self, D=8, W=256, style_dim=256, input_ch=3, input_ch_views=3, output_ch=4, output_features=True):
+        super().__init__()
+        self.D, self.W = D, W
+        self.input_ch, self.input_ch_views = input_ch, input_ch_views
+        self.style_dim = style_dim
+        self.output_features = output_features
+        self.n_freq_posenc, self.n_freq_posenc_views = 10, 4
+        self.x_in = nn.Linear(3 * self.n_freq_posenc * 2, W)
+        self.style_in = nn.Linear(style_dim, W)
+        self.pts_linears = nn.ModuleList([nn.Linear(W, W) for _ in range(D - 1)])
+        self.views_linears = nn.Linear(3 * self.n_freq_posenc_views * 2 + W, W)
+        self.rgb_linear = nn.Linear(W, 3)
+        self.sigma_linear = nn.Linear(W, 1)
+
+    def transform_points(self, p, views=False):
+        p = p / 2
+        L = self.n_freq_posenc_views if views else self.n_freq_posenc
+        return torch.cat([torch.cat([torch.sin((2 ** i) * math.pi * p), torch.cos((2 ** i) * math.pi * p)], dim=-1) for i in range(L)], dim=-1)
+
+    def forward(self, x, styles):
+        if not x.is_cuda:
+            raise RuntimeError("x must be a CUDA tensor (this path has no CPU fallback)")
+        input_pts, input_views = torch.split(x, [self.input_ch, self.input_ch_views], dim=-1)
+        input_pts = self.transform_points(input_pts)
+        input_views = self.transform_points(input_views, True)
+        style_in = self.style_in(styles).view([styles.shape[0]] + [1] * (x.dim() - 2) + [-1])
+        h = F.relu(self.x_in(input_pts) + style_in)
+        for lin in self.pts_linears:
+            h = F.relu(lin(h))
+        sdf = self.sigma_linear(h)
+        feat = self.views_linears(torch.cat([h, input_views], -1))
+        out = [self.rgb_linear(feat), sdf]
+        if self.output_features:
+            out.append(feat)
+        return torch.cat(out, -1)
+
+    def forward_rays(self, npts, viewdirs, styles, want_rgb=True, want_feat=True, want_dsdf=False, feat_f16=False):
+        B, R1, R2, S, _ = npts.shape
+        if want_dsdf:
+            npts = npts.detach().requires_grad_(True)
+        x = torch.cat([npts, viewdirs[:, :, :, None, :].expand(B, R1, R2, S, 3)], -1)
+        out = self.forward(x, styles)
+        sdf = out[..., 3].reshape(-1)
+        rgb = out[..., :3].reshape(-1, 3).contiguous()
+        feat = out[..., 4:].reshape(-1, self.W).contiguous() if (want_feat and self.output_features) else None
+        dsdf = None
+        if want_dsdf:       # ref get_eikonal_term :224-229 (second-order capable: plain torch ops)
+            dsdf = torch.autograd.grad(sdf, npts, torch.ones_like(sdf), create_graph=torch.is_grad_enabled())[0].reshape(-1, 3)
+        return sdf, rgb, feat, dsdf
+
+
 # --------------------------------------------------------------------------------------------------------------------------
 # compositing as one autograd node
 
@@ -411,7 +467,8 @@ class VolumeFeatureRenderer(nn.Module):
         if opt.type == "ngp":
             self.network = NGPSIRENGenerator(D=2, W=style_dim, style_dim=style_dim, output_features=self.output_features)
         elif opt.fc:
-            raise NotImplementedError("--fc 1 (FCGenerator, ref :1599-1670) is an ablation outside the accelerated path")
+            self.network = FCGenerator(D=opt.depth, W=opt.width, style_dim=style_dim, input_ch=self.input_ch, output_ch=4,
+                                       input_ch_views=self.input_ch_views, output_features=self.output_features)
         else:
             self.network = SirenGenerator(D=opt.depth, W=opt.width, style_dim=style_dim, input_ch=self.input_ch, output_ch=4,
                                           input_ch_views=self.input_ch_views, output_features=self.output_features)

@@ -71,6 +71,8 @@ def product_generator(z, device, precision="fp32", seed=0):
             over[k] = bool(r[k])
     if cfg["no_features_output"]:
         over["no_features_output"] = True
+    if cfg.get("fc"):
+        over["fc"] = 1
     mo, ro = sg.default_options(cfg["net_type"], renderer_res=cfg["res"], n_samples=cfg["S"], **over)
     g = sg.Generator(mo, ro, full_pipeline=False)
     pf.fill_state(g, pf.table_from_npz(z), seed, table_std_override=cfg["table_std"])

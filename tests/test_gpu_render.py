@@ -38,7 +38,7 @@ def _gen_kwargs(z):
     return kw
 
 
-@pytest.mark.parametrize("name", ["siren_fwd", "ngp_fwd_init", "ngp_fwd_tab1", "ngp_mesh", "ngp_nosdf_strat"])
+@pytest.mark.parametrize("name", ["siren_fwd", "ngp_fwd_init", "ngp_fwd_tab1", "ngp_mesh", "ngp_nosdf_strat", "fc_fwd"])
 def test_generator_forward_matches_reference_fixture(name):
     z = H.load_fixture(name)
     g = H.product_generator(z, DEV)
