@@ -372,44 +372,64 @@ __global__ void __launch_bounds__(128) wgrad_finish_kernel(const float* __restri
     if (threadIdx.x == 0) db[j] += dbj;
 }
 
-// head weight gradient: dw[c, k] += sum_n dout[n, c] * h[n, k]   (h fp16, pitch ld), db[c] += sum_n dout[n, c].
-// Block = 256 columns x 2 row groups: a thread owns a column PAIR (one 4-byte load per row) and every other row; 8 rows are in
-// flight per thread so the fp16 stream runs at HBM speed (512 B per sample).
+// head weight gradient: dw[c, k] += sum_n dout[n, c] * h[n, k]   (h fp16 [*, 256], pitch ld), db[c] += sum_n dout[n, c].
+// A warp reads one 512-byte row per load instruction (16 bytes per lane), 8 warps x 4 rows are in flight per block; the
+// per-warp partial sums meet in shared memory and one warp per head issues the global reductions.
 template <int NOUT>
 __global__ void __launch_bounds__(256) head_wgrad16_kernel(const float* __restrict__ dout, const h16* __restrict__ h, int64_t ld,
                                                             float* __restrict__ dw, float* __restrict__ db, uint64_t M, uint32_t rows_per_block) {
-    const uint32_t cp = threadIdx.x & 127, rg = threadIdx.x >> 7;
+    __shared__ float red[8][NOUT][256 + 8];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t m0 = (uint64_t)blockIdx.x * rows_per_block, m1 = min(M, m0 + rows_per_block);
-    float gw0[NOUT], gw1[NOUT], gb[NOUT];
+    float acc[NOUT][8], gb[NOUT];
 #pragma unroll
-    for (int c = 0; c < NOUT; c++) { gw0[c] = 0.f; gw1[c] = 0.f; gb[c] = 0.f; }
-    constexpr int U = 8;
-    for (uint64_t m = m0 + rg; m < m1; m += 2 * U) {
-        uint32_t hv[U];
+    for (int c = 0; c < NOUT; c++) {
+        gb[c] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[c][k] = 0.f;
+    }
+    constexpr int U = 4;
+    for (uint64_t m = m0 + warp; m < m1; m += 8 * U) {
+        uint4 hv[U];
         float d[U][NOUT];
 #pragma unroll
         for (int j = 0; j < U; j++) {
-            const uint64_t mm = m + 2 * j;
-            const bool ok = mm < m1;
-            hv[j] = ok ? __ldg(reinterpret_cast<const uint32_t*>(h + mm * ld) + cp) : 0u;
+            const uint64_t mm = min(m + 8 * j, m1 - 1);
+            const float live = (m + 8 * j < m1) ? 1.f : 0.f;
+            hv[j] = __ldg(reinterpret_cast<const uint4*>(h + mm * ld) + lane);
 #pragma unroll
-            for (int c = 0; c < NOUT; c++) d[j][c] = ok ? __ldg(dout + mm * NOUT + c) : 0.f;
+            for (int c = 0; c < NOUT; c++) d[j][c] = live * __ldg(dout + mm * NOUT + c);
         }
 #pragma unroll
         for (int j = 0; j < U; j++) {
-            const float2 f = tc::unpack_f16(hv[j]);
+            const uint32_t w[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w};
 #pragma unroll
-            for (int c = 0; c < NOUT; c++) {
-                gw0[c] = fmaf(d[j][c], f.x, gw0[c]);
-                gw1[c] = fmaf(d[j][c], f.y, gw1[c]);
-                gb[c] += d[j][c];
+            for (int k = 0; k < 4; k++) {
+                const float2 f = tc::unpack_f16(w[k]);
+#pragma unroll
+                for (int c = 0; c < NOUT; c++) {
+                    acc[c][2 * k] = fmaf(d[j][c], f.x, acc[c][2 * k]);
+                    acc[c][2 * k + 1] = fmaf(d[j][c], f.y, acc[c][2 * k + 1]);
+                }
             }
+#pragma unroll
+            for (int c = 0; c < NOUT; c++) gb[c] += d[j][c];
         }
     }
 #pragma unroll
     for (int c = 0; c < NOUT; c++) {
-        red_add_v2(dw + (size_t)c * 256 + 2 * cp, gw0[c], gw1[c]);
-        if (cp == 0) red_add_f32(db + c, gb[c]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) red[warp][c][lane * 8 + k] = acc[c][k];
+        if (lane == 0) red[warp][c][256] = gb[c];
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < NOUT * 257; i += blockDim.x) {
+        const uint32_t c = i / 257, k = i % 257;
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) v += red[w][c][k];
+        if (k < 256) red_add_f32(dw + (size_t)c * 256 + k, v);
+        else red_add_f32(db + c, v);
     }
 }
 
