@@ -231,6 +231,36 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
 
+    # --- inference forward (configs[2], field part: rays -> encoder -> field chain -> compositing), same per-GPU batch
+    g_inf = sg.Generator(mo, ro, full_pipeline=False, ema=True).to(dev).eval()
+    g_inf.load_state_dict(g.state_dict())
+    g_inf.renderer.network.precision = args.precision
+    mo_f, ro_f = sg.default_options("ngp", renderer_res=R, n_samples=S, perturb=0.)
+    g_feat = sg.Generator(mo_f, ro_f, full_pipeline=False, ema=True).to(dev).eval()        # with the 256-channel feature map
+    g_feat.renderer.network.precision = args.precision
+    inf = {}
+    with torch.no_grad():
+        for name, gi in (("thumb_only", g_inf), ("with_features", g_feat)):
+            for _ in range(3):
+                gi([z], cam, focal, near, far)
+            barrier()
+            sg._lib.prof_enable(True, dominant)
+            i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            i0.record()
+            for _ in range(args.steps):
+                gi([z], cam, focal, near, far)
+            i1.record()
+            barrier()
+            sg._lib.prof_enable(False, "")
+            ik_ms, ik_n = sg._lib.prof_collect()
+            t = torch.tensor([i0.elapsed_time(i1) / args.steps], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ims = float(t.item())
+            inf[name] = {"ms_per_pass": ims, "images_per_s": world * B / (ims * 1e-3), "msamples_per_s": world * B * SAMPLES_PER_IMAGE / (ims * 1e-3) / 1e6,
+                         "field_chain_ms": ik_ms / max(ik_n, 1),
+                         "field_chain_tflops": B * SAMPLES_PER_IMAGE * FIELD_FLOP_FWD / (ik_ms / max(ik_n, 1) * 1e-3) / 1e12 if ik_n else None}
+
     if rank == 0:
         peaks = {}
         try:
@@ -248,9 +278,16 @@ def run_ours(args):
                          + (trunk + first)                      # eikonal pass: trunk dgrads + input-linear dgrad
                          + (2 * trunk + 2 * first + views + 2 * 256 * 256 + 2 * 16 * 256))   # backward: dgrad + wgrad
         achieved = flop_step / (k_ms / args.steps * 1e-3) / 1e12 if k_n else None
+        traffic, traffic_note = None, None
+        try:        # dram bytes per launch of the largest GEMM-class kernel, from the committed ncu --set full capture (B = 32)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if B == tj.get("batch") and args.precision == "tc16":
+                traffic, traffic_note = tj["dram_bytes_per_launch"], tj["note"]
+        except Exception:
+            pass
         roof = {"bound": "tensor", "kernel": "field GEMMs (%s)" % ("gemm_f32_kernel, fp32 SIMT" if args.precision == "fp32" else "tcgen05"),
                 "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": (achieved / tensor_peak) if achieved else None,
-                "traffic": None, "peak_source": peak_src, "kernel_ms_per_step": k_ms / args.steps, "kernel_launches_per_step": k_n / args.steps,
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "kernel_ms_per_step": k_ms / args.steps, "kernel_launches_per_step": k_n / args.steps,
                 "kernel_share_of_step": (k_ms / args.steps) / ms}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -267,14 +304,14 @@ def run_ours(args):
                    "sample": "1 image (98304 samples) per step, fwd+bwd, %d steps" % n}
         line = {"metric": "images/sec (generator fwd+bwd, field+composite)", "value": world * B / (ms * 1e-3), "unit": "images/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f16/bf16 operands, f32 accumulate", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "f16 operands (activations, loss-scaled gradients), f32 accumulate", "data": "synthetic",
                 "msamples_per_s": world * N / (ms * 1e-3) / 1e6,
                 "config": {"workload": "configs[1]: 64^2 SDF + hash-grid (ngp=1) generator forward+backward, stage-1 G step", "rays": R,
                            "samples_per_ray": S, "batch_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world,
-                           "l2": "per-step activations (%.1f GB) exceed L2; no flush needed" % (N * 256 * 4 * 8 / 1e9)},
+                           "l2": "per-step saved activations + gradient tiles (%.1f GB) exceed the 126 MB L2; no flush needed" % (N * 5.8e3 / 1e9)},
                 "clocks": clk.summary(),
                 "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": launches, "roofline": roof, "inference": inf, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
