@@ -96,4 +96,17 @@ tc_peak = peaks.get("bf16_tflops_sustained", 1393.1)
 out["inference_forward"] = {"ms": ms_fw, "images_per_s": B / ms_fw * 1e3, "Msamples_per_s": N / ms_fw / 1e3,
                             "field_chain_ms": kms / max(kn, 1), "field_chain_TFLOPs": flop / (kms / max(kn, 1) * 1e-3) / 1e12,
                             "field_chain_frac_of_tensor_peak": flop / (kms / max(kn, 1) * 1e-3) / 1e12 / tc_peak}
+# --- configs[4]: the sdf_mesh.py frustum query (sdf_mesh.py:243-253): R' x R' rays x R' samples, return_sdf + return_xyz,
+#     static view directions, forced background; R' = 128 is the reference call, R' = 256 the BASELINE "256^3" size
+out["sdf_mesh_query"] = {}
+for Rm in (128, 256):
+    mo_m, ro_m = sg.default_options("ngp", renderer_res=Rm, n_samples=Rm, perturb=0., return_sdf=True, return_xyz=True,
+                                    static_viewdirs=True, force_background=True)
+    gm = sg.Generator(mo_m, ro_m, full_pipeline=False, ema=True).to(dev).eval()
+    cam_m, focal_m, near_m, far_m, _ = sg.generate_camera_params(Rm, dev, batch=1)
+    with torch.no_grad():
+        ms_m = timed(lambda: gm([z[:1]], cam_m, focal_m, near_m, far_m, return_sdf=True, return_xyz=True), reps=3, warm=2)
+    out["sdf_mesh_query"]["R%d" % Rm] = {"points": Rm ** 3, "ms": ms_m, "Mpoints_per_s": Rm ** 3 / ms_m / 1e3}
+    del gm
+    torch.cuda.empty_cache()
 print(json.dumps(out))

@@ -15,7 +15,7 @@
 
 namespace sdfg {
 
-constexpr int kMaxPerLane = 4;   // samples per lane -> S <= 128
+constexpr int kMaxPerLane = 8;   // samples per lane -> S <= 256 (sdf_mesh.py renders 128- and 256-sample frusta)
 constexpr int kMaxF4 = 4;        // float4 per lane over the channels -> F <= 512
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -351,7 +351,8 @@ extern "C" int sdfg_composite_forward(const float* sdf, const float* rgb, const 
                                                          feat_map, xyz_map, mask, weights)
     if (S <= 32) LAUNCH(1);
     else if (S <= 64) LAUNCH(2);
-    else LAUNCH(4);
+    else if (S <= 128) LAUNCH(4);
+    else LAUNCH(8);
 #undef LAUNCH
     return check_launch("composite_forward_kernel");
 }
@@ -374,7 +375,8 @@ extern "C" int sdfg_composite_forward_h(const float* sdf, const float* rgb, cons
                                                                mask, weights)
     if (S <= 32) LAUNCH(1);
     else if (S <= 64) LAUNCH(2);
-    else LAUNCH(4);
+    else if (S <= 128) LAUNCH(4);
+    else LAUNCH(8);
 #undef LAUNCH
     return check_launch("composite_forward_kernel<h>");
 }
@@ -399,7 +401,8 @@ extern "C" int sdfg_composite_backward(const float* sdf, const float* rgb, const
                                                           d_mask, d_sdf, d_rgb, d_feat, d_pts, d_sigmoid_beta)
     if (S <= 32) LAUNCH(1);
     else if (S <= 64) LAUNCH(2);
-    else LAUNCH(4);
+    else if (S <= 128) LAUNCH(4);
+    else LAUNCH(8);
 #undef LAUNCH
     return check_launch("composite_backward_kernel");
 }

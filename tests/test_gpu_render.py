@@ -131,7 +131,7 @@ def test_compat_network_forward_matches_oracle():
 
 
 @pytest.mark.parametrize("S,F,with_sdf,fb", [(24, 256, True, False), (24, 0, True, False), (128, 256, True, True), (40, 64, False, False),
-                                              (1, 8, True, False)])
+                                              (1, 8, True, False), (256, 16, True, True), (200, 0, True, False)])
 def test_composite_forward_backward_matches_oracle(S, F, with_sdf, fb):
     import sdface_gan_b200 as sg
     from importlib import import_module
