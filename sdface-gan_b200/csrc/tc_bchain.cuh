@@ -15,7 +15,7 @@
 // CG = 2: two CTAs of a cluster run one tcgen05.mma.cta_group::2 (M = 256) per K-step: each stages its own 128 rows of A / G
 // and HALF of every weight chunk, so the L2 -> SM weight stream (the measured bound of the CG = 1 kernel: ~1.3 MB per tile,
 // 6.9 TB/s over the chip) is halved.  The leader CTA's MMA thread issues for the pair; the peer's epilogue warps arrive on
-// the leader's barriers through the cluster (mapa + mbarrier.arrive.release.cluster), commits are multicast to both CTAs.
+// the leader's barriers through the cluster (mapa + mbarrier.arrive.shared::cluster), commits are multicast to both CTAs.
 // Algorithmic HBM traffic per sample and layer: 512 B (A_l) in, 512 B (du) out -- the per-layer kernels moved 2.5 KB.
 #pragma once
 #include "tc_chain.cuh"

@@ -153,3 +153,48 @@ def test_tc_training_step_gradients_close_to_fp32_path(name):
     assert set(g0) == set(g1)
     worst = max((H.rel_err(g1[n], g0[n]), n) for n in g0 if g0[n].abs().max() > 0)
     assert worst[0] < 2e-2, worst
+
+
+_VARIANT_SCRIPT = r"""
+import json, sys, torch
+sys.path.insert(0, %r)
+import sdface_gan_b200 as sg
+torch.manual_seed(0)
+mo, ro = sg.default_options("ngp", renderer_res=16, n_samples=24, perturb=0., return_sdf=True)
+g = sg.Generator(mo, ro, full_pipeline=False).to("cuda")
+g.renderer.network.encoder.embeddings.data.uniform_(-0.5, 0.5)
+g.renderer.network.precision = "tc16"
+cam, focal, near, far, _ = sg.generate_camera_params(16, "cuda", batch=2)
+z = torch.randn(2, 256, device="cuda")
+_, thumb, sdf, eik = g([z], cam, focal, near, far, return_sdf=True, return_eikonal=True)
+loss = (thumb * torch.linspace(-1, 1, thumb.numel(), device="cuda").view_as(thumb)).sum() + sdf.square().mean() * 10
+loss.backward()
+out = {"thumb": thumb.detach().flatten()[::7].tolist(), "eik": eik.flatten()[::997].tolist()}
+for n, p in g.named_parameters():
+    if p.grad is not None:
+        out["g:" + n] = float(p.grad.norm())
+print("RESULT" + json.dumps(out))
+"""
+
+
+def test_tc_kernel_variants_agree():
+    '''The fallback kernels must not rot: fused chains on CTA pairs (default), fused chains on single CTAs (SDFG_TC_CG=1) and the
+    per-layer kernels (SDFG_TC_CHAIN=0) are the same computation in the same number formats -- outputs and gradient norms of a
+    small training step agree to 1e-2 relative (different accumulation orders, atomics).  Env switches are read once per
+    process, hence the subprocesses.'''
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for name, env in (("pairs", {}), ("single", {"SDFG_TC_CG": "1"}), ("per_layer", {"SDFG_TC_CHAIN": "0"})):
+        e = dict(os.environ, **env)
+        r = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT % root], capture_output=True, text=True, env=e, timeout=300)
+        assert r.returncode == 0, (name, r.stderr[-2000:])
+        line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][-1]
+        res[name] = json.loads(line[len("RESULT"):])
+    ref = res["pairs"]
+    for name in ("single", "per_layer"):
+        got = res[name]
+        assert set(got) == set(ref)
+        for k in ref:
+            a, b = np.asarray(ref[k], np.float64), np.asarray(got[k], np.float64)
+            assert np.linalg.norm(a - b) <= 1e-2 * max(np.linalg.norm(a), 1e-12), (name, k, a, b)
