@@ -193,6 +193,14 @@ int sdfg_field_backward(const sdfg_field_params* p, const sdfg_field_grads* g, c
                         uint64_t N, const float* d_sdf, const float* d_rgb, const float* d_feat, const float* out_feat,
                         const void* workspace, void* scratch, float* d_x_in, int precision, void* stream);
 
+/* two-stream variant (tensor-core path): d_x_in is complete on `stream` when the call returns to the host's stream order, while the
+ * parameter gradients (g) are produced on `wgrad_stream`, which the library makes wait for the gradient chain.  The caller may
+ * enqueue work that only needs d_x_in on `stream` (the hash-grid scatter) and must make `stream` wait for `wgrad_stream` before
+ * g, scratch or the upstream gradients are reused.  Falls back to sdfg_field_backward for fp32 or a NULL wgrad_stream. */
+int sdfg_field_backward_2s(const sdfg_field_params* p, const sdfg_field_grads* g, const float* x_in, const float* view_feat,
+                           uint64_t N, const float* d_sdf, const float* d_rgb, const float* d_feat, const float* out_feat,
+                           const void* workspace, void* scratch, float* d_x_in, int precision, void* stream, void* wgrad_stream);
+
 /* probe of the tcgen05 pipeline for the parity tests: out[M,N] (fp32) = bf16(x)[M,K] * bf16(w)[N,K]^T with fp32 accumulation.
  * N multiple of 32 in 32..256, K <= 320. */
 uint64_t sdfg_tc_linear_probe_workspace_bytes(uint32_t M, uint32_t K, uint32_t N);

@@ -227,9 +227,12 @@ def field_forward(spec, x_in, view_feat, gamma, beta, weights, samples_per_image
 
 
 def field_backward(spec, x_in, view_feat, gamma, beta, weights, samples_per_image, samples_per_ray, workspace, out_feat,
-                   d_sdf, d_rgb, d_feat, grads=None, want_dx=False, precision=_lib.PRECISION_FP32):
+                   d_sdf, d_rgb, d_feat, grads=None, want_dx=False, precision=_lib.PRECISION_FP32, wgrad_stream=None):
     """grads: None (no parameter gradients) or dict like `weights` + gamma/beta of pre-zeroed (or live .grad) buffers that are
-    accumulated into.  Returns d_x_in [N,in_dim] or None."""
+    accumulated into.  Returns d_x_in [N,in_dim] or None.
+    wgrad_stream (torch.cuda.Stream): the parameter gradients are produced on that stream (sdfg_field_backward_2s) while d_x_in is
+    ready in the current stream's order; returns (d_x_in, scratch) -- the caller must keep `scratch` alive and make the current
+    stream wait for wgrad_stream before it lets go of scratch / grads / the upstream gradients."""
     lib = _lib.load()
     N = x_in.shape[0]
     dev = x_in.device
@@ -254,6 +257,12 @@ def field_backward(spec, x_in, view_feat, gamma, beta, weights, samples_per_imag
     scratch = torch.empty(max(nbytes, 16) // 4, device=dev, dtype=torch.float32)
     dx = torch.empty(N, spec.in_dim, device=dev) if want_dx else None
     with torch.cuda.device(dev):
+        if wgrad_stream is not None:
+            _lib.check(lib.sdfg_field_backward_2s(ctypes.byref(p), ctypes.byref(g) if g is not None else None, _ptr(x_in), _ptr(view_feat), N,
+                                                  _ptr(_chk(d_sdf, "d_sdf")), _ptr(_chk(d_rgb, "d_rgb")), _ptr(_chk(d_feat, "d_feat")),
+                                                  _ptr(out_feat), _ptr(workspace), _ptr(scratch), _ptr(dx), int(precision), _stream(),
+                                                  ctypes.c_void_p(wgrad_stream.cuda_stream)), "sdfg_field_backward_2s")
+            return dx, scratch
         _lib.check(lib.sdfg_field_backward(ctypes.byref(p), ctypes.byref(g) if g is not None else None, _ptr(x_in), _ptr(view_feat), N,
                                            _ptr(_chk(d_sdf, "d_sdf")), _ptr(_chk(d_rgb, "d_rgb")), _ptr(_chk(d_feat, "d_feat")),
                                            _ptr(out_feat), _ptr(workspace), _ptr(scratch), _ptr(dx), int(precision), _stream()),

@@ -9,6 +9,7 @@ sample), the field as a fused sequence of layer kernels (csrc/field_*.cu) and on
 instead of ~45 + the [N,272]/[N,260] concatenations.  There is no CPU path: tensors must live on a CUDA device.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -74,11 +75,30 @@ class FiLMSiren(nn.Module):
 # --------------------------------------------------------------------------------------------------------------------------
 # the fused field as one autograd node
 
+_SIDE_STREAMS = {}
+# Two-stream backward (weight-gradient contractions on a side stream while the hash-table scatter runs): measured neutral on B200
+# (19.5-20.2 ms per step either way: the contractions already saturate HBM and push the table gradient out of L2), so it is
+# off unless SDFG_OVERLAP=1.
+_OVERLAP = os.environ.get("SDFG_OVERLAP", "0") == "1"
+
+
+def _side_stream(device):
+    """One extra stream per device for the weight-gradient contractions of the field backward (see _field.backward)."""
+    key = torch.device(device).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 class _field(Function):
-    """(x_in [N,in_dim], view_feat [N/S,V], gamma/beta [B,n+1,W], weights...) -> (sdf [N], rgb [N,3], feat [N,W], dsdf_dx [N,in_dim])."""
+    """(x_in [N,in_dim], view_feat [N/S,V], gamma/beta [B,n+1,W], emb, weights...) -> (sdf [N], rgb [N,3], feat [N,W], dsdf_dx [N,in_dim]).
+
+    `emb` is the hash table when the caller computed x_in = grid_encode(meta["grid"]["pts"], emb) itself (without autograd):
+    the node then also owns the table gradient, which lets its backward overlap the L2-atomic-bound scatter (main stream)
+    with the HBM-bound weight-gradient contractions (side stream).  emb = None: x_in is an ordinary differentiable input."""
 
     @staticmethod
-    def forward(ctx, spec, meta, x_in, view_feat, gamma, beta, *wts):
+    def forward(ctx, spec, meta, x_in, view_feat, gamma, beta, emb, *wts):
         ctx.set_materialize_grads(False)
         x_in = x_in.contiguous()
         view_feat = view_feat.contiguous()
@@ -99,7 +119,7 @@ class _field(Function):
             dsdf = ops.field_backward(spec, x_in, view_feat, gamma, beta, weights, meta["spi"], meta["spr"], ws, feat, ones, None, None,
                                       grads=None, want_dx=True, precision=meta["precision"])
         if need_bwd:
-            ctx.save_for_backward(x_in, view_feat, gamma, beta, feat, ws, *wts)
+            ctx.save_for_backward(x_in, view_feat, gamma, beta, feat, ws, emb, *wts)
         ctx.spec, ctx.meta = spec, meta
         empty = x_in.new_empty(0)
         outs = (sdf, rgb if rgb is not None else empty, feat if feat is not None else empty, dsdf if dsdf is not None else empty)
@@ -113,31 +133,45 @@ class _field(Function):
     @staticmethod
     def backward(ctx, d_sdf, d_rgb, d_feat, _d_dsdf):
         spec, meta = ctx.spec, ctx.meta
-        x_in, view_feat, gamma, beta, feat, ws = ctx.saved_tensors[:6]
-        wts = ctx.saved_tensors[6:]
+        x_in, view_feat, gamma, beta, feat, ws, emb = ctx.saved_tensors[:7]
+        wts = ctx.saved_tensors[7:]
         weights = _unpack_weights(spec, wts)
         if d_sdf is None and d_rgb is None and d_feat is None:
-            return (None,) * (6 + len(wts))
+            return (None,) * (7 + len(wts))
         if not meta["want_rgb"]:
             d_rgb = None
         if not meta["want_feat"]:
             d_feat = None
         cont = lambda t: None if t is None else t.contiguous()
-        need_param = any(ctx.needs_input_grad[4:])
+        need_param = any(ctx.needs_input_grad[4:6]) or any(ctx.needs_input_grad[7:])
+        grid = meta.get("grid")
+        need_table = grid is not None and emb is not None and ctx.needs_input_grad[6]
         grads = None
         if need_param:
             gw = tuple(torch.zeros_like(w) for w in wts)
             grads = _unpack_weights(spec, gw)
             grads["gamma"] = torch.zeros_like(gamma)
             grads["beta"] = torch.zeros_like(beta)
-        dx = ops.field_backward(spec, x_in, view_feat, gamma, beta, weights, meta["spi"], meta["spr"], ws,
-                                feat if meta["want_feat"] else None, cont(d_sdf), cont(d_rgb), cont(d_feat), grads=grads,
-                                want_dx=ctx.needs_input_grad[2], precision=meta["precision"])
-        out = [None, None, dx, None]
+        d_sdf, d_rgb, d_feat = cont(d_sdf), cont(d_rgb), cont(d_feat)
+        want_dx = bool(ctx.needs_input_grad[2] or need_table)
+        side = _side_stream(x_in.device) if (need_table and need_param and meta["precision"] == _lib.PRECISION_TC16 and _OVERLAP) else None
+        res = ops.field_backward(spec, x_in, view_feat, gamma, beta, weights, meta["spi"], meta["spr"], ws,
+                                 feat if meta["want_feat"] else None, d_sdf, d_rgb, d_feat, grads=grads,
+                                 want_dx=want_dx, precision=meta["precision"], wgrad_stream=side)
+        dx, scratch = res if side is not None else (res, None)
+        d_emb = None
+        if need_table:
+            d_emb = torch.zeros_like(emb)
+            ops.grid_encode_backward(dx, grid["pts"], emb, grid["offsets"], grid["S"], grid["H"], bound=grid["bound"], grad_embeddings=d_emb,
+                                     gridtype=grid["gridtype"], align_corners=grid["align_corners"], interp=grid["interp"])
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)      # joins before scratch / grads / upstream gradients are let go
+        del scratch
+        out = [None, None, dx if ctx.needs_input_grad[2] else None, None]
         if need_param:
-            out += [grads["gamma"], grads["beta"]] + list(gw)
+            out += [grads["gamma"], grads["beta"], d_emb] + list(gw)
         else:
-            out += [None, None] + [None] * len(wts)
+            out += [None, None, d_emb] + [None] * len(wts)
         return tuple(out)
 
 
@@ -184,13 +218,13 @@ class _FieldNetwork(nn.Module):
         return gamma, beta
 
     def _run_field(self, x_in, view_feat, styles, samples_per_image, samples_per_ray, want_rgb=True, want_feat=True, want_dsdf=False,
-                   feat_f16=False):
+                   feat_f16=False, emb=None, grid=None):
         spec = self._spec
         gamma, beta = self._modulation(styles)
         meta = dict(spi=int(samples_per_image), spr=int(samples_per_ray), want_rgb=bool(want_rgb), want_feat=bool(want_feat),
                     want_dsdf=bool(want_dsdf), precision=self._pick_precision(int(samples_per_image)),
-                    grad=torch.is_grad_enabled(), feat_f16=bool(feat_f16))   # Function.forward itself always runs with grad mode off
-        sdf, rgb, feat, dsdf = _field.apply(spec, meta, x_in, view_feat, gamma, beta, *_pack_weights(spec, self))
+                    grad=torch.is_grad_enabled(), feat_f16=bool(feat_f16), grid=grid)   # Function.forward itself always runs with grad mode off
+        sdf, rgb, feat, dsdf = _field.apply(spec, meta, x_in, view_feat, gamma, beta, emb, *_pack_weights(spec, self))
         return sdf, (rgb if rgb.numel() else None), (feat if feat.numel() else None), (dsdf if dsdf.numel() else None)
 
     def forward(self, x, styles):
@@ -210,8 +244,9 @@ class _FieldNetwork(nn.Module):
         """Renderer entry: npts [B,R,R,S,3], viewdirs [B,R,R,3] (one per ray) -> (sdf [N], rgb [N,3], feat [N,W], dsdf_dnpts [N,3])."""
         B, R1, R2, S, _ = npts.shape
         flat = npts.reshape(-1, 3)
-        x_in, view_feat, grid_ctx = self._encode_rays(flat, viewdirs.reshape(-1, 3), want_dsdf)
-        sdf, rgb, feat, dsdf = self._run_field(x_in, view_feat, styles, R1 * R2 * S, S, want_rgb, want_feat, want_dsdf, feat_f16)
+        x_in, view_feat, grid_ctx, emb, grid = self._encode_rays(flat, viewdirs.reshape(-1, 3), want_dsdf)
+        sdf, rgb, feat, dsdf = self._run_field(x_in, view_feat, styles, R1 * R2 * S, S, want_rgb, want_feat, want_dsdf, feat_f16,
+                                               emb=emb, grid=grid)
         if want_dsdf:
             dsdf = self._dsdf_to_points(dsdf, flat, grid_ctx)
         return sdf, rgb, feat, dsdf
@@ -237,7 +272,7 @@ class SirenGenerator(_FieldNetwork):
         return pts.contiguous(), dirs
 
     def _encode_rays(self, flat_pts, ray_dirs, want_dsdf):
-        return flat_pts.contiguous(), ray_dirs.contiguous(), None
+        return flat_pts.contiguous(), ray_dirs.contiguous(), None, None, None
 
     def _dsdf_to_points(self, dsdf, flat_pts, grid_ctx):
         return dsdf
@@ -281,17 +316,19 @@ class NGPSIRENGenerator(_FieldNetwork):
         return self.encoder(pts, bound=self.bound), self.encoder_dir(dirs)
 
     def _encode_rays(self, flat_pts, ray_dirs, want_dsdf):
+        # The features are computed here WITHOUT an autograd node: the field node (`_field`) receives the table as an extra input and
+        # owns its gradient, so that its backward can run the table scatter and the weight-gradient contractions concurrently.
+        # dy_dx is kept for the eikonal chain rule only.
         enc = self.encoder
-        if want_dsdf:
-            # keep dy_dx for the eikonal chain rule; the table gradient still flows through the autograd node
-            feats, grid_ctx = _grid_encode_keep.apply(flat_pts, enc.embeddings, enc.offsets, enc.per_level_scale, enc.base_resolution,
-                                                      enc.gridtype_id, enc.align_corners, enc.interp_id, float(self.bound))
-        else:
-            feats = enc(flat_pts, bound=self.bound)
-            grid_ctx = None
+        pts = flat_pts.detach().contiguous().float()
+        grid = dict(pts=pts, offsets=enc.offsets, S=ops.log2_scale(enc.per_level_scale), H=enc.base_resolution, bound=float(self.bound),
+                    gridtype=enc.gridtype_id, align_corners=enc.align_corners, interp=enc.interp_id)
         with torch.no_grad():
+            feats, dy_dx = ops.grid_encode_forward(pts, enc.embeddings.detach(), enc.offsets, grid["S"], grid["H"], bound=grid["bound"],
+                                                   calc_dy_dx=bool(want_dsdf), gridtype=grid["gridtype"], align_corners=grid["align_corners"],
+                                                   interp=grid["interp"])
             sh = self.encoder_dir(ray_dirs)
-        return feats, sh, grid_ctx
+        return feats, sh, dy_dx, enc.embeddings, grid
 
     def _dsdf_to_points(self, dsdf, flat_pts, dy_dx):
         enc = self.encoder
