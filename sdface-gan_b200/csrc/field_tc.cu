@@ -21,6 +21,7 @@
 
 #include "field.cuh"
 #include "tc_bchain.cuh"
+#include "tc_bchain2.cuh"
 #include "tc_chain.cuh"
 #include "tc_layer.cuh"
 #include "tc_wgrad.cuh"
@@ -85,6 +86,7 @@ struct TcLayout {
     uint64_t N;
     uint64_t off_w[SDFG_MAX_FILM + 1];           // fp16 weights: [0] = input_linear, [1 + l] = FiLM layer l
     uint64_t off_x0, off_a[SDFG_MAX_FILM + 1], off_hv, total;
+    uint64_t off_c[SDFG_MAX_FILM + 1];           // save: cos(gamma u + c) of FiLM layer l, fp16 [N, W] (written by the forward chain)
     int save;
 };
 
@@ -111,6 +113,7 @@ static TcLayout tc_layout(const sdfg_field_params* p, uint64_t N, int save) {
         L.off_a[l] = take(N * L.W * 2);
     }
     L.off_hv = take(save ? N * L.W * 2 : 0);
+    for (uint32_t l = 0; l < L.n_layers; l++) L.off_c[l] = take(save ? N * L.W * 2 : 0);
     L.total = off;
     return L;
 }
@@ -197,6 +200,7 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
             if (save) if (int e = store_to(nl, A(0), W)) return e;
         } else {
             Y.act = 1; Y.film = 0; Y.bias = p->film_b[0];
+            if (save) Y.out_cos = (h16*)(ws + L.off_c[0]);
             if (int e = trunk_outputs(nl, 0)) return e;
         }
         nl++;
@@ -204,6 +208,7 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
     for (uint32_t l = p->has_input_linear ? 0u : 1u; l < nf; l++) {
         tc::ChainLayer& Y = P.layer[nl];
         Y.has_main = 1; Y.tm = nm; Y.act = 1; Y.film = l; Y.bias = p->film_b[l];
+        if (save) Y.out_cos = (h16*)(ws + L.off_c[l]);
         if (int e = add_main_map(1 + l, W)) return e;
         nm++;
         if (int e = trunk_outputs(nl, l)) return e;
@@ -212,6 +217,7 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
     if (want_views) {
         tc::ChainLayer& Y = P.layer[nl];
         Y.has_main = 1; Y.tm = nm; Y.act = 1; Y.film = nf; Y.bias = p->film_b[nf];
+        if (save) Y.out_cos = (h16*)(ws + L.off_c[nf]);
         Y.small_k0 = P.x_nk; Y.small_nk = P.v_nk;
         if (int e = add_main_map(1 + nf, L.Kp_v)) return e;
         nm++;
@@ -548,6 +554,118 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
     auto layer_K = [&](uint32_t l) { return l == nf ? L.Kp_v : ((l == 0 && !p->has_input_linear) ? L.Kp_in : W); };      // padded
     auto layer_Kx = [&](uint32_t l) { return l == nf ? W + p->view_dim : ((l == 0 && !p->has_input_linear) ? p->in_dim : W); };
 
+    static const bool recompute_env = getenv("SDFG_TC_RECOMPUTE") != nullptr;      // force the recompute chain (tc_bchain.cuh)
+    const bool has_views = d_rgb || d_feat;
+    if (chain_enabled() && bchain_eligible(p, d_x_in) && chain_eligible(p, true) && !recompute_env) {
+        // ---------------------------------------------------------------- backward chain on the saved cos tiles (tc_bchain2.cuh)
+        // (chain_eligible(with views): whatever outputs the forward produced, it was the fused chain -- the one that saves cos(gamma u + c))
+        const bool store = g != nullptr;
+        const bool need_dh0 = p->has_input_linear && (d_x_in || (g && g->input_w));
+        static const int cg_env = []() { const char* e = getenv("SDFG_TC_CG"); return e ? atoi(e) : 2; }();
+        const int cg = (cg_env == 2 && spi % 256 == 0 && (N / tc::CH_TILE_M) % 2 == 0 && (!p->has_input_linear || p->in_dim % 32 == 0)) ? 2 : 1;
+        const uint32_t wrows = 256 / cg;
+        std::unique_ptr<tc::B2ChainMaps> maps(new tc::B2ChainMaps);
+        tc::B2ChainParams P = {};
+        P.M_total = (uint32_t)N; P.rows_per_image = spi; P.gscale = gscale;
+        P.vecs[0] = p->sigma_w;
+        if (p->rgb_w) { P.vecs[1] = p->rgb_w; P.vecs[2] = p->rgb_w + W; P.vecs[3] = p->rgb_w + 2 * W; }
+        uint32_t nl = 0;
+        auto add_layer = [&](uint32_t l) -> int {                      // FiLM layer l (nf = views) becomes chain layer nl
+            tc::B2Layer& Y = P.layer[nl];
+            Y.do_D = l == nf ? 1u : ((l > 0 || need_dh0) ? 1u : 0u);
+            if (int e = make_tensor_map_16(&maps->c[nl], (const h16*)(ws + L.off_c[l]), N, W, W, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
+            if (Y.do_D) {
+                h16* wgt = (h16*)(sc + SC.off_wgt[l]);
+                wgt_kernel<<<dim3(W, B), 256, 0, st>>>(p->film_w[l], layer_Kx(l), p->gamma + (size_t)l * W, gstride, wgt, W, B);
+                if (int e = check_launch("wgt_kernel")) return e;
+                if (int e = make_tensor_map_16(&maps->wgt[nl], wgt, (uint64_t)B * W, W, W, wrows, 64, tc::FMT_F16)) return e;
+            }
+            if (store)
+                if (int e = make_tensor_map_16(&maps->dz[nl], (h16*)(sc + SC.off_dz[l]), N, W, W, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
+            nl++;
+            return SDFG_OK;
+        };
+        if (has_views) {
+            if (int e = add_layer(nf)) return e;
+            P.top_rank = d_rgb ? 3 : 0; P.top_vec0 = 1; P.top_rank_s = d_rgb; P.top_dfeat = d_feat;
+            P.layer[0].d_rank = d_sdf ? 1 : 0; P.layer[0].d_vec0 = 0; P.layer[0].d_rank_s = d_sdf;
+        } else {
+            P.top_rank = 1; P.top_vec0 = 0; P.top_rank_s = d_sdf;
+        }
+        for (int l = (int)nf - 1; l >= 0; l--)
+            if (int e = add_layer((uint32_t)l)) return e;
+        P.n_layers = nl;
+        if (need_dh0) {
+            P.has_in = 1; P.in_dim = p->in_dim; P.d_x_in = d_x_in;
+            h16* wgt_in = (h16*)(sc + SC.off_wgt_in);
+            wgt_kernel<<<dim3(p->in_dim, 1), 256, 0, st>>>(p->input_w, p->in_dim, nullptr, 0, wgt_in, p->in_dim, 1);
+            if (int e = check_launch("wgt_kernel")) return e;
+            if (int e = make_tensor_map_16(&maps->wgt_in, wgt_in, p->in_dim, W, W, p->in_dim / cg, 64, tc::FMT_F16)) return e;
+            if (store)
+                if (int e = make_tensor_map_16(&maps->dh0, DH, N, W, W, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
+        }
+        P.n_units = (uint32_t)(N / (tc::CH_TILE_M * cg));
+        const uint32_t groups = std::min<uint32_t>((uint32_t)sm_count() / cg, P.n_units);
+        P.units_per_cta = ceil_div<uint32_t>(P.n_units, groups);
+        const uint32_t grid = cg * ceil_div<uint32_t>(P.n_units, P.units_per_cta);
+        const uint32_t smem = tc::bchain2_smem_bytes(cg);
+        typedef void (*b2kern_t)(const tc::B2ChainMaps, const tc::B2ChainParams);
+        const b2kern_t kern = cg == 2 ? (store ? (b2kern_t)tc::tc_chain_bwd2_kernel<true, 2> : (b2kern_t)tc::tc_chain_bwd2_kernel<false, 2>)
+                                      : (store ? (b2kern_t)tc::tc_chain_bwd2_kernel<true, 1> : (b2kern_t)tc::tc_chain_bwd2_kernel<false, 1>);
+        static thread_local bool configured[4] = {false, false, false, false};
+        const int ki = (cg == 2 ? 2 : 0) + (store ? 1 : 0);
+        if (!configured[ki]) {
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return set_error(SDFG_ERR_CUDA, "tc_chain_bwd2_kernel: cannot opt in to %u bytes of shared memory", smem);
+            configured[ki] = true;
+        }
+        {
+            ProfScope prof("tc_chain_bwd2_kernel<gemm>", st);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            if (cudaLaunchKernelEx(&cfg, kern, *maps, P) != cudaSuccess) { (void)check_launch("tc_chain_bwd2_kernel<gemm>"); return SDFG_ERR_CUDA; }
+            if (int e = check_launch("tc_chain_bwd2_kernel<gemm>")) return e;
+        }
+        if (!g) return SDFG_OK;
+        if (st_w != st) {                                               // see the note in the recompute chain below
+            cudaEvent_t ev;
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: event");
+            cudaEventRecord(ev, st);
+            cudaStreamWaitEvent(st_w, ev, 0);
+            cudaEventDestroy(ev);
+            st = st_w;
+        }
+        if (has_views && g->rgb_w && d_rgb) {
+            head_wgrad16_kernel<3><<<(unsigned)ceil_div<uint64_t>(N, 512), 256, 0, st>>>(d_rgb, (const h16*)(ws + L.off_hv), W, g->rgb_w, g->rgb_b, N, 512);
+            if (int e = check_launch("head_wgrad16_kernel<3>")) return e;
+        }
+        if (g->sigma_w && d_sdf) {
+            head_wgrad16_kernel<1><<<(unsigned)ceil_div<uint64_t>(N, 512), 256, 0, st>>>(d_sdf, A(nf), L.Kp_v, g->sigma_w, g->sigma_b, N, 512);
+            if (int e = check_launch("head_wgrad16_kernel<1>")) return e;
+        }
+        for (int l = has_views ? (int)nf : (int)nf - 1; l >= 0; l--) {
+            if (!g->film_w[l]) continue;
+            if (cudaMemsetAsync(G, 0, (size_t)B * 256 * 336 * 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");
+            uint32_t ldg, ones;
+            if (int e = launch_wgrad((const h16*)(sc + SC.off_dz[l]), A(l), layer_Kx(l), layer_K(l), N, spi, G, &ldg, &ones, st, tc::FMT_F16)) return e;
+            wgrad_finish_kernel<<<256, 128, 0, st>>>(G, ldg, ones, B, p->film_w[l], layer_Kx(l), layer_Kx(l), p->film_b[l], p->gamma + (size_t)l * W,
+                                                     gstride, 1, g->film_w[l], g->film_b[l], g->gamma + (size_t)l * W, g->beta + (size_t)l * W, gscale);
+            if (int e = check_launch("wgrad_finish_kernel")) return e;
+        }
+        if (p->has_input_linear && g->input_w) {
+            if (cudaMemsetAsync(G, 0, (size_t)B * 256 * 336 * 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");
+            uint32_t ldg, ones;
+            if (int e = launch_wgrad(DH, (const h16*)(ws + L.off_x0), p->in_dim, L.Kp_in, N, spi, G, &ldg, &ones, st, tc::FMT_F16)) return e;
+            wgrad_finish_kernel<<<256, 128, 0, st>>>(G, ldg, ones, B, p->input_w, p->in_dim, p->in_dim, p->input_b, nullptr, 0, 0, g->input_w,
+                                                     g->input_b, nullptr, nullptr, gscale);
+            if (int e = check_launch("wgrad_finish_kernel")) return e;
+        }
+        return SDFG_OK;
+    }
     if (chain_enabled() && bchain_eligible(p, d_x_in)) {
         // ---------------------------------------------------------------- fused backward chain (tc_bchain.cuh)
         const bool views = d_rgb || d_feat;

@@ -1,0 +1,356 @@
+// Backward chain WITHOUT recompute: the forward chain saved c_l = cos(gamma u_l + c) per FiLM layer (fp16, tc_chain.cuh), so the
+// gradient of a 128-sample tile flows through the layers with ONE GEMM per layer and a light epilogue:
+//
+//   du_top = (head rank terms + d_feat) * c_top                                   (first epilogue, no GEMM)
+//   for l = top .. bottom:   D_l: dh = du_l (gamma o W_l)   ->   epilogue: du_{l-1} = (dh [+ d_sdf w_sigma]) * c_{l-1}  -> G (fp16)
+//   input stage:             d x_in = dh_0 W_in  (fp32 out)
+//
+// (ref: autograd of FiLMSiren.forward sdf_model.py:61-69 through NGPSIRENGenerator.forward :1566-1592; without stores and
+// started from d_sdf = 1 this is the eikonal chain of get_eikonal_term :224-229).  dh never leaves TMEM in fp16: the epilogue
+// reads the fp32 accumulator, multiplies by the cos tile (64 KB shared-memory buffer, TMA-prefetched chunk by chunk as the
+// previous layer's epilogue releases it) and writes the next GEMM's A operand in place into G; D_{l-1}'s MMAs trail the
+// epilogue at 64-column chunk granularity into the other accumulator.  Compared with tc_bchain.cuh (recompute): no R GEMM,
+// no W_l stream, no MUFU, no FiLM constant tables.
+// CG = 2: CTA pairs with tcgen05.mma.cta_group::2, exactly as in tc_bchain.cuh (leader-issued MMAs, multicast commits, the
+// peer's epilogue arrives on the leader's barriers); cos tiles are per-CTA data and complete on local barriers.
+// With STORE the du tiles (and dh_0) are TMA-stored for the weight-gradient kernels (tc_wgrad.cuh).
+// Algorithmic HBM traffic per sample and layer: 512 B (c_l) in, 512 B (du_l) out.
+#pragma once
+#include "tc_bchain.cuh"
+
+namespace sdfg {
+namespace tc {
+
+struct B2Layer {
+    uint32_t do_D;              // run D (the layer below, or the input stage, needs the gradient)
+    uint32_t d_rank, d_vec0;    // epilogue of D_l: + gs * d_rank_s[row] * vecs[d_vec0][col]   (d_sdf w_sigma behind the view layer)
+    uint32_t pad;
+    const float* d_rank_s;
+};
+
+struct B2ChainParams {
+    uint32_t M_total, rows_per_image, n_units, units_per_cta, n_layers;
+    uint32_t has_in, in_dim;
+    uint32_t top_rank, top_vec0;        // first epilogue: dh_top = sum_r gs * top_rank_s[row*top_rank + r] * vecs[top_vec0 + r] + gs * top_dfeat
+    uint32_t pad;
+    const float* top_rank_s;
+    const float* top_dfeat;             // fp32 [M, 256] or NULL
+    float* d_x_in;
+    const float* gscale;                // {s, 1/s}
+    const float* vecs[4];               // 0 = w_sigma, 1..3 = w_rgb rows
+    unsigned long long* dbg;
+    B2Layer layer[BC_MAX_LAYERS];       // index 0 = TOP layer
+};
+
+struct alignas(64) B2ChainMaps {
+    CUtensorMap c[BC_MAX_LAYERS];       // cos tile of layer l          [M, 256]      box 128 x 64
+    CUtensorMap wgt[BC_MAX_LAYERS];     // (gamma o W_l)^T per image    [B*256, 256]  box (256/CG) x 64
+    CUtensorMap dz[BC_MAX_LAYERS];      // du store                     [M, 256]      box 128 x 64
+    CUtensorMap wgt_in;                 // W_in^T                       [in_dim, 256] box (in_dim/CG) x 64
+    CUtensorMap dh0;                    // dh_0 store                   [M, 256]      box 128 x 64
+};
+
+struct B2ChainSmem {
+    uint64_t c_full[4], c_empty[4];
+    uint64_t w_full[BC_MAX_W_STAGES], w_empty[BC_MAX_W_STAGES];
+    uint64_t g_ready[4], g_ready_st[4], st_done[4];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad[3];
+    alignas(16) float vecs[4][256];
+};
+
+__host__ __device__ inline uint32_t bchain2_smem_bytes(int cg) {
+    return 1024 + 2 * BC_G_BYTES + bc_w_stages(cg) * bc_w_bytes(cg) + (uint32_t)sizeof(B2ChainSmem);
+}
+
+template <bool STORE, int CG>
+__global__ void __launch_bounds__(CH_THREADS, 1)
+tc_chain_bwd2_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_constant__ B2ChainParams P) {
+    constexpr bool PAIR = CG == 2;
+    constexpr uint32_t W_BYTES = bc_w_bytes(CG), NW = bc_w_stages(CG);
+    constexpr uint32_t W_ROWS = 256 / CG;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smG = smem;                                               // gradient tile = A operand of the D GEMMs
+    uint8_t* smC = smG + BC_G_BYTES;                                   // cos tile of the layer being entered
+    uint8_t* smW = smC + BC_G_BYTES;
+    B2ChainSmem& S = *reinterpret_cast<B2ChainSmem*>(smW + NW * W_BYTES);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const uint32_t u_begin = (blockIdx.x / CG) * P.units_per_cta;
+    const uint32_t u_end = min(P.n_units, u_begin + P.units_per_cta);
+    const uint32_t nL = P.n_layers;
+    uint32_t nD = 0;                                                   // D GEMMs per unit (layers with do_D)
+    for (uint32_t i = 0; i < nL; i++) nD += P.layer[i].do_D ? 1u : 0u;
+    uint32_t dbg_n = 0;
+    (void)dbg_n;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < 4; i++) {
+            mbar_init(&S.c_full[i], 1); mbar_init(&S.c_empty[i], CH_EPI_WARPS);
+            mbar_init(&S.g_ready[i], CH_EPI_WARPS * CG); mbar_init(&S.g_ready_st[i], CH_EPI_WARPS); mbar_init(&S.st_done[i], 1);
+        }
+        for (uint32_t i = 0; i < NW; i++) { mbar_init(&S.w_full[i], 1); mbar_init(&S.w_empty[i], 1); }
+        for (uint32_t i = 0; i < 2; i++) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], CH_EPI_WARPS * CG); }
+        fence_barrier_init();
+    }
+    if (warp == CH_WARP_TMA && lane == 0) {
+        for (uint32_t i = 0; i < nL; i++) {
+            tma_prefetch_desc(&maps.c[i]);
+            if (P.layer[i].do_D) tma_prefetch_desc(&maps.wgt[i]);
+            if (STORE) tma_prefetch_desc(&maps.dz[i]);
+        }
+        if (P.has_in) tma_prefetch_desc(&maps.wgt_in);
+    }
+    if (warp == CH_WARP_MMA) { if (PAIR) tmem_alloc_2cta(&S.tmem_base, 512); else tmem_alloc(&S.tmem_base, 512); }
+    for (uint32_t i = threadIdx.x; i < 4 * 256; i += blockDim.x) S.vecs[i >> 8][i & 255] = P.vecs[i >> 8] ? __ldg(P.vecs[i >> 8] + (i & 255)) : 0.f;
+    tc_fence_before();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = S.tmem_base;
+    const uint32_t in_rows = P.in_dim / CG, in_box_bytes = in_rows * 128;
+
+    if (warp == CH_WARP_TMA) {
+        // ===================================================== weight producer (both CTAs): own half of every chunk, in MMA issue order
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            auto put = [&](const CUtensorMap* m, uint32_t bytes, int32_t c0, int32_t c1) {
+                mbar_wait(&S.w_empty[stage], phase ^ 1);
+                if (leader) mbar_arrive_expect_tx(&S.w_full[stage], CG * bytes);
+                if (PAIR) tma_load_2d_2cta(smW + stage * W_BYTES, m, &S.w_full[stage], c0, c1);
+                else tma_load_2d(smW + stage * W_BYTES, m, &S.w_full[stage], c0, c1);
+                if (++stage == NW) { stage = 0; phase ^= 1; }
+            };
+            for (uint32_t u = u_begin; u < u_end; u++) {
+                const uint32_t t = u * CG + rank;
+                const int32_t img = (int32_t)((t * CH_TILE_M) / P.rows_per_image);
+                for (uint32_t i = 0; i < nL; i++)
+                    if (P.layer[i].do_D)
+                        for (uint32_t kc = 0; kc < 4; kc++) put(&maps.wgt[i], W_BYTES, (int32_t)(kc * 64), img * 256 + (int32_t)(rank * W_ROWS));
+                if (P.has_in)
+                    for (uint32_t kc = 0; kc < 4; kc++) put(&maps.wgt_in, in_box_bytes, (int32_t)(kc * 64), (int32_t)(rank * in_rows));
+            }
+        }
+    } else if (warp == CH_WARP_LOAD) {
+        // ===================================================== cos-tile producer (per CTA, local barriers): layer after layer, chunk by chunk
+        if (lane == 0) {
+            uint32_t cgen = 0;
+            for (uint32_t u = u_begin; u < u_end; u++) {
+                const int32_t row0 = (int32_t)((u * CG + rank) * CH_TILE_M);
+                for (uint32_t i = 0; i < nL; i++, cgen++)
+                    for (uint32_t kc = 0; kc < 4; kc++) {
+                        mbar_wait(&S.c_empty[kc], (cgen & 1) ^ 1);
+                        mbar_arrive_expect_tx(&S.c_full[kc], CH_CHUNK_BYTES);
+                        tma_load_2d(smC + kc * CH_CHUNK_BYTES, &maps.c[i], &S.c_full[kc], (int32_t)(kc * 64), row0);
+                    }
+            }
+        }
+    } else if (warp == CH_WARP_MMA) {
+        // ===================================================== MMA issuer (leader CTA only)
+        if (lane == 0 && leader) {
+            const uint32_t idesc = idesc_f16(CH_TILE_M * CG, 256, FMT_F16, FMT_F16, 0, 0);
+            const uint32_t idesc_in = idesc_f16(CH_TILE_M * CG, P.in_dim, FMT_F16, FMT_F16, 0, 0);
+            const uint32_t g_addr = smem_u32(smG);
+            uint32_t stage = 0, phase = 0, gev = 0, ng = 0;             // gev: G-write events seen, ng: GEMMs issued
+            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t accum) {
+                if (PAIR) umma_f16_2cta(d, da, db, id, accum); else umma_bf16(d, da, db, id, accum);
+            };
+            auto commit = [&](uint64_t* bar) { if (PAIR) umma_commit_2cta(bar, 3); else umma_commit(bar); };
+            auto gemm = [&](uint32_t id) {                              // one GEMM over the 4 chunks of the current G event
+                const uint32_t acc = ng & 1;
+                mbar_wait(&S.acc_empty[acc], ((ng >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (uint32_t kc = 0; kc < 4; kc++) {
+                    mbar_wait(&S.g_ready[kc], gev & 1);
+                    mbar_wait(&S.w_full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(smW + stage * W_BYTES), a_addr = g_addr + kc * CH_CHUNK_BYTES;
+                    for (uint32_t s = 0; s < 4; s++)
+                        mma(tmem_base + acc * 256, smem_desc_sw128(a_addr + s * 32, 16, 1024), smem_desc_sw128(b_addr + s * 32, 16, 1024), id, (kc | s) != 0);
+                    commit(&S.w_empty[stage]);
+                    if (++stage == NW) { stage = 0; phase ^= 1; }
+                }
+                commit(&S.acc_full[acc]);
+                ng++;
+                gev++;
+            };
+            for (uint32_t u = u_begin; u < u_end; u++) {
+                for (uint32_t i = 0; i < nL; i++) {
+                    if (P.layer[i].do_D) gemm(idesc);
+                    else {                                              // du of the bottom layer: written for the storer only
+                        for (uint32_t kc = 0; kc < 4; kc++) mbar_wait(&S.g_ready[kc], gev & 1);
+                        gev++;
+                    }
+                }
+                if (P.has_in) gemm(idesc_in);
+            }
+        }
+    } else if (warp == CH_WARP_STORE) {
+        // ===================================================== storer (STORE): every G event -> HBM (du_l for the weight gradients, dh_0)
+        if (STORE && lane == 0) {
+            uint32_t gev = 0;
+            for (uint32_t u = u_begin; u < u_end; u++) {
+                const int32_t row0 = (int32_t)((u * CG + rank) * CH_TILE_M);
+                const uint32_t n_ev = nL + (P.has_in ? 1u : 0u);
+                for (uint32_t e = 0; e < n_ev; e++, gev++) {
+                    const CUtensorMap* m = e < nL ? &maps.dz[e] : &maps.dh0;
+                    for (uint32_t c = 0; c < 4; c++) {
+                        mbar_wait(&S.g_ready_st[c], gev & 1);
+                        tma_store_2d(m, smG + c * CH_CHUNK_BYTES, (int32_t)(c * 64), row0);
+                        tma_store_commit();
+                        tma_store_wait_read();
+                        mbar_arrive(&S.st_done[c]);
+                    }
+                }
+            }
+            tma_store_wait_all();
+        }
+    } else if (warp < CH_EPI_WARPS) {
+        // ===================================================== epilogue: 16 warps, 4 per TMEM lane quarter, 16 columns of every chunk each
+        const uint32_t q = warp & 3, sb = warp >> 2;
+        const uint32_t r = q * 32 + lane;
+        const uint32_t g_row = smem_u32(smG) + r * 128, c_row = smem_u32(smC) + r * 128;
+        const uint32_t u0 = ((2 * sb) ^ (r & 7)) << 4, u1 = ((2 * sb + 1) ^ (r & 7)) << 4;
+        const float gs = __ldg(P.gscale), gs_inv = __ldg(P.gscale + 1);
+        const uint32_t lane_base = (q * 32) << 16;
+        auto arrive_mma = [&](uint64_t* bar) { if (PAIR && !leader) mbar_arrive_remote(bar, 0); else mbar_arrive(bar); };
+        uint32_t gev = 0, cgen = 0, ng = 0;
+        // write one 16-column piece of a G event: v (fp32) [* cos tile chunk] -> fp16 (saturating) -> G, publish
+        auto emit = [&](const float (&v)[16], uint32_t c, bool mul_cos) {
+            const uint32_t chunk = g_row + c * CH_CHUNK_BYTES;
+            float w[16];
+            if (mul_cos) {
+                mbar_wait(&S.c_full[c], cgen & 1);
+                const uint4 a = lds128u(c_row + c * CH_CHUNK_BYTES + u0), b = lds128u(c_row + c * CH_CHUNK_BYTES + u1);
+                const uint32_t cw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int k = 0; k < 8; k++) { const float2 f = unpack_f16(cw[k]); w[2 * k] = v[2 * k] * f.x; w[2 * k + 1] = v[2 * k + 1] * f.y; }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.c_empty[c]);              // this warp is done with the cos chunk
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; k++) w[k] = v[k];
+            }
+            const uint4 h0 = make_uint4(pack_f16_sat(w[0], w[1]), pack_f16_sat(w[2], w[3]), pack_f16_sat(w[4], w[5]), pack_f16_sat(w[6], w[7]));
+            const uint4 h1 = make_uint4(pack_f16_sat(w[8], w[9]), pack_f16_sat(w[10], w[11]), pack_f16_sat(w[12], w[13]), pack_f16_sat(w[14], w[15]));
+            if (STORE && gev > 0) mbar_wait(&S.st_done[c], (gev - 1) & 1);   // the store of the previous event has read the chunk
+            sts128(chunk + u0, h0);
+            sts128(chunk + u1, h1);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                arrive_mma(&S.g_ready[c]);
+                if (STORE) mbar_arrive(&S.g_ready_st[c]);
+            }
+        };
+        for (uint32_t u = u_begin; u < u_end; u++) {
+            const uint32_t t = u * CG + rank;
+            const uint64_t row = (uint64_t)t * CH_TILE_M + r;
+            // ---------------- top: du_top = (rank terms + d_feat) * c_top
+            {
+                float rs[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    if ((uint32_t)k < P.top_rank) rs[k] = gs * __ldg(P.top_rank_s + row * P.top_rank + k);
+                const uint32_t rvec_s = smem_u32(&S.vecs[P.top_vec0][0]);
+#pragma unroll 1
+                for (uint32_t c = 0; c < 4; c++) {
+                    const uint32_t col = c * 64 + sb * 16;
+                    float dh[16];
+#pragma unroll
+                    for (int k = 0; k < 16; k++) dh[k] = 0.f;
+                    if (P.top_dfeat) {
+                        const float4* src = reinterpret_cast<const float4*>(P.top_dfeat + row * 256 + col);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float4 f = ldg_stream4(src + j);
+                            dh[4 * j] = gs * f.x; dh[4 * j + 1] = gs * f.y; dh[4 * j + 2] = gs * f.z; dh[4 * j + 3] = gs * f.w;
+                        }
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 3; rr++) {
+                        if ((uint32_t)rr < P.top_rank) {
+#pragma unroll
+                            for (int k = 0; k < 16; k += 4) {
+                                const float4 w4 = lds128(rvec_s + (rr * 256 + col + k) * 4);
+                                dh[k] = fmaf(rs[rr], w4.x, dh[k]); dh[k + 1] = fmaf(rs[rr], w4.y, dh[k + 1]);
+                                dh[k + 2] = fmaf(rs[rr], w4.z, dh[k + 2]); dh[k + 3] = fmaf(rs[rr], w4.w, dh[k + 3]);
+                            }
+                        }
+                    }
+                    emit(dh, c, true);
+                }
+                gev++; cgen++;
+            }
+            // ---------------- per D GEMM: dh (fp32, TMEM) [+ rank-1] [* cos of the layer below] -> next G event
+            for (uint32_t i = 0; i < nL; i++) {
+                if (!P.layer[i].do_D) continue;
+                const bool last = i + 1 == nL;                          // dh_0: no layer below inside the chain
+                const uint32_t d_rank = P.layer[i].d_rank;
+                const float ds = d_rank ? gs * __ldg(P.layer[i].d_rank_s + row) : 0.f;
+                const uint32_t dvec_s = smem_u32(&S.vecs[P.layer[i].d_vec0][0]);
+                const uint32_t acc = ng & 1;
+                mbar_wait(&S.acc_full[acc], (ng >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + lane_base + acc * 256 + sb * 16;
+                uint32_t raw[2][16];
+                tmem_ld16_issue(taddr, raw[0]);
+#pragma unroll
+                for (uint32_t c = 0; c < 4; c++) {
+                    const uint32_t col = c * 64 + sb * 16;
+                    tmem_ld_wait16(raw[c & 1]);
+                    if (c < 3) tmem_ld16_issue(taddr + (c + 1) * 64, raw[(c + 1) & 1]);
+                    float v[16];
+#pragma unroll
+                    for (int k = 0; k < 16; k++) v[k] = __uint_as_float(raw[c & 1][k]);
+                    if (d_rank) {
+#pragma unroll
+                        for (int k = 0; k < 16; k += 4) {
+                            const float4 w4 = lds128(dvec_s + (col + k) * 4);
+                            v[k] = fmaf(ds, w4.x, v[k]); v[k + 1] = fmaf(ds, w4.y, v[k + 1]);
+                            v[k + 2] = fmaf(ds, w4.z, v[k + 2]); v[k + 3] = fmaf(ds, w4.w, v[k + 3]);
+                        }
+                    }
+                    emit(v, c, !last);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) arrive_mma(&S.acc_empty[acc]);
+                ng++;
+                gev++;
+                if (!last) cgen++;
+            }
+            // ---------------- input stage: d_x_in = gs_inv * acc
+            if (P.has_in) {
+                const uint32_t acc = ng & 1;
+                mbar_wait(&S.acc_full[acc], (ng >> 1) & 1);
+                tc_fence_after();
+                if (sb * 16 < P.in_dim && P.d_x_in) {                   // warp-uniform: tcgen05.ld is a whole-warp instruction
+                    uint32_t raw[16];
+                    tmem_ld16(tmem_base + lane_base + acc * 256 + sb * 16, raw);
+                    tmem_ld_wait();
+                    if (row < P.M_total) {
+                        float4* dst = reinterpret_cast<float4*>(P.d_x_in + row * P.in_dim + sb * 16);
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            dst[j] = make_float4(gs_inv * __uint_as_float(raw[4 * j]), gs_inv * __uint_as_float(raw[4 * j + 1]),
+                                                 gs_inv * __uint_as_float(raw[4 * j + 2]), gs_inv * __uint_as_float(raw[4 * j + 3]));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) arrive_mma(&S.acc_empty[acc]);
+                ng++;
+            }
+        }
+    }
+    tc_fence_before();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
+    if (warp == CH_WARP_MMA) { if (PAIR) tmem_dealloc_2cta(tmem_base, 512); else tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace tc
+}  // namespace sdfg

@@ -57,6 +57,7 @@ struct ChainLayer {
     float* out_head;
     float* out_f32;             // optional fp32 copy of the output in HBM
     int64_t ld_out_f32;
+    uint16_t* out_cos;          // SAVE: cos(gamma u + c) as fp16 [M, 256] -- the activation derivative the backward chain multiplies with
 };
 
 struct ChainParams {
@@ -349,6 +350,7 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                 // layer description -> registers (constant-bank reads with a dynamic index are slow inside the chunk loop)
                 const uint32_t L_act = P.layer[i].act, L_nh = P.layer[i].nh, L_to_act = P.layer[i].to_act, L_film = P.layer[i].film;
                 float* const o32 = P.layer[i].out_f32;
+                uint16_t* const ocos = SAVE ? P.layer[i].out_cos : nullptr;
                 const int64_t ld32 = P.layer[i].ld_out_f32;
                 const uint32_t acc = n & 1, use = n >> 1, tb = n & 1;
                 const uint32_t gam_s = smem_u32(&S.gam[tb][0]), cst_s = smem_u32(&S.cst[tb][0]);
@@ -388,6 +390,16 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                         v[k + 3] = fmaf(__uint_as_float(raw[c & 1][k + 3]), g4.w, c4.w);
                     }
                     if (L_act) {
+                        if (SAVE && ocos) {                              // derivative for the backward chain (no recompute there)
+                            float cs[16];
+#pragma unroll
+                            for (int k = 0; k < 16; k++) cs[k] = __cosf(v[k]);
+                            if (valid) {
+                                uint4* dst = reinterpret_cast<uint4*>(ocos + row * 256 + col);
+                                dst[0] = make_uint4(pack_f16(cs[0], cs[1]), pack_f16(cs[2], cs[3]), pack_f16(cs[4], cs[5]), pack_f16(cs[6], cs[7]));
+                                dst[1] = make_uint4(pack_f16(cs[8], cs[9]), pack_f16(cs[10], cs[11]), pack_f16(cs[12], cs[13]), pack_f16(cs[14], cs[15]));
+                            }
+                        }
 #pragma unroll
                         for (int k = 0; k < 16; k++) v[k] = __sinf(v[k]);
                     }
