@@ -169,8 +169,6 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
     P.x_nk = ceil_div<uint32_t>(p->in_dim, 16);
     P.v_nk = want_views ? ceil_div<uint32_t>(p->view_dim, 16) : 0;   // the view part is loaded only when a layer consumes it
     P.x_in = x_in; P.view_feat = view_feat;
-    P.w_x = p->has_input_linear ? p->input_w : p->film_w[0]; P.ld_wx = p->in_dim;
-    P.w_v = p->film_w[nf] ? p->film_w[nf] + W : nullptr; P.ld_wv = W + p->view_dim;
     P.gamma = p->gamma; P.beta = p->beta; P.gstride = (int64_t)(nf + 1) * W;
     P.kp_x = L.Kp_in; P.kp_v = L.Kp_v - W;
     if (save) {
@@ -178,8 +176,13 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
         if (P.v_nk) { P.v16 = A(nf) + W; P.ld_v16 = L.Kp_v; }
     }
     uint32_t nl = 0, nm = 0;
-    auto add_main_map = [&](uint32_t wi, uint32_t ldw) -> int {
-        return make_tensor_map_16(&maps.m[nm], Wb(wi), W, W, ldw, 256, 64, tc::FMT_F16);
+    auto add_main_map = [&](uint32_t wi, uint32_t ldw) -> int {          // fp16 weights [W, ldw]: every 64-column chunk incl. a partial tail (OOB = 0)
+        return make_tensor_map_16(&maps.m[nm], Wb(wi), W, ldw, ldw, 256, 64, tc::FMT_F16);
+    };
+    // SAVE: cos(gamma u + c) of FiLM layer l, TMA-stored chunk by chunk for the backward chain
+    auto cos_to = [&](uint32_t layer, uint32_t l) -> int {
+        P.layer[layer].store_cos = 1;
+        return make_tensor_map_16(&stores.c[layer], (h16*)(ws + L.off_c[l]), N, W, W, tc::CH_TILE_M, 64, tc::FMT_F16);
     };
     // SAVE: the layer's output tile is TMA-stored chunk by chunk to dst [N, 256] (pitch ld)
     auto store_to = [&](uint32_t layer, h16* dst, uint64_t ld) -> int {
@@ -195,12 +198,14 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
     {
         tc::ChainLayer& Y = P.layer[nl];
         Y.small_k0 = 0; Y.small_nk = P.x_nk;
+        Y.tm_small = tc::CH_MAX_MAPS; Y.c0_small = 0;                   // layer 0's weights: one chunk of the last map slot
+        if (int e = make_tensor_map_16(&maps.m[tc::CH_MAX_MAPS], Wb(p->has_input_linear ? 0 : 1), W, L.Kp_in, L.Kp_in, 256, 64, tc::FMT_F16)) return e;
         if (p->has_input_linear) {
             Y.act = 0; Y.bias = p->input_b;
             if (save) if (int e = store_to(nl, A(0), W)) return e;
         } else {
             Y.act = 1; Y.film = 0; Y.bias = p->film_b[0];
-            if (save) Y.out_cos = (h16*)(ws + L.off_c[0]);
+            if (save) if (int e = cos_to(nl, 0)) return e;
             if (int e = trunk_outputs(nl, 0)) return e;
         }
         nl++;
@@ -208,7 +213,7 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
     for (uint32_t l = p->has_input_linear ? 0u : 1u; l < nf; l++) {
         tc::ChainLayer& Y = P.layer[nl];
         Y.has_main = 1; Y.tm = nm; Y.act = 1; Y.film = l; Y.bias = p->film_b[l];
-        if (save) Y.out_cos = (h16*)(ws + L.off_c[l]);
+        if (save) if (int e = cos_to(nl, l)) return e;
         if (int e = add_main_map(1 + l, W)) return e;
         nm++;
         if (int e = trunk_outputs(nl, l)) return e;
@@ -217,8 +222,9 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
     if (want_views) {
         tc::ChainLayer& Y = P.layer[nl];
         Y.has_main = 1; Y.tm = nm; Y.act = 1; Y.film = nf; Y.bias = p->film_b[nf];
-        if (save) Y.out_cos = (h16*)(ws + L.off_c[nf]);
+        if (save) if (int e = cos_to(nl, nf)) return e;
         Y.small_k0 = P.x_nk; Y.small_nk = P.v_nk;
+        Y.tm_small = nm; Y.c0_small = W;                                // the view columns: the 5th chunk of the same matrix
         if (int e = add_main_map(1 + nf, L.Kp_v)) return e;
         nm++;
         if (save) if (int e = store_to(nl, (h16*)(ws + L.off_hv), W)) return e;

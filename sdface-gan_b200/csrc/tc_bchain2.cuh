@@ -192,6 +192,7 @@ tc_chain_bwd2_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
         // ===================================================== storer (STORE): every G event -> HBM (du_l for the weight gradients, dh_0)
         if (STORE && lane == 0) {
             uint32_t gev = 0;
+            uint64_t* pend = nullptr;                                   // one store group may still be reading G while the next is issued
             for (uint32_t u = u_begin; u < u_end; u++) {
                 const int32_t row0 = (int32_t)((u * CG + rank) * CH_TILE_M);
                 const uint32_t n_ev = nL + (P.has_in ? 1u : 0u);
@@ -201,11 +202,13 @@ tc_chain_bwd2_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
                         mbar_wait(&S.g_ready_st[c], gev & 1);
                         tma_store_2d(m, smG + c * CH_CHUNK_BYTES, (int32_t)(c * 64), row0);
                         tma_store_commit();
-                        tma_store_wait_read();
-                        mbar_arrive(&S.st_done[c]);
+                        if (pend) { tma_store_wait_read_pending<1>(); mbar_arrive(pend); }
+                        pend = &S.st_done[c];
                     }
                 }
             }
+            tma_store_wait_read();
+            if (pend) mbar_arrive(pend);
             tma_store_wait_all();
         }
     } else if (warp < CH_EPI_WARPS) {

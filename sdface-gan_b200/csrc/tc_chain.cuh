@@ -1,9 +1,9 @@
 // The whole field forward as ONE persistent tcgen05 kernel: every layer of a 128-sample tile runs back to back on the SM that
 // owns the tile, activations never leave the chip.
 //
-//   layer 0         K <= 32 "x part" (hash features / raw points)            A = SMALL tile,  B = WSMALL (resident)
+//   layer 0         K <= 32 "x part" (hash features / raw points)            A = SMALL tile,  B = one streamed chunk
 //   layers 1..n-1   K = 256 hidden activations                               A = ACT tile,    B = weight chunks streamed from L2
-//   last layer      K = 256 + "view part" (SH of the view direction, <= 16)  A = ACT + SMALL, B = streamed + WSMALL
+//   last layer      K = 256 + "view part" (SH of the view direction, <= 16)  A = ACT + SMALL, B = 4 + 1 streamed chunks
 //
 // Data flow per tile (ref NGPSIRENGenerator.forward sdf_model.py:1566-1592, SirenGenerator.forward :121-139):
 //   loader warp   x_in / view_feat (fp32, HBM) -> fp16 -> SMALL (128B-swizzled K-major operand tile, written by hand)
@@ -31,7 +31,7 @@ namespace tc {
 constexpr uint32_t CH_TILE_M = 128;
 constexpr uint32_t CH_CHUNK_BYTES = CH_TILE_M * 128;        // [128 samples x 64 fp16] = 16 KB
 constexpr uint32_t CH_ACT_BYTES = 4 * CH_CHUNK_BYTES;       // K = 256
-constexpr uint32_t CH_WSMALL_BYTES = 256 * 128;             // [256 neurons x 64 fp16] = 32 KB (4 K-steps of 16)
+constexpr uint32_t CH_COS_SLOTS = 2;                        // SAVE: staging chunks of the cos tile (TMA-stored for the backward chain)
 constexpr uint32_t CH_W_STAGE_BYTES = 256 * 128;            // one streamed weight chunk
 constexpr uint32_t CH_W_STAGES = 3;
 constexpr uint32_t CH_MAX_LAYERS = SDFG_MAX_FILM + 1;
@@ -44,7 +44,8 @@ constexpr uint32_t CH_THREADS = 640;
 struct ChainLayer {
     uint32_t has_main;          // K = 256 part: A = ACT, B streamed through the ring with tensor map `tm`
     uint32_t tm;
-    uint32_t small_k0, small_nk;   // K-steps [small_k0, small_k0 + small_nk) of SMALL / WSMALL (0 = none)
+    uint32_t small_k0, small_nk;   // K-steps [small_k0, small_k0 + small_nk) of SMALL; its weights are one extra streamed chunk (tensor map `tm_small`, column c0_small)
+    uint32_t tm_small, c0_small;
     uint32_t act;               // 1: FiLM + sin, 0: linear
     uint32_t film;              // row of gamma / beta
     uint32_t to_act;            // write the fp16 output into ACT (input of the next layer and / or source of the TMA store)
@@ -57,7 +58,8 @@ struct ChainLayer {
     float* out_head;
     float* out_f32;             // optional fp32 copy of the output in HBM
     int64_t ld_out_f32;
-    uint16_t* out_cos;          // SAVE: cos(gamma u + c) as fp16 [M, 256] -- the activation derivative the backward chain multiplies with
+    uint32_t store_cos;         // SAVE: TMA-store cos(gamma u + c) (fp16 [M, 256], the derivative the backward chain multiplies with) via stores.c[layer]
+    uint32_t pad2;
 };
 
 struct ChainParams {
@@ -65,10 +67,6 @@ struct ChainParams {
     uint32_t in_dim, view_dim, x_nk, v_nk;     // v_nk = 0: no view part
     const float* x_in;          // [M, in_dim] fp32
     const float* view_feat;     // [M / rows_per_ray, view_dim] fp32
-    const float* w_x;           // fp32 [256, in_dim] (pitch ld_wx): layer 0's weights
-    int64_t ld_wx;
-    const float* w_v;           // fp32 [256, view_dim] (pitch ld_wv): the view columns of the last layer's weights
-    int64_t ld_wv;
     const float* gamma;         // + img * gstride + film * 256 + n
     const float* beta;
     int64_t gstride;
@@ -80,14 +78,15 @@ struct ChainParams {
     ChainLayer layer[CH_MAX_LAYERS];
 };
 
-struct alignas(64) ChainMaps { CUtensorMap m[CH_MAX_MAPS]; };
-struct alignas(64) ChainStoreMaps { CUtensorMap m[CH_MAX_LAYERS]; };
+struct alignas(64) ChainMaps { CUtensorMap m[CH_MAX_MAPS + 1]; };      // K = 256 layers (+ layer 0's small weight matrix)
+struct alignas(64) ChainStoreMaps { CUtensorMap m[CH_MAX_LAYERS]; CUtensorMap c[CH_MAX_LAYERS]; };
 
 struct ChainSmem {
     uint64_t w_full[CH_W_STAGES], w_empty[CH_W_STAGES];
     uint64_t act_ready[4], fin_ready[4], st_done[4];   // fin_ready: chunks of the LAST layer's output (consumed by the storer only)
     uint64_t acc_full[2], acc_empty[2];
     uint64_t x_full, x_free, v_full, v_free;
+    uint64_t cos_ready[CH_COS_SLOTS], cos_done[CH_COS_SLOTS];
     uint32_t tmem_base;
     uint32_t pad[3];
     alignas(16) float gam[2][256];      // double-buffered per-layer FiLM constants: gamma, gamma*bias + beta
@@ -97,7 +96,7 @@ struct ChainSmem {
 };
 
 __host__ __device__ inline uint32_t chain_smem_bytes() {
-    return 1024 + CH_ACT_BYTES + CH_CHUNK_BYTES + CH_WSMALL_BYTES + CH_W_STAGES * CH_W_STAGE_BYTES + (uint32_t)sizeof(ChainSmem);
+    return 1024 + CH_ACT_BYTES + CH_CHUNK_BYTES + CH_W_STAGES * CH_W_STAGE_BYTES + CH_COS_SLOTS * CH_CHUNK_BYTES + (uint32_t)sizeof(ChainSmem);
 }
 
 // byte offset of 16-byte unit u of row r inside a 128B-swizzled tile (what TMA SWIZZLE_128B / the UMMA descriptor expect)
@@ -143,9 +142,9 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smACT = smem;
     uint8_t* smSMALL = smACT + CH_ACT_BYTES;
-    uint8_t* smWSMALL = smSMALL + CH_CHUNK_BYTES;
-    uint8_t* smRING = smWSMALL + CH_WSMALL_BYTES;
-    ChainSmem& S = *reinterpret_cast<ChainSmem*>(smRING + CH_W_STAGES * CH_W_STAGE_BYTES);
+    uint8_t* smRING = smSMALL + CH_CHUNK_BYTES;
+    uint8_t* smCOS = smRING + CH_W_STAGES * CH_W_STAGE_BYTES;
+    ChainSmem& S = *reinterpret_cast<ChainSmem*>(smCOS + CH_COS_SLOTS * CH_CHUNK_BYTES);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t t_begin = blockIdx.x * P.tiles_per_cta;
@@ -158,24 +157,19 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
         for (uint32_t i = 0; i < 4; i++) { mbar_init(&S.act_ready[i], CH_EPI_WARPS); mbar_init(&S.fin_ready[i], CH_EPI_WARPS); mbar_init(&S.st_done[i], 1); }
         for (uint32_t i = 0; i < 2; i++) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], CH_EPI_WARPS); }
         mbar_init(&S.x_full, 1); mbar_init(&S.x_free, 1); mbar_init(&S.v_full, 1); mbar_init(&S.v_free, 1);
+        for (uint32_t i = 0; i < CH_COS_SLOTS; i++) { mbar_init(&S.cos_ready[i], CH_EPI_WARPS); mbar_init(&S.cos_done[i], 1); }
         fence_barrier_init();
     }
     if (warp == CH_WARP_TMA && lane == 0)
         for (uint32_t i = 0; i < nL; i++) {
             if (P.layer[i].has_main) tma_prefetch_desc(&maps.m[P.layer[i].tm]);
+            if (P.layer[i].small_nk) tma_prefetch_desc(&maps.m[P.layer[i].tm_small]);
             if (SAVE && P.layer[i].store) tma_prefetch_desc(&stores.m[i]);
+            if (SAVE && P.layer[i].store_cos) tma_prefetch_desc(&stores.c[i]);
         }
     if (warp == CH_WARP_MMA) tmem_alloc(&S.tmem_base, 512);
-    // resident small weights: K-steps [0, x_nk) = layer 0, [x_nk, x_nk + v_nk) = view columns of the last layer; head vectors
+    // head vectors
     {
-        const uint32_t units = 2 * (P.x_nk + P.v_nk);
-        for (uint32_t i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
-            const uint32_t j = i >> 3, u = i & 7;
-            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (u < 2 * P.x_nk) load8(P.w_x + (int64_t)j * P.ld_wx, u * 8, P.in_dim, v);
-            else if (u < units) load8(P.w_v + (int64_t)j * P.ld_wv, (u - 2 * P.x_nk) * 8, P.view_dim, v);
-            *reinterpret_cast<uint4*>(smWSMALL + sw128(j, u)) = pack8(v, FMT_F16);
-        }
         uint32_t hrow = 0;
         for (uint32_t i = 0; i < nL; i++) {
             const uint32_t nh = P.layer[i].nh;
@@ -197,13 +191,16 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = t_begin; t < t_end; t++)
                 for (uint32_t i = 0; i < nL; i++) {
-                    if (!P.layer[i].has_main) continue;
-                    const CUtensorMap* tm = &maps.m[P.layer[i].tm];
-                    for (uint32_t kc = 0; kc < 4; kc++) {
+                    // issue order of the MMA thread: layer 0's small chunk first, a view layer's small chunk after its 4 main chunks
+                    const uint32_t n_main = P.layer[i].has_main ? 4u : 0u, n_chunks = n_main + (P.layer[i].small_nk ? 1u : 0u);
+                    for (uint32_t k = 0; k < n_chunks; k++) {
+                        const bool small = P.layer[i].small_nk && (i == 0 ? k == 0 : k == n_main);
+                        const uint32_t kc = (i == 0 && P.layer[i].small_nk) ? k - 1 : k;
                         mbar_wait(&S.w_empty[stage], phase ^ 1);
                         mbar_arrive_expect_tx(&S.w_full[stage], CH_W_STAGE_BYTES);
-                        tma_load_2d(smRING + stage * CH_W_STAGE_BYTES, tm, &S.w_full[stage], (int32_t)(kc * 64), 0);
-                        CH_DBG(3, i * 16 + kc);
+                        if (small) tma_load_2d(smRING + stage * CH_W_STAGE_BYTES, &maps.m[P.layer[i].tm_small], &S.w_full[stage], (int32_t)P.layer[i].c0_small, 0);
+                        else tma_load_2d(smRING + stage * CH_W_STAGE_BYTES, &maps.m[P.layer[i].tm], &S.w_full[stage], (int32_t)(kc * 64), 0);
+                        CH_DBG(3, i * 16 + k);
                         if (++stage == CH_W_STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -212,7 +209,7 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
         // ===================================================== MMA issuer
         if (lane == 0) {
             const uint32_t idesc = idesc_f16(CH_TILE_M, 256, FMT_F16, FMT_F16, 0, 0);
-            const uint32_t a_small = smem_u32(smSMALL), b_small = smem_u32(smWSMALL), a_act = smem_u32(smACT);
+            const uint32_t a_small = smem_u32(smSMALL), a_act = smem_u32(smACT);
             uint32_t stage = 0, phase = 0, n = 0, actgen = 0, it = 0;
             for (uint32_t t = t_begin; t < t_end; t++, it++)
                 for (uint32_t i = 0; i < nL; i++, n++) {
@@ -224,10 +221,14 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                     uint32_t accumulate = 0;
                     if (snk && i == 0) {                                  // x part
                         mbar_wait(&S.x_full, it & 1);
+                        mbar_wait(&S.w_full[stage], phase);
                         tc_fence_after();
-                        for (uint32_t s = sk0; s < sk0 + snk; s++, accumulate = 1)
-                            umma_bf16(tmem_d, smem_desc_sw128(a_small + s * 32, 16, 1024), smem_desc_sw128(b_small + s * 32, 16, 1024), idesc, accumulate);
+                        const uint32_t b_addr = smem_u32(smRING + stage * CH_W_STAGE_BYTES);
+                        for (uint32_t s = 0; s < snk; s++, accumulate = 1)
+                            umma_bf16(tmem_d, smem_desc_sw128(a_small + (sk0 + s) * 32, 16, 1024), smem_desc_sw128(b_addr + s * 32, 16, 1024), idesc, accumulate);
                         umma_commit(&S.x_free);
+                        umma_commit(&S.w_empty[stage]);
+                        if (++stage == CH_W_STAGES) { stage = 0; phase ^= 1; }
                     }
                     if (has_main) {
                         for (uint32_t kc = 0; kc < 4; kc++) {
@@ -247,10 +248,14 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                     }
                     if (snk && i != 0) {                                  // view part
                         mbar_wait(&S.v_full, it & 1);
+                        mbar_wait(&S.w_full[stage], phase);
                         tc_fence_after();
-                        for (uint32_t s = sk0; s < sk0 + snk; s++, accumulate = 1)
-                            umma_bf16(tmem_d, smem_desc_sw128(a_small + s * 32, 16, 1024), smem_desc_sw128(b_small + s * 32, 16, 1024), idesc, accumulate);
+                        const uint32_t b_addr = smem_u32(smRING + stage * CH_W_STAGE_BYTES);
+                        for (uint32_t s = 0; s < snk; s++, accumulate = 1)
+                            umma_bf16(tmem_d, smem_desc_sw128(a_small + (sk0 + s) * 32, 16, 1024), smem_desc_sw128(b_addr + s * 32, 16, 1024), idesc, accumulate);
                         umma_commit(&S.v_free);
+                        umma_commit(&S.w_empty[stage]);
+                        if (++stage == CH_W_STAGES) { stage = 0; phase ^= 1; }
                     }
                     umma_commit(&S.acc_full[acc]);
                 }
@@ -313,23 +318,47 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
     } else if (warp == CH_WARP_STORE) {
         // ===================================================== storer (SAVE): finished ACT chunks -> saved activations in HBM
         if (SAVE && lane == 0) {
-            uint32_t actgen = 0, fingen = 0;
+            uint32_t actgen = 0, fingen = 0, ncos = 0;
+            // the stores of one chunk are one bulk group; one group may still be reading shared memory while the next chunk's stores
+            // are issued -- the "may be overwritten" arrivals of a chunk are made once its group has drained.  (A deeper queue would
+            // deadlock on the 2 cos staging slots: slot k+2 is released by group k, which would wait for group k+2.)
+            uint64_t* pend[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+            uint32_t np = 0;
+            auto retire = [&](uint32_t k) {
+                if (pend[k][0]) mbar_arrive(pend[k][0]);
+                if (pend[k][1]) mbar_arrive(pend[k][1]);
+            };
             for (uint32_t t = t_begin; t < t_end; t++)
                 for (uint32_t i = 0; i < nL; i++) {
-                    if (!P.layer[i].to_act) continue;
-                    const bool st = P.layer[i].store != 0, fin = i + 1 == nL;
+                    const bool st = P.layer[i].store != 0, fin = i + 1 == nL, to_act = P.layer[i].to_act != 0, cs = P.layer[i].store_cos != 0;
+                    if (!to_act && !cs) continue;
                     for (uint32_t c = 0; c < 4; c++) {
-                        if (fin) mbar_wait(&S.fin_ready[c], fingen & 1);
-                        else mbar_wait(&S.act_ready[c], actgen & 1);
-                        if (st) {
-                            tma_store_2d(&stores.m[i], smACT + c * CH_CHUNK_BYTES, (int32_t)(c * 64), (int32_t)(t * CH_TILE_M));
-                            tma_store_commit();
-                            tma_store_wait_read();
+                        const uint32_t slot = ncos % CH_COS_SLOTS, use = ncos / CH_COS_SLOTS;
+                        if (cs) {                                        // cos chunk (staged before the activation chunk is published)
+                            mbar_wait(&S.cos_ready[slot], use & 1);
+                            tma_store_2d(&stores.c[i], smCOS + slot * CH_CHUNK_BYTES, (int32_t)(c * 64), (int32_t)(t * CH_TILE_M));
                         }
-                        mbar_arrive(&S.st_done[c]);                       // the chunk may be overwritten
+                        if (to_act) {
+                            if (fin) mbar_wait(&S.fin_ready[c], fingen & 1);
+                            else mbar_wait(&S.act_ready[c], actgen & 1);
+                            if (st) tma_store_2d(&stores.m[i], smACT + c * CH_CHUNK_BYTES, (int32_t)(c * 64), (int32_t)(t * CH_TILE_M));
+                        }
+                        tma_store_commit();
+                        pend[np][0] = cs ? &S.cos_done[slot] : nullptr;
+                        pend[np][1] = to_act ? &S.st_done[c] : nullptr;
+                        np++;
+                        if (np == 2) {                                   // the older group has drained once at most 1 is still reading
+                            tma_store_wait_read_pending<1>();
+                            retire(0);
+                            pend[0][0] = pend[1][0]; pend[0][1] = pend[1][1];
+                            np = 1;
+                        }
+                        if (cs) ncos++;
                     }
-                    if (fin) fingen++; else actgen++;
+                    if (to_act) { if (fin) fingen++; else actgen++; }
                 }
+            tma_store_wait_read();
+            for (uint32_t k = 0; k < np; k++) retire(k);
             tma_store_wait_all();
         }
     } else {
@@ -340,7 +369,7 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
         const uint32_t r = q * 32 + lane;                              // row of the tile = TMEM lane
         const uint32_t act_row = smem_u32(smACT) + r * 128;
         const uint32_t u0 = ((2 * sb) ^ (r & 7)) << 4, u1 = ((2 * sb + 1) ^ (r & 7)) << 4;
-        uint32_t n = 0, stgen = 0;
+        uint32_t n = 0, stgen = 0, ncos = 0;
         for (uint32_t t = t_begin; t < t_end; t++) {
             const uint64_t row = (uint64_t)t * CH_TILE_M + r;
             const bool valid = row < P.M_total;
@@ -350,7 +379,7 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                 // layer description -> registers (constant-bank reads with a dynamic index are slow inside the chunk loop)
                 const uint32_t L_act = P.layer[i].act, L_nh = P.layer[i].nh, L_to_act = P.layer[i].to_act, L_film = P.layer[i].film;
                 float* const o32 = P.layer[i].out_f32;
-                uint16_t* const ocos = SAVE ? P.layer[i].out_cos : nullptr;
+                const bool do_cos = SAVE && P.layer[i].store_cos;
                 const int64_t ld32 = P.layer[i].ld_out_f32;
                 const uint32_t acc = n & 1, use = n >> 1, tb = n & 1;
                 const uint32_t gam_s = smem_u32(&S.gam[tb][0]), cst_s = smem_u32(&S.cst[tb][0]);
@@ -390,15 +419,19 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                         v[k + 3] = fmaf(__uint_as_float(raw[c & 1][k + 3]), g4.w, c4.w);
                     }
                     if (L_act) {
-                        if (SAVE && ocos) {                              // derivative for the backward chain (no recompute there)
+                        if (do_cos) {                                    // derivative for the backward chain (no recompute there)
                             float cs[16];
 #pragma unroll
                             for (int k = 0; k < 16; k++) cs[k] = __cosf(v[k]);
-                            if (valid) {
-                                uint4* dst = reinterpret_cast<uint4*>(ocos + row * 256 + col);
-                                dst[0] = make_uint4(pack_f16(cs[0], cs[1]), pack_f16(cs[2], cs[3]), pack_f16(cs[4], cs[5]), pack_f16(cs[6], cs[7]));
-                                dst[1] = make_uint4(pack_f16(cs[8], cs[9]), pack_f16(cs[10], cs[11]), pack_f16(cs[12], cs[13]), pack_f16(cs[14], cs[15]));
-                            }
+                            const uint32_t slot = ncos % CH_COS_SLOTS, use = ncos / CH_COS_SLOTS;
+                            mbar_wait(&S.cos_done[slot], (use & 1) ^ 1);   // the store of the slot's previous contents has read it
+                            const uint32_t dstc = smem_u32(smCOS) + slot * CH_CHUNK_BYTES + r * 128;
+                            sts128(dstc + u0, make_uint4(pack_f16(cs[0], cs[1]), pack_f16(cs[2], cs[3]), pack_f16(cs[4], cs[5]), pack_f16(cs[6], cs[7])));
+                            sts128(dstc + u1, make_uint4(pack_f16(cs[8], cs[9]), pack_f16(cs[10], cs[11]), pack_f16(cs[12], cs[13]), pack_f16(cs[14], cs[15])));
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&S.cos_ready[slot]);
+                            ncos++;
                         }
 #pragma unroll
                         for (int k = 0; k < 16; k++) v[k] = __sinf(v[k]);

@@ -88,6 +88,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// at most N committed store groups of this thread may still be reading their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_pending() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------------
