@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for v in 0 1; do
-  if [ $v = 1 ]; then export SDFG_EXP_HALFW=1; fi
-  timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/exp_$v.log 2>&1
-  grep -o '"ms_per_step": [0-9.]*\|"kernel_ms_per_step": [0-9.]*' gpurun_out/exp_$v.log
+for v in 0 4 5; do
+  SDFG_EXP=$v python scripts/prof_step.py 32 > gpurun_out/exp_$v.log 2>&1
+  echo "exp=$v"; grep "tc_chain_fwd" gpurun_out/exp_$v.log | tail -1
 done

@@ -169,6 +169,9 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
     P.x_nk = ceil_div<uint32_t>(p->in_dim, 16);
     P.v_nk = want_views ? ceil_div<uint32_t>(p->view_dim, 16) : 0;   // the view part is loaded only when a layer consumes it
     P.x_in = x_in; P.view_feat = view_feat;
+    P.w_x = p->has_input_linear ? p->input_w : p->film_w[0]; P.ld_wx = p->in_dim;
+    P.w_v = p->film_w[nf] ? p->film_w[nf] + W : nullptr; P.ld_wv = W + p->view_dim;
+    if (!P.w_v) P.v_nk = 0;
     P.gamma = p->gamma; P.beta = p->beta; P.gstride = (int64_t)(nf + 1) * W;
     P.kp_x = L.Kp_in; P.kp_v = L.Kp_v - W;
     if (save) {
@@ -235,18 +238,21 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
     }
     P.n_layers = nl;
     for (uint32_t i = 0; i < nl; i++) P.layer[i].to_act = (i + 1 < nl || P.layer[i].store) ? 1 : 0;
+    { static const int ef = []() { const char* e = getenv("SDFG_EXP"); return e ? atoi(e) : 0; }(); P.exp_flags = (uint32_t)ef;
+      if (ef & 2) for (uint32_t i = 0; i < nl; i++) P.layer[i].store_cos = 0; }      // 2 = no cos tile at all
     P.n_tiles = (uint32_t)ceil_div<uint64_t>(N, tc::CH_TILE_M);
     const uint32_t ctas = std::min<uint32_t>((uint32_t)sm_count(), P.n_tiles);
     P.tiles_per_cta = ceil_div<uint32_t>(P.n_tiles, ctas);
     const uint32_t grid = ceil_div<uint32_t>(P.n_tiles, P.tiles_per_cta);
     const uint32_t smem = tc::chain_smem_bytes();
     const bool storing = save || out_feat16;
-    auto kern = storing ? tc::tc_chain_fwd_kernel<true> : tc::tc_chain_fwd_kernel<false>;
-    static thread_local bool configured[2] = {false, false};
-    if (!configured[storing ? 1 : 0]) {
+    auto kern = save ? tc::tc_chain_fwd_kernel<true, true> : (storing ? tc::tc_chain_fwd_kernel<true, false> : tc::tc_chain_fwd_kernel<false, false>);
+    static thread_local bool configured[3] = {false, false, false};
+    const int kidx = save ? 2 : (storing ? 1 : 0);
+    if (!configured[kidx]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return set_error(SDFG_ERR_CUDA, "tc_chain_fwd_kernel: cannot opt in to %u bytes of shared memory", smem);
-        configured[storing ? 1 : 0] = true;
+        configured[kidx] = true;
     }
     static const bool dbg_on = getenv("SDFG_CHAIN_DBG") != nullptr;     // debugging aid: event log of CTA 0 to stderr
     if (dbg_on) {

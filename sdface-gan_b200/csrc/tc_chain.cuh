@@ -67,6 +67,10 @@ struct ChainParams {
     uint32_t in_dim, view_dim, x_nk, v_nk;     // v_nk = 0: no view part
     const float* x_in;          // [M, in_dim] fp32
     const float* view_feat;     // [M / rows_per_ray, view_dim] fp32
+    const float* w_x;           // inference: fp32 [256, in_dim] (pitch ld_wx), layer 0's weights -> resident small-weight tile
+    int64_t ld_wx;
+    const float* w_v;           // inference: fp32 [256, view_dim] (pitch ld_wv), the view columns of the last layer's weights
+    int64_t ld_wv;
     const float* gamma;         // + img * gstride + film * 256 + n
     const float* beta;
     int64_t gstride;
@@ -75,6 +79,8 @@ struct ChainParams {
     uint16_t* v16;              // SAVE: view part expanded per sample, kp_v columns (NULL ok)
     int64_t ld_v16;
     unsigned long long* dbg;    // debugging: per-role (tag, clock) event log of CTA 0, 4 x 2048 entries (NULL = off)
+    uint32_t exp_flags;         // timing experiments only (wrong results): 1 = no MUFU for the cos tile
+    uint32_t pad3;
     ChainLayer layer[CH_MAX_LAYERS];
 };
 
@@ -135,7 +141,10 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8], uint32_t fmt) {
         }                                                                                                   \
     } while (0)
 
-template <bool SAVE>
+// SAVE: a storer thread TMA-stores finished activation chunks (training: every layer; inference: the fp16 features).
+// COS (training only): FiLM layers also produce cos(gamma u + c) tiles for the backward chain; the 32 KB that hold the resident
+// small weights in inference become the cos staging slots and the small weights are streamed through the ring instead.
+template <bool SAVE, bool COS>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainStoreMaps stores, const __grid_constant__ ChainParams P) {
     extern __shared__ uint8_t smem_raw[];
@@ -143,7 +152,9 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
     uint8_t* smACT = smem;
     uint8_t* smSMALL = smACT + CH_ACT_BYTES;
     uint8_t* smRING = smSMALL + CH_CHUNK_BYTES;
-    uint8_t* smCOS = smRING + CH_W_STAGES * CH_W_STAGE_BYTES;
+    uint8_t* smCOS = smRING + CH_W_STAGES * CH_W_STAGE_BYTES;   // SAVE: cos staging slots; inference: the same 32 KB hold the RESIDENT
+    uint8_t* smWSMALL = smCOS;                                  // small weights (layer 0 + view columns), which SAVE streams instead
+    constexpr bool RESIDENT = !COS;
     ChainSmem& S = *reinterpret_cast<ChainSmem*>(smCOS + CH_COS_SLOTS * CH_CHUNK_BYTES);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -165,9 +176,20 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
             if (P.layer[i].has_main) tma_prefetch_desc(&maps.m[P.layer[i].tm]);
             if (P.layer[i].small_nk) tma_prefetch_desc(&maps.m[P.layer[i].tm_small]);
             if (SAVE && P.layer[i].store) tma_prefetch_desc(&stores.m[i]);
-            if (SAVE && P.layer[i].store_cos) tma_prefetch_desc(&stores.c[i]);
+            if (COS && P.layer[i].store_cos) tma_prefetch_desc(&stores.c[i]);
         }
     if (warp == CH_WARP_MMA) tmem_alloc(&S.tmem_base, 512);
+    // inference: resident small weights, K-steps [0, x_nk) = layer 0, [x_nk, x_nk + v_nk) = view columns of the last layer
+    if (RESIDENT) {
+        const uint32_t units = 2 * (P.x_nk + P.v_nk);
+        for (uint32_t i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
+            const uint32_t j = i >> 3, u = i & 7;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (u < 2 * P.x_nk) load8(P.w_x + (int64_t)j * P.ld_wx, u * 8, P.in_dim, v);
+            else if (u < units) load8(P.w_v + (int64_t)j * P.ld_wv, (u - 2 * P.x_nk) * 8, P.view_dim, v);
+            *reinterpret_cast<uint4*>(smWSMALL + sw128(j, u)) = pack8(v, FMT_F16);
+        }
+    }
     // head vectors
     {
         uint32_t hrow = 0;
@@ -192,9 +214,9 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
             for (uint32_t t = t_begin; t < t_end; t++)
                 for (uint32_t i = 0; i < nL; i++) {
                     // issue order of the MMA thread: layer 0's small chunk first, a view layer's small chunk after its 4 main chunks
-                    const uint32_t n_main = P.layer[i].has_main ? 4u : 0u, n_chunks = n_main + (P.layer[i].small_nk ? 1u : 0u);
+                    const uint32_t n_main = P.layer[i].has_main ? 4u : 0u, n_chunks = n_main + ((P.layer[i].small_nk && !RESIDENT) ? 1u : 0u);
                     for (uint32_t k = 0; k < n_chunks; k++) {
-                        const bool small = P.layer[i].small_nk && (i == 0 ? k == 0 : k == n_main);
+                        const bool small = !RESIDENT && P.layer[i].small_nk && (i == 0 ? k == 0 : k == n_main);
                         const uint32_t kc = (i == 0 && P.layer[i].small_nk) ? k - 1 : k;
                         mbar_wait(&S.w_empty[stage], phase ^ 1);
                         mbar_arrive_expect_tx(&S.w_full[stage], CH_W_STAGE_BYTES);
@@ -221,14 +243,16 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                     uint32_t accumulate = 0;
                     if (snk && i == 0) {                                  // x part
                         mbar_wait(&S.x_full, it & 1);
-                        mbar_wait(&S.w_full[stage], phase);
+                        if (!RESIDENT) mbar_wait(&S.w_full[stage], phase);
                         tc_fence_after();
-                        const uint32_t b_addr = smem_u32(smRING + stage * CH_W_STAGE_BYTES);
+                        const uint32_t b_addr = RESIDENT ? smem_u32(smWSMALL) + sk0 * 32 : smem_u32(smRING + stage * CH_W_STAGE_BYTES);
                         for (uint32_t s = 0; s < snk; s++, accumulate = 1)
                             umma_bf16(tmem_d, smem_desc_sw128(a_small + (sk0 + s) * 32, 16, 1024), smem_desc_sw128(b_addr + s * 32, 16, 1024), idesc, accumulate);
                         umma_commit(&S.x_free);
-                        umma_commit(&S.w_empty[stage]);
-                        if (++stage == CH_W_STAGES) { stage = 0; phase ^= 1; }
+                        if (!RESIDENT) {
+                            umma_commit(&S.w_empty[stage]);
+                            if (++stage == CH_W_STAGES) { stage = 0; phase ^= 1; }
+                        }
                     }
                     if (has_main) {
                         for (uint32_t kc = 0; kc < 4; kc++) {
@@ -248,14 +272,16 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                     }
                     if (snk && i != 0) {                                  // view part
                         mbar_wait(&S.v_full, it & 1);
-                        mbar_wait(&S.w_full[stage], phase);
+                        if (!RESIDENT) mbar_wait(&S.w_full[stage], phase);
                         tc_fence_after();
-                        const uint32_t b_addr = smem_u32(smRING + stage * CH_W_STAGE_BYTES);
+                        const uint32_t b_addr = RESIDENT ? smem_u32(smWSMALL) + sk0 * 32 : smem_u32(smRING + stage * CH_W_STAGE_BYTES);
                         for (uint32_t s = 0; s < snk; s++, accumulate = 1)
                             umma_bf16(tmem_d, smem_desc_sw128(a_small + (sk0 + s) * 32, 16, 1024), smem_desc_sw128(b_addr + s * 32, 16, 1024), idesc, accumulate);
                         umma_commit(&S.v_free);
-                        umma_commit(&S.w_empty[stage]);
-                        if (++stage == CH_W_STAGES) { stage = 0; phase ^= 1; }
+                        if (!RESIDENT) {
+                            umma_commit(&S.w_empty[stage]);
+                            if (++stage == CH_W_STAGES) { stage = 0; phase ^= 1; }
+                        }
                     }
                     umma_commit(&S.acc_full[acc]);
                 }
@@ -319,46 +345,37 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
         // ===================================================== storer (SAVE): finished ACT chunks -> saved activations in HBM
         if (SAVE && lane == 0) {
             uint32_t actgen = 0, fingen = 0, ncos = 0;
-            // the stores of one chunk are one bulk group; one group may still be reading shared memory while the next chunk's stores
-            // are issued -- the "may be overwritten" arrivals of a chunk are made once its group has drained.  (A deeper queue would
-            // deadlock on the 2 cos staging slots: slot k+2 is released by group k, which would wait for group k+2.)
-            uint64_t* pend[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-            uint32_t np = 0;
-            auto retire = [&](uint32_t k) {
-                if (pend[k][0]) mbar_arrive(pend[k][0]);
-                if (pend[k][1]) mbar_arrive(pend[k][1]);
-            };
+            // Per chunk: the cos store is one bulk group, the activation store the next.  After both are committed we wait until at
+            // most ONE group is still reading shared memory: the cos slot (older group) is then free again -- it is needed two
+            // chunks later and must not wait for the next chunk's stores -- while the activation chunk (only overwritten one layer
+            // later) is released one iteration behind.
+            uint64_t* pend = nullptr;
             for (uint32_t t = t_begin; t < t_end; t++)
                 for (uint32_t i = 0; i < nL; i++) {
-                    const bool st = P.layer[i].store != 0, fin = i + 1 == nL, to_act = P.layer[i].to_act != 0, cs = P.layer[i].store_cos != 0;
+                    const bool st = P.layer[i].store != 0, fin = i + 1 == nL, to_act = P.layer[i].to_act != 0, cs = COS && P.layer[i].store_cos != 0;
                     if (!to_act && !cs) continue;
                     for (uint32_t c = 0; c < 4; c++) {
                         const uint32_t slot = ncos % CH_COS_SLOTS, use = ncos / CH_COS_SLOTS;
-                        if (cs) {                                        // cos chunk (staged before the activation chunk is published)
+                        if (cs) {
                             mbar_wait(&S.cos_ready[slot], use & 1);
-                            tma_store_2d(&stores.c[i], smCOS + slot * CH_CHUNK_BYTES, (int32_t)(c * 64), (int32_t)(t * CH_TILE_M));
+                            if (!(P.exp_flags & 4)) tma_store_2d(&stores.c[i], smCOS + slot * CH_CHUNK_BYTES, (int32_t)(c * 64), (int32_t)(t * CH_TILE_M));
                         }
+                        tma_store_commit();
                         if (to_act) {
                             if (fin) mbar_wait(&S.fin_ready[c], fingen & 1);
                             else mbar_wait(&S.act_ready[c], actgen & 1);
                             if (st) tma_store_2d(&stores.m[i], smACT + c * CH_CHUNK_BYTES, (int32_t)(c * 64), (int32_t)(t * CH_TILE_M));
                         }
                         tma_store_commit();
-                        pend[np][0] = cs ? &S.cos_done[slot] : nullptr;
-                        pend[np][1] = to_act ? &S.st_done[c] : nullptr;
-                        np++;
-                        if (np == 2) {                                   // the older group has drained once at most 1 is still reading
-                            tma_store_wait_read_pending<1>();
-                            retire(0);
-                            pend[0][0] = pend[1][0]; pend[0][1] = pend[1][1];
-                            np = 1;
-                        }
-                        if (cs) ncos++;
+                        tma_store_wait_read_pending<1>();
+                        if (cs) { mbar_arrive(&S.cos_done[slot]); ncos++; }
+                        if (pend) mbar_arrive(pend);
+                        pend = to_act ? &S.st_done[c] : nullptr;
                     }
                     if (to_act) { if (fin) fingen++; else actgen++; }
                 }
             tma_store_wait_read();
-            for (uint32_t k = 0; k < np; k++) retire(k);
+            if (pend) mbar_arrive(pend);
             tma_store_wait_all();
         }
     } else {
@@ -379,7 +396,7 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                 // layer description -> registers (constant-bank reads with a dynamic index are slow inside the chunk loop)
                 const uint32_t L_act = P.layer[i].act, L_nh = P.layer[i].nh, L_to_act = P.layer[i].to_act, L_film = P.layer[i].film;
                 float* const o32 = P.layer[i].out_f32;
-                const bool do_cos = SAVE && P.layer[i].store_cos;
+                const bool do_cos = COS && P.layer[i].store_cos;
                 const int64_t ld32 = P.layer[i].ld_out_f32;
                 const uint32_t acc = n & 1, use = n >> 1, tb = n & 1;
                 const uint32_t gam_s = smem_u32(&S.gam[tb][0]), cst_s = smem_u32(&S.cst[tb][0]);
@@ -418,20 +435,14 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                         v[k + 2] = fmaf(__uint_as_float(raw[c & 1][k + 2]), g4.z, c4.z);
                         v[k + 3] = fmaf(__uint_as_float(raw[c & 1][k + 3]), g4.w, c4.w);
                     }
+                    uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
                     if (L_act) {
                         if (do_cos) {                                    // derivative for the backward chain (no recompute there)
                             float cs[16];
 #pragma unroll
-                            for (int k = 0; k < 16; k++) cs[k] = __cosf(v[k]);
-                            const uint32_t slot = ncos % CH_COS_SLOTS, use = ncos / CH_COS_SLOTS;
-                            mbar_wait(&S.cos_done[slot], (use & 1) ^ 1);   // the store of the slot's previous contents has read it
-                            const uint32_t dstc = smem_u32(smCOS) + slot * CH_CHUNK_BYTES + r * 128;
-                            sts128(dstc + u0, make_uint4(pack_f16(cs[0], cs[1]), pack_f16(cs[2], cs[3]), pack_f16(cs[4], cs[5]), pack_f16(cs[6], cs[7])));
-                            sts128(dstc + u1, make_uint4(pack_f16(cs[8], cs[9]), pack_f16(cs[10], cs[11]), pack_f16(cs[12], cs[13]), pack_f16(cs[14], cs[15])));
-                            fence_proxy_async();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&S.cos_ready[slot]);
-                            ncos++;
+                            for (int k = 0; k < 16; k++) cs[k] = (P.exp_flags & 1) ? v[k] * 0.01f : __cosf(v[k]);
+                            c0 = make_uint4(pack_f16(cs[0], cs[1]), pack_f16(cs[2], cs[3]), pack_f16(cs[4], cs[5]), pack_f16(cs[6], cs[7]));
+                            c1 = make_uint4(pack_f16(cs[8], cs[9]), pack_f16(cs[10], cs[11]), pack_f16(cs[12], cs[13]), pack_f16(cs[14], cs[15]));
                         }
 #pragma unroll
                         for (int k = 0; k < 16; k++) v[k] = __sinf(v[k]);
@@ -454,11 +465,22 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                         const uint4 h1 = make_uint4(pack_f16(v[8], v[9]), pack_f16(v[10], v[11]), pack_f16(v[12], v[13]), pack_f16(v[14], v[15]));
                         if (SAVE) mbar_wait(&S.st_done[c], (stgen & 1) ^ 1);   // the previous contents of the chunk have been stored
                         const uint32_t chunk = act_row + c * CH_CHUNK_BYTES;
+                        const uint32_t slot = ncos % CH_COS_SLOTS;
+                        if (do_cos) {                                    // cos chunk -> staging slot (one fence for both tiles)
+                            mbar_wait(&S.cos_done[slot], ((ncos / CH_COS_SLOTS) & 1) ^ 1);   // the slot's previous store has read it
+                            const uint32_t dstc = smem_u32(smCOS) + slot * CH_CHUNK_BYTES + r * 128;
+                            sts128(dstc + u0, c0);
+                            sts128(dstc + u1, c1);
+                        }
                         sts128(chunk + u0, h0);
                         sts128(chunk + u1, h1);
                         fence_proxy_async();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(i + 1 == nL ? &S.fin_ready[c] : &S.act_ready[c]);
+                        if (lane == 0) {
+                            if (do_cos) mbar_arrive(&S.cos_ready[slot]);
+                            mbar_arrive(i + 1 == nL ? &S.fin_ready[c] : &S.act_ready[c]);
+                        }
+                        if (do_cos) ncos++;
                         if (threadIdx.x == 0) CH_DBG(1, 500 + i * 16 + c);
                     }
                     if (o32 && valid) {
