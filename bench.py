@@ -170,7 +170,7 @@ def run_ours(args):
     if world > 1:      # identical weights on every rank
         for p_ in g.parameters():
             dist.broadcast(p_.data, 0)
-    model = torch.nn.parallel.DistributedDataParallel(g, device_ids=[local], bucket_cap_mb=64) if world > 1 else g
+    model = torch.nn.parallel.DistributedDataParallel(g, device_ids=[local], bucket_cap_mb=64, gradient_as_bucket_view=True) if world > 1 else g
     opt = torch.optim.Adam(g.parameters(), lr=2e-5, betas=(0.0, 0.9), fused=True)      # im2scene/config.py:196-204 (stage 1); one fused update kernel
 
     # synthetic inputs: resident copies for `value`, pinned host copies for `e2e`
