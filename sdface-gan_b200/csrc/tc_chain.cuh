@@ -387,6 +387,16 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
         const uint32_t act_row = smem_u32(smACT) + r * 128;
         const uint32_t u0 = ((2 * sb) ^ (r & 7)) << 4, u1 = ((2 * sb + 1) ^ (r & 7)) << 4;
         uint32_t n = 0, stgen = 0, ncos = 0;
+        // FiLM constant of (layer, image) this thread publishes: threads 0..255 gamma (1 for a linear layer), 256..511 gamma*bias + beta.
+        // It is fetched one layer AHEAD so that its L2 latency hides behind the chunk loop instead of sitting between two layers.
+        auto film_const = [&](uint32_t i, uint32_t img) -> float {
+            const uint32_t col = etid & 255, act = P.layer[i].act, film = P.layer[i].film;
+            const float gm = act ? __ldg(P.gamma + (int64_t)img * P.gstride + film * 256 + col) : 1.f;
+            if (etid < 256) return gm;
+            const float b = __ldg(P.layer[i].bias + col);
+            return act ? fmaf(gm, b, __ldg(P.beta + (int64_t)img * P.gstride + film * 256 + col)) : b;
+        };
+        float pre = t_begin < t_end ? film_const(0, (t_begin * CH_TILE_M) / P.rows_per_image) : 0.f;
         for (uint32_t t = t_begin; t < t_end; t++) {
             const uint64_t row = (uint64_t)t * CH_TILE_M + r;
             const bool valid = row < P.M_total;
@@ -394,22 +404,17 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
             uint32_t hrow = 0;
             for (uint32_t i = 0; i < nL; i++, n++) {
                 // layer description -> registers (constant-bank reads with a dynamic index are slow inside the chunk loop)
-                const uint32_t L_act = P.layer[i].act, L_nh = P.layer[i].nh, L_to_act = P.layer[i].to_act, L_film = P.layer[i].film;
+                const uint32_t L_act = P.layer[i].act, L_nh = P.layer[i].nh, L_to_act = P.layer[i].to_act;
                 float* const o32 = P.layer[i].out_f32;
                 const bool do_cos = COS && P.layer[i].store_cos;
                 const int64_t ld32 = P.layer[i].ld_out_f32;
                 const uint32_t acc = n & 1, use = n >> 1, tb = n & 1;
                 const uint32_t gam_s = smem_u32(&S.gam[tb][0]), cst_s = smem_u32(&S.cst[tb][0]);
-                {   // per-layer FiLM constants (overlaps the MMAs of this layer): threads 0..255 gamma, 256..511 gamma*bias + beta
-                    const uint32_t col = etid & 255;
-                    float gm = 1.f;
-                    if (L_act) gm = __ldg(P.gamma + (int64_t)img * P.gstride + L_film * 256 + col);
-                    if (etid < 256) sts32(gam_s + col * 4, gm);
-                    else {
-                        const float b = __ldg(P.layer[i].bias + col);
-                        sts32(cst_s + col * 4, L_act ? fmaf(gm, b, __ldg(P.beta + (int64_t)img * P.gstride + L_film * 256 + col)) : b);
-                    }
+                {   // publish this layer's FiLM constants (prefetched), then fetch the next layer's
+                    sts32((etid < 256 ? gam_s : cst_s) + (etid & 255) * 4, pre);
                     named_bar_sync(1, CH_EPI_THREADS);
+                    if (i + 1 < nL) pre = film_const(i + 1, img);
+                    else if (t + 1 < t_end) pre = film_const(0, ((t + 1) * CH_TILE_M) / P.rows_per_image);
                 }
                 const uint32_t heads_s = smem_u32(&S.heads[hrow][0]);
                 float hacc[3] = {0.f, 0.f, 0.f};
