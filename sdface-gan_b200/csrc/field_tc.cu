@@ -257,16 +257,16 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
     static const bool dbg_on = getenv("SDFG_CHAIN_DBG") != nullptr;     // debugging aid: event log of CTA 0 to stderr
     if (dbg_on) {
         static unsigned long long* dbuf = nullptr;
-        if (!dbuf) cudaMalloc(&dbuf, 4 * 2048 * 8);
-        cudaMemsetAsync(dbuf, 0, 4 * 2048 * 8, st);
+        if (!dbuf) cudaMalloc(&dbuf, 20 * 2048 * 8);
+        cudaMemsetAsync(dbuf, 0, 20 * 2048 * 8, st);
         P.dbg = dbuf;
         kern<<<grid, tc::CH_THREADS, smem, st>>>(maps, stores, P);
         cudaStreamSynchronize(st);
-        static unsigned long long host[4 * 2048];
+        static unsigned long long host[20 * 2048];
         cudaMemcpy(host, dbuf, sizeof(host), cudaMemcpyDeviceToHost);
         static int dumps = 0;
         if (dumps++ == 2)
-            for (int role = 0; role < 4; role++)
+            for (int role = 0; role < 20; role++)
                 for (int k = 0; k < 1024 && host[role * 2048 + 2 * k + 1]; k++)
                     fprintf(stderr, "CHDBG %d %llu %llu\n", role, host[role * 2048 + 2 * k], host[role * 2048 + 2 * k + 1]);
         return check_launch("tc_chain_fwd_kernel<gemm>");

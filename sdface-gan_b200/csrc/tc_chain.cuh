@@ -487,6 +487,7 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                         }
                         if (do_cos) ncos++;
                         if (threadIdx.x == 0) CH_DBG(1, 500 + i * 16 + c);
+                        if (lane == 0 && warp != 0) CH_DBG(4 + warp, 500 + i * 16 + c);
                     }
                     if (o32 && valid) {
                         float4* dst = reinterpret_cast<float4*>(o32 + row * ld32 + col);

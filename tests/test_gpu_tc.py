@@ -199,3 +199,30 @@ def test_tc_kernel_variants_agree():
         for k in ref:
             a, b = np.asarray(ref[k], np.float64), np.asarray(got[k], np.float64)
             assert np.linalg.norm(a - b) <= 1e-2 * max(np.linalg.norm(a), 1e-12), (name, k, a, b)
+
+
+@pytest.mark.parametrize("B,R,S", [(1, 8, 24), (3, 16, 24), (2, 32, 12), (5, 8, 48)])
+def test_tc_training_step_small_and_ragged_shapes(B, R, S):
+    """Fused chains at shapes where the persistent grids are ragged (fewer tile pairs than SM pairs, odd image counts, one tile
+    pair per image boundary ...): outputs and every parameter gradient against the fp32 CUDA path, 2e-2 relative."""
+    sg = _sg()
+    res = {}
+    for prec in ("fp32", "tc16"):
+        torch.manual_seed(7)
+        mo, ro = sg.default_options("ngp", renderer_res=R, n_samples=S, perturb=0., return_sdf=True)
+        g = sg.Generator(mo, ro, full_pipeline=False).to(DEV)
+        g.renderer.network.encoder.embeddings.data.uniform_(-0.5, 0.5)
+        g.renderer.network.precision = prec
+        cam, focal, near, far, _ = sg.generate_camera_params(R, DEV, batch=B)
+        z = torch.randn(B, 256, device=DEV)
+        _, thumb, sdf, eik = g([z], cam, focal, near, far, return_sdf=True, return_eikonal=True)
+        w = torch.linspace(-1, 1, thumb.numel(), device=DEV).view_as(thumb)
+        loss = (thumb * w).sum() + 10 * sdf.square().mean() + ((eik.norm(dim=-1) - 1) ** 2).mean()
+        loss.backward()
+        res[prec] = (thumb.detach(), sdf.detach(), eik.detach(), {n: p.grad.detach().clone() for n, p in g.named_parameters() if p.grad is not None})
+    t0, s0, e0, g0 = res["fp32"]
+    t1, s1, e1, g1 = res["tc16"]
+    assert H.max_abs(t1, t0) < 2e-2 and H.rel_err(s1, s0) < 2e-2 and H.rel_err(e1, e0) < 2e-2
+    assert set(g0) == set(g1)
+    worst = max((H.rel_err(g1[n], g0[n]), n) for n in g0 if g0[n].abs().max() > 0)
+    assert worst[0] < 2e-2, worst
