@@ -238,8 +238,6 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
     }
     P.n_layers = nl;
     for (uint32_t i = 0; i < nl; i++) P.layer[i].to_act = (i + 1 < nl || P.layer[i].store) ? 1 : 0;
-    { static const int ef = []() { const char* e = getenv("SDFG_EXP"); return e ? atoi(e) : 0; }(); P.exp_flags = (uint32_t)ef;
-      if (ef & 2) for (uint32_t i = 0; i < nl; i++) P.layer[i].store_cos = 0; }      // 2 = no cos tile at all
     P.n_tiles = (uint32_t)ceil_div<uint64_t>(N, tc::CH_TILE_M);
     const uint32_t ctas = std::min<uint32_t>((uint32_t)sm_count(), P.n_tiles);
     P.tiles_per_cta = ceil_div<uint32_t>(P.n_tiles, ctas);

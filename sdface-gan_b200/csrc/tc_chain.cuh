@@ -79,8 +79,6 @@ struct ChainParams {
     uint16_t* v16;              // SAVE: view part expanded per sample, kp_v columns (NULL ok)
     int64_t ld_v16;
     unsigned long long* dbg;    // debugging: per-role (tag, clock) event log of CTA 0, 4 x 2048 entries (NULL = off)
-    uint32_t exp_flags;         // timing experiments only (wrong results): 1 = no MUFU for the cos tile
-    uint32_t pad3;
     ChainLayer layer[CH_MAX_LAYERS];
 };
 
@@ -358,7 +356,7 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                         const uint32_t slot = ncos % CH_COS_SLOTS, use = ncos / CH_COS_SLOTS;
                         if (cs) {
                             mbar_wait(&S.cos_ready[slot], use & 1);
-                            if (!(P.exp_flags & 4)) tma_store_2d(&stores.c[i], smCOS + slot * CH_CHUNK_BYTES, (int32_t)(c * 64), (int32_t)(t * CH_TILE_M));
+                            tma_store_2d(&stores.c[i], smCOS + slot * CH_CHUNK_BYTES, (int32_t)(c * 64), (int32_t)(t * CH_TILE_M));
                         }
                         tma_store_commit();
                         if (to_act) {
@@ -445,7 +443,7 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                         if (do_cos) {                                    // derivative for the backward chain (no recompute there)
                             float cs[16];
 #pragma unroll
-                            for (int k = 0; k < 16; k++) cs[k] = (P.exp_flags & 1) ? v[k] * 0.01f : __cosf(v[k]);
+                            for (int k = 0; k < 16; k++) cs[k] = __cosf(v[k]);
                             c0 = make_uint4(pack_f16(cs[0], cs[1]), pack_f16(cs[2], cs[3]), pack_f16(cs[4], cs[5]), pack_f16(cs[6], cs[7]));
                             c1 = make_uint4(pack_f16(cs[8], cs[9]), pack_f16(cs[10], cs[11]), pack_f16(cs[12], cs[13]), pack_f16(cs[14], cs[15]));
                         }
