@@ -86,7 +86,7 @@ struct TcLayout {
     uint64_t N;
     uint64_t off_w[SDFG_MAX_FILM + 1];           // fp16 weights: [0] = input_linear, [1 + l] = FiLM layer l
     uint64_t off_x0, off_a[SDFG_MAX_FILM + 1], off_hv, total;
-    uint64_t off_c[SDFG_MAX_FILM + 1];           // save: cos(gamma u + c) of FiLM layer l, fp16 [N, W] (written by the forward chain)
+    uint64_t off_c[SDFG_MAX_FILM + 1];           // save: sign(cos(gamma u + c)) bit masks of FiLM layer l, 4 KB per 128-sample tile (forward chain)
     int save;
 };
 
@@ -113,7 +113,7 @@ static TcLayout tc_layout(const sdfg_field_params* p, uint64_t N, int save) {
         L.off_a[l] = take(N * L.W * 2);
     }
     L.off_hv = take(save ? N * L.W * 2 : 0);
-    for (uint32_t l = 0; l < L.n_layers; l++) L.off_c[l] = take(save ? N * L.W * 2 : 0);
+    for (uint32_t l = 0; l < L.n_layers; l++) L.off_c[l] = take(save ? ceil_div<uint64_t>(N, tc::CH_TILE_M) * tc::CH_SGN_TILE_BYTES : 0);
     L.total = off;
     return L;
 }
@@ -182,10 +182,10 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
     auto add_main_map = [&](uint32_t wi, uint32_t ldw) -> int {          // fp16 weights [W, ldw]: every 64-column chunk incl. a partial tail (OOB = 0)
         return make_tensor_map_16(&maps.m[nm], Wb(wi), W, ldw, ldw, 256, 64, tc::FMT_F16);
     };
-    // SAVE: cos(gamma u + c) of FiLM layer l, TMA-stored chunk by chunk for the backward chain
+    // SAVE: sign(cos(gamma u + c)) masks of FiLM layer l for the backward chain
     auto cos_to = [&](uint32_t layer, uint32_t l) -> int {
-        P.layer[layer].store_cos = 1;
-        return make_tensor_map_16(&stores.c[layer], (h16*)(ws + L.off_c[l]), N, W, W, tc::CH_TILE_M, 64, tc::FMT_F16);
+        P.layer[layer].sgn = ws + L.off_c[l];
+        return SDFG_OK;
     };
     // SAVE: the layer's output tile is TMA-stored chunk by chunk to dst [N, 256] (pitch ld)
     auto store_to = [&](uint32_t layer, h16* dst, uint64_t ld) -> int {
@@ -583,7 +583,11 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         auto add_layer = [&](uint32_t l) -> int {                      // FiLM layer l (nf = views) becomes chain layer nl
             tc::B2Layer& Y = P.layer[nl];
             Y.do_D = l == nf ? 1u : ((l > 0 || need_dh0) ? 1u : 0u);
-            if (int e = make_tensor_map_16(&maps->c[nl], (const h16*)(ws + L.off_c[l]), N, W, W, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
+            // the layer's OUTPUT sin(gamma u + c) as saved for the next layer / the rgb head, and the sign masks of its cos
+            const h16* sin_l = l == nf ? (const h16*)(ws + L.off_hv) : A(l + 1);
+            const uint64_t ld_sin = (l == nf || l + 1 != nf) ? W : L.Kp_v;
+            if (int e = make_tensor_map_16(&maps->c[nl], sin_l, N, W, ld_sin, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
+            Y.sgn = ws + L.off_c[l];
             if (Y.do_D) {
                 h16* wgt = (h16*)(sc + SC.off_wgt[l]);
                 wgt_kernel<<<dim3(W, B), 256, 0, st>>>(p->film_w[l], layer_Kx(l), p->gamma + (size_t)l * W, gstride, wgt, W, B);

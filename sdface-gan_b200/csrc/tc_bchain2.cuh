@@ -26,6 +26,7 @@ struct B2Layer {
     uint32_t d_rank, d_vec0;    // epilogue of D_l: + gs * d_rank_s[row] * vecs[d_vec0][col]   (d_sdf w_sigma behind the view layer)
     uint32_t pad;
     const float* d_rank_s;
+    const uint8_t* sgn;         // sign(cos) masks of this layer, [tiles][CH_SGN_TILE_BYTES] (tc_chain.cuh)
 };
 
 struct B2ChainParams {
@@ -43,7 +44,7 @@ struct B2ChainParams {
 };
 
 struct alignas(64) B2ChainMaps {
-    CUtensorMap c[BC_MAX_LAYERS];       // cos tile of layer l          [M, 256]      box 128 x 64
+    CUtensorMap c[BC_MAX_LAYERS];       // sin tile of layer l (its saved output)  [M, 256]  box 128 x 64
     CUtensorMap wgt[BC_MAX_LAYERS];     // (gamma o W_l)^T per image    [B*256, 256]  box (256/CG) x 64
     CUtensorMap dz[BC_MAX_LAYERS];      // du store                     [M, 256]      box 128 x 64
     CUtensorMap wgt_in;                 // W_in^T                       [in_dim, 256] box (in_dim/CG) x 64
@@ -61,7 +62,7 @@ struct B2ChainSmem {
 };
 
 __host__ __device__ inline uint32_t bchain2_smem_bytes(int cg) {
-    return 1024 + 2 * BC_G_BYTES + bc_w_stages(cg) * bc_w_bytes(cg) + (uint32_t)sizeof(B2ChainSmem);
+    return 1024 + 2 * BC_G_BYTES + bc_w_stages(cg) * bc_w_bytes(cg) + 2 * CH_SGN_TILE_BYTES + (uint32_t)sizeof(B2ChainSmem);
 }
 
 template <bool STORE, int CG>
@@ -75,7 +76,8 @@ tc_chain_bwd2_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
     uint8_t* smG = smem;                                               // gradient tile = A operand of the D GEMMs
     uint8_t* smC = smG + BC_G_BYTES;                                   // cos tile of the layer being entered
     uint8_t* smW = smC + BC_G_BYTES;
-    B2ChainSmem& S = *reinterpret_cast<B2ChainSmem*>(smW + NW * W_BYTES);
+    uint8_t* smSGN = smW + NW * W_BYTES;                               // two sign-mask tiles (double-buffered by layer)
+    B2ChainSmem& S = *reinterpret_cast<B2ChainSmem*>(smSGN + 2 * CH_SGN_TILE_BYTES);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
@@ -143,8 +145,10 @@ tc_chain_bwd2_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
                 for (uint32_t i = 0; i < nL; i++, cgen++)
                     for (uint32_t kc = 0; kc < 4; kc++) {
                         mbar_wait(&S.c_empty[kc], (cgen & 1) ^ 1);
-                        mbar_arrive_expect_tx(&S.c_full[kc], CH_CHUNK_BYTES);
+                        mbar_arrive_expect_tx(&S.c_full[kc], CH_CHUNK_BYTES + (kc == 0 ? CH_SGN_TILE_BYTES : 0u));
                         tma_load_2d(smC + kc * CH_CHUNK_BYTES, &maps.c[i], &S.c_full[kc], (int32_t)(kc * 64), row0);
+                        // the layer's sign masks arrive with chunk 0 (double-buffered: the previous layer's may still be in use)
+                        if (kc == 0) bulk_load(smSGN + (cgen & 1) * CH_SGN_TILE_BYTES, P.layer[i].sgn + (size_t)(u * CG + rank) * CH_SGN_TILE_BYTES, CH_SGN_TILE_BYTES, &S.c_full[0]);
                     }
             }
         }
@@ -228,9 +232,21 @@ tc_chain_bwd2_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
             if (mul_cos) {
                 mbar_wait(&S.c_full[c], cgen & 1);
                 const uint4 a = lds128u(c_row + c * CH_CHUNK_BYTES + u0), b = lds128u(c_row + c * CH_CHUNK_BYTES + u1);
+                uint32_t msk;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(msk) : "r"(smem_u32(smSGN) + (((cgen & 1) * 16 + c * 4 + sb) * 128 + r) * 2));
                 const uint32_t cw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                // cos = (-1)^bit * sqrt(1 - sin^2): the saved activation is the sine of the same argument
 #pragma unroll
-                for (int k = 0; k < 8; k++) { const float2 f = unpack_f16(cw[k]); w[2 * k] = v[2 * k] * f.x; w[2 * k + 1] = v[2 * k + 1] * f.y; }
+                for (int k = 0; k < 8; k++) {
+                    const float2 f = unpack_f16(cw[k]);
+                    float c0, c1;
+                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(c0) : "f"(fmaxf(fmaf(-f.x, f.x, 1.f), 0.f)));
+                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(c1) : "f"(fmaxf(fmaf(-f.y, f.y, 1.f), 0.f)));
+                    c0 = __uint_as_float(__float_as_uint(c0) ^ ((msk >> (2 * k)) << 31));
+                    c1 = __uint_as_float(__float_as_uint(c1) ^ ((msk >> (2 * k + 1)) << 31));
+                    w[2 * k] = v[2 * k] * c0;
+                    w[2 * k + 1] = v[2 * k + 1] * c1;
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.c_empty[c]);              // this warp is done with the cos chunk
             } else {

@@ -31,7 +31,8 @@ namespace tc {
 constexpr uint32_t CH_TILE_M = 128;
 constexpr uint32_t CH_CHUNK_BYTES = CH_TILE_M * 128;        // [128 samples x 64 fp16] = 16 KB
 constexpr uint32_t CH_ACT_BYTES = 4 * CH_CHUNK_BYTES;       // K = 256
-constexpr uint32_t CH_COS_SLOTS = 2;                        // SAVE: staging chunks of the cos tile (TMA-stored for the backward chain)
+constexpr uint32_t CH_SGN_TILE_BYTES = 4096;                // sign(cos) bits of one tile and layer: [4 chunks][4 sub-blocks][128 rows] x 16 bit
+constexpr uint32_t CH_AUX_BYTES = 32768;                    // inference: resident small weights; training: 2 sign-mask tiles
 constexpr uint32_t CH_W_STAGE_BYTES = 256 * 128;            // one streamed weight chunk
 constexpr uint32_t CH_W_STAGES = 3;
 constexpr uint32_t CH_MAX_LAYERS = SDFG_MAX_FILM + 1;
@@ -58,8 +59,8 @@ struct ChainLayer {
     float* out_head;
     float* out_f32;             // optional fp32 copy of the output in HBM
     int64_t ld_out_f32;
-    uint32_t store_cos;         // SAVE: TMA-store cos(gamma u + c) (fp16 [M, 256], the derivative the backward chain multiplies with) via stores.c[layer]
-    uint32_t pad2;
+    uint8_t* sgn;               // COS: sign(cos(gamma u + c)) bit masks, [tiles][CH_SGN_TILE_BYTES] -- with |cos| = sqrt(1 - sin^2) from the saved
+                                // activation this is the derivative the backward chain multiplies with (NULL = not wanted)
 };
 
 struct ChainParams {
@@ -83,14 +84,13 @@ struct ChainParams {
 };
 
 struct alignas(64) ChainMaps { CUtensorMap m[CH_MAX_MAPS + 1]; };      // K = 256 layers (+ layer 0's small weight matrix)
-struct alignas(64) ChainStoreMaps { CUtensorMap m[CH_MAX_LAYERS]; CUtensorMap c[CH_MAX_LAYERS]; };
+struct alignas(64) ChainStoreMaps { CUtensorMap m[CH_MAX_LAYERS]; };
 
 struct ChainSmem {
     uint64_t w_full[CH_W_STAGES], w_empty[CH_W_STAGES];
     uint64_t act_ready[4], fin_ready[4], st_done[4];   // fin_ready: chunks of the LAST layer's output (consumed by the storer only)
     uint64_t acc_full[2], acc_empty[2];
     uint64_t x_full, x_free, v_full, v_free;
-    uint64_t cos_ready[CH_COS_SLOTS], cos_done[CH_COS_SLOTS];
     uint32_t tmem_base;
     uint32_t pad[3];
     alignas(16) float gam[2][256];      // double-buffered per-layer FiLM constants: gamma, gamma*bias + beta
@@ -100,7 +100,7 @@ struct ChainSmem {
 };
 
 __host__ __device__ inline uint32_t chain_smem_bytes() {
-    return 1024 + CH_ACT_BYTES + CH_CHUNK_BYTES + CH_W_STAGES * CH_W_STAGE_BYTES + CH_COS_SLOTS * CH_CHUNK_BYTES + (uint32_t)sizeof(ChainSmem);
+    return 1024 + CH_ACT_BYTES + CH_CHUNK_BYTES + CH_W_STAGES * CH_W_STAGE_BYTES + CH_AUX_BYTES + (uint32_t)sizeof(ChainSmem);
 }
 
 // byte offset of 16-byte unit u of row r inside a 128B-swizzled tile (what TMA SWIZZLE_128B / the UMMA descriptor expect)
@@ -140,8 +140,9 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8], uint32_t fmt) {
     } while (0)
 
 // SAVE: a storer thread TMA-stores finished activation chunks (training: every layer; inference: the fp16 features).
-// COS (training only): FiLM layers also produce cos(gamma u + c) tiles for the backward chain; the 32 KB that hold the resident
-// small weights in inference become the cos staging slots and the small weights are streamed through the ring instead.
+// COS (training only): FiLM layers also record sign(cos(gamma u + c)) as one bit per element (4 KB per tile and layer, bulk-stored
+// with the activation tile); the backward chain rebuilds cos = +-sqrt(1 - sin^2) from the saved activation.  The aux region
+// holds the two mask tiles and the small weights are streamed through the ring instead of being resident.
 template <bool SAVE, bool COS>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant__ ChainStoreMaps stores, const __grid_constant__ ChainParams P) {
@@ -150,10 +151,11 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
     uint8_t* smACT = smem;
     uint8_t* smSMALL = smACT + CH_ACT_BYTES;
     uint8_t* smRING = smSMALL + CH_CHUNK_BYTES;
-    uint8_t* smCOS = smRING + CH_W_STAGES * CH_W_STAGE_BYTES;   // SAVE: cos staging slots; inference: the same 32 KB hold the RESIDENT
-    uint8_t* smWSMALL = smCOS;                                  // small weights (layer 0 + view columns), which SAVE streams instead
+    uint8_t* smAUX = smRING + CH_W_STAGES * CH_W_STAGE_BYTES;   // inference: the RESIDENT small weights (layer 0 + view columns);
+    uint8_t* smWSMALL = smAUX;                                  // training (COS): two sign-mask tiles, the small weights are streamed
+    uint8_t* smSGN = smAUX;
     constexpr bool RESIDENT = !COS;
-    ChainSmem& S = *reinterpret_cast<ChainSmem*>(smCOS + CH_COS_SLOTS * CH_CHUNK_BYTES);
+    ChainSmem& S = *reinterpret_cast<ChainSmem*>(smAUX + CH_AUX_BYTES);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t t_begin = blockIdx.x * P.tiles_per_cta;
@@ -166,7 +168,6 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
         for (uint32_t i = 0; i < 4; i++) { mbar_init(&S.act_ready[i], CH_EPI_WARPS); mbar_init(&S.fin_ready[i], CH_EPI_WARPS); mbar_init(&S.st_done[i], 1); }
         for (uint32_t i = 0; i < 2; i++) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], CH_EPI_WARPS); }
         mbar_init(&S.x_full, 1); mbar_init(&S.x_free, 1); mbar_init(&S.v_full, 1); mbar_init(&S.v_free, 1);
-        for (uint32_t i = 0; i < CH_COS_SLOTS; i++) { mbar_init(&S.cos_ready[i], CH_EPI_WARPS); mbar_init(&S.cos_done[i], 1); }
         fence_barrier_init();
     }
     if (warp == CH_WARP_TMA && lane == 0)
@@ -174,7 +175,6 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
             if (P.layer[i].has_main) tma_prefetch_desc(&maps.m[P.layer[i].tm]);
             if (P.layer[i].small_nk) tma_prefetch_desc(&maps.m[P.layer[i].tm_small]);
             if (SAVE && P.layer[i].store) tma_prefetch_desc(&stores.m[i]);
-            if (COS && P.layer[i].store_cos) tma_prefetch_desc(&stores.c[i]);
         }
     if (warp == CH_WARP_MMA) tmem_alloc(&S.tmem_base, 512);
     // inference: resident small weights, K-steps [0, x_nk) = layer 0, [x_nk, x_nk + v_nk) = view columns of the last layer
@@ -342,35 +342,25 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
     } else if (warp == CH_WARP_STORE) {
         // ===================================================== storer (SAVE): finished ACT chunks -> saved activations in HBM
         if (SAVE && lane == 0) {
-            uint32_t actgen = 0, fingen = 0, ncos = 0;
-            // Per chunk: the cos store is one bulk group, the activation store the next.  After both are committed we wait until at
-            // most ONE group is still reading shared memory: the cos slot (older group) is then free again -- it is needed two
-            // chunks later and must not wait for the next chunk's stores -- while the activation chunk (only overwritten one layer
-            // later) is released one iteration behind.
+            uint32_t actgen = 0, fingen = 0, nn = 0;
+            // One bulk group per chunk (the sign-mask tile of a layer rides with its last chunk); one group may still be reading
+            // shared memory while the next chunk's store is issued -- a chunk is released for overwriting one iteration behind.
             uint64_t* pend = nullptr;
             for (uint32_t t = t_begin; t < t_end; t++)
-                for (uint32_t i = 0; i < nL; i++) {
-                    const bool st = P.layer[i].store != 0, fin = i + 1 == nL, to_act = P.layer[i].to_act != 0, cs = COS && P.layer[i].store_cos != 0;
-                    if (!to_act && !cs) continue;
+                for (uint32_t i = 0; i < nL; i++, nn++) {
+                    const bool st = P.layer[i].store != 0, fin = i + 1 == nL;
+                    if (!P.layer[i].to_act) continue;
                     for (uint32_t c = 0; c < 4; c++) {
-                        const uint32_t slot = ncos % CH_COS_SLOTS, use = ncos / CH_COS_SLOTS;
-                        if (cs) {
-                            mbar_wait(&S.cos_ready[slot], use & 1);
-                            tma_store_2d(&stores.c[i], smCOS + slot * CH_CHUNK_BYTES, (int32_t)(c * 64), (int32_t)(t * CH_TILE_M));
-                        }
+                        if (fin) mbar_wait(&S.fin_ready[c], fingen & 1);
+                        else mbar_wait(&S.act_ready[c], actgen & 1);
+                        if (st) tma_store_2d(&stores.m[i], smACT + c * CH_CHUNK_BYTES, (int32_t)(c * 64), (int32_t)(t * CH_TILE_M));
+                        if (COS && c == 3 && P.layer[i].sgn)              // every warp has written its bits of all 4 chunks
+                            bulk_store(P.layer[i].sgn + (size_t)t * CH_SGN_TILE_BYTES, smSGN + (nn & 1) * CH_SGN_TILE_BYTES, CH_SGN_TILE_BYTES);
                         tma_store_commit();
-                        if (to_act) {
-                            if (fin) mbar_wait(&S.fin_ready[c], fingen & 1);
-                            else mbar_wait(&S.act_ready[c], actgen & 1);
-                            if (st) tma_store_2d(&stores.m[i], smACT + c * CH_CHUNK_BYTES, (int32_t)(c * 64), (int32_t)(t * CH_TILE_M));
-                        }
-                        tma_store_commit();
-                        tma_store_wait_read_pending<1>();
-                        if (cs) { mbar_arrive(&S.cos_done[slot]); ncos++; }
-                        if (pend) mbar_arrive(pend);
-                        pend = to_act ? &S.st_done[c] : nullptr;
+                        if (pend) { tma_store_wait_read_pending<1>(); mbar_arrive(pend); }
+                        pend = &S.st_done[c];
                     }
-                    if (to_act) { if (fin) fingen++; else actgen++; }
+                    if (fin) fingen++; else actgen++;
                 }
             tma_store_wait_read();
             if (pend) mbar_arrive(pend);
@@ -384,7 +374,7 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
         const uint32_t r = q * 32 + lane;                              // row of the tile = TMEM lane
         const uint32_t act_row = smem_u32(smACT) + r * 128;
         const uint32_t u0 = ((2 * sb) ^ (r & 7)) << 4, u1 = ((2 * sb + 1) ^ (r & 7)) << 4;
-        uint32_t n = 0, stgen = 0, ncos = 0;
+        uint32_t n = 0, stgen = 0;
         // FiLM constant of (layer, image) this thread publishes: threads 0..255 gamma (1 for a linear layer), 256..511 gamma*bias + beta.
         // It is fetched one layer AHEAD so that its L2 latency hides behind the chunk loop instead of sitting between two layers.
         auto film_const = [&](uint32_t i, uint32_t img) -> float {
@@ -404,7 +394,7 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                 // layer description -> registers (constant-bank reads with a dynamic index are slow inside the chunk loop)
                 const uint32_t L_act = P.layer[i].act, L_nh = P.layer[i].nh, L_to_act = P.layer[i].to_act;
                 float* const o32 = P.layer[i].out_f32;
-                const bool do_cos = COS && P.layer[i].store_cos;
+                const bool do_sgn = COS && P.layer[i].sgn != nullptr;
                 const int64_t ld32 = P.layer[i].ld_out_f32;
                 const uint32_t acc = n & 1, use = n >> 1, tb = n & 1;
                 const uint32_t gam_s = smem_u32(&S.gam[tb][0]), cst_s = smem_u32(&S.cst[tb][0]);
@@ -438,14 +428,15 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                         v[k + 2] = fmaf(__uint_as_float(raw[c & 1][k + 2]), g4.z, c4.z);
                         v[k + 3] = fmaf(__uint_as_float(raw[c & 1][k + 3]), g4.w, c4.w);
                     }
-                    uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
                     if (L_act) {
-                        if (do_cos) {                                    // derivative for the backward chain (no recompute there)
-                            float cs[16];
+                        if (do_sgn) {
+                            // sign of cos(u) = parity of rint(u / pi): one fma against the 1.5 * 2^23 magic constant puts that integer
+                            // into the low mantissa bits.  Together with |cos| = sqrt(1 - sin^2) from the saved activation this is the
+                            // whole derivative -- 16 bits per thread and chunk instead of a second fp16 tile and a second SFU op.
+                            uint32_t m = 0;
 #pragma unroll
-                            for (int k = 0; k < 16; k++) cs[k] = __cosf(v[k]);
-                            c0 = make_uint4(pack_f16(cs[0], cs[1]), pack_f16(cs[2], cs[3]), pack_f16(cs[4], cs[5]), pack_f16(cs[6], cs[7]));
-                            c1 = make_uint4(pack_f16(cs[8], cs[9]), pack_f16(cs[10], cs[11]), pack_f16(cs[12], cs[13]), pack_f16(cs[14], cs[15]));
+                            for (int k = 0; k < 16; k++) m |= (__float_as_uint(fmaf(v[k], 0.31830988618379067f, 12582912.f)) & 1u) << k;
+                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(smem_u32(smSGN) + (((n & 1) * 16 + c * 4 + sb) * 128 + r) * 2), "h"((uint16_t)m) : "memory");
                         }
 #pragma unroll
                         for (int k = 0; k < 16; k++) v[k] = __sinf(v[k]);
@@ -468,22 +459,11 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                         const uint4 h1 = make_uint4(pack_f16(v[8], v[9]), pack_f16(v[10], v[11]), pack_f16(v[12], v[13]), pack_f16(v[14], v[15]));
                         if (SAVE) mbar_wait(&S.st_done[c], (stgen & 1) ^ 1);   // the previous contents of the chunk have been stored
                         const uint32_t chunk = act_row + c * CH_CHUNK_BYTES;
-                        const uint32_t slot = ncos % CH_COS_SLOTS;
-                        if (do_cos) {                                    // cos chunk -> staging slot (one fence for both tiles)
-                            mbar_wait(&S.cos_done[slot], ((ncos / CH_COS_SLOTS) & 1) ^ 1);   // the slot's previous store has read it
-                            const uint32_t dstc = smem_u32(smCOS) + slot * CH_CHUNK_BYTES + r * 128;
-                            sts128(dstc + u0, c0);
-                            sts128(dstc + u1, c1);
-                        }
                         sts128(chunk + u0, h0);
                         sts128(chunk + u1, h1);
                         fence_proxy_async();
                         __syncwarp();
-                        if (lane == 0) {
-                            if (do_cos) mbar_arrive(&S.cos_ready[slot]);
-                            mbar_arrive(i + 1 == nL ? &S.fin_ready[c] : &S.act_ready[c]);
-                        }
-                        if (do_cos) ncos++;
+                        if (lane == 0) mbar_arrive(i + 1 == nL ? &S.fin_ready[c] : &S.act_ready[c]);
                         if (threadIdx.x == 0) CH_DBG(1, 500 + i * 16 + c);
                         if (lane == 0 && warp != 0) CH_DBG(4 + warp, 500 + i * 16 + c);
                     }
