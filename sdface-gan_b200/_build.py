@@ -20,6 +20,7 @@ LIB = os.path.join(LIBDIR, "libsdfg.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+FLAGS += os.environ.get("SDFG_BUILD_DEFS", "").split()      # e.g. -DSDFG_CHAIN_DEBUG for the chain kernels' event log (use with --force)
 
 
 def _sources():

@@ -228,33 +228,34 @@ tc_chain_bwd2_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
         // write one 16-column piece of a G event: v (fp32) [* cos tile chunk] -> fp16 (saturating) -> G, publish
         auto emit = [&](const float (&v)[16], uint32_t c, bool mul_cos) {
             const uint32_t chunk = g_row + c * CH_CHUNK_BYTES;
-            float w[16];
+            uint32_t hw[8];
             if (mul_cos) {
                 mbar_wait(&S.c_full[c], cgen & 1);
                 const uint4 a = lds128u(c_row + c * CH_CHUNK_BYTES + u0), b = lds128u(c_row + c * CH_CHUNK_BYTES + u1);
                 uint32_t msk;
                 asm volatile("ld.shared.u16 %0, [%1];" : "=r"(msk) : "r"(smem_u32(smSGN) + (((cgen & 1) * 16 + c * 4 + sb) * 128 + r) * 2));
                 const uint32_t cw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                // cos = (-1)^bit * sqrt(1 - sin^2): the saved activation is the sine of the same argument
+                // cos = (-1)^bit * sqrt(1 - sin^2): the saved activation is the sine of the same argument.  1 - s^2 as one packed-half fma
+                // (s is an fp16 value in [-1, 1], so the result is >= 0 and its rounding is below the error s already carries); the
+                // sign flips are applied to the packed fp16 products: mask bit j = element 2j, bit 8 + j = element 2j + 1.
+                const uint32_t m2 = __byte_perm(msk, 0, 0x4140);       // bits 0..7 stay, bits 8..15 -> 16..23
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    const float2 f = unpack_f16(cw[k]);
+                    const __half2 s2 = *reinterpret_cast<const __half2*>(&cw[k]);
+                    const float2 x = __half22float2(__hfma2(__hneg2(s2), s2, __float2half2_rn(1.f)));
                     float c0, c1;
-                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(c0) : "f"(fmaxf(fmaf(-f.x, f.x, 1.f), 0.f)));
-                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(c1) : "f"(fmaxf(fmaf(-f.y, f.y, 1.f), 0.f)));
-                    c0 = __uint_as_float(__float_as_uint(c0) ^ ((msk >> (2 * k)) << 31));
-                    c1 = __uint_as_float(__float_as_uint(c1) ^ ((msk >> (2 * k + 1)) << 31));
-                    w[2 * k] = v[2 * k] * c0;
-                    w[2 * k + 1] = v[2 * k + 1] * c1;
+                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(c0) : "f"(x.x));
+                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(c1) : "f"(x.y));
+                    hw[k] = pack_f16_sat(v[2 * k] * c0, v[2 * k + 1] * c1) ^ ((m2 << (15 - k)) & 0x80008000u);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.c_empty[c]);              // this warp is done with the cos chunk
             } else {
 #pragma unroll
-                for (int k = 0; k < 16; k++) w[k] = v[k];
+                for (int k = 0; k < 8; k++) hw[k] = pack_f16_sat(v[2 * k], v[2 * k + 1]);
             }
-            const uint4 h0 = make_uint4(pack_f16_sat(w[0], w[1]), pack_f16_sat(w[2], w[3]), pack_f16_sat(w[4], w[5]), pack_f16_sat(w[6], w[7]));
-            const uint4 h1 = make_uint4(pack_f16_sat(w[8], w[9]), pack_f16_sat(w[10], w[11]), pack_f16_sat(w[12], w[13]), pack_f16_sat(w[14], w[15]));
+            const uint4 h0 = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            const uint4 h1 = make_uint4(hw[4], hw[5], hw[6], hw[7]);
             if (STORE && gev > 0) mbar_wait(&S.st_done[c], (gev - 1) & 1);   // the store of the previous event has read the chunk
             sts128(chunk + u0, h0);
             sts128(chunk + u1, h1);

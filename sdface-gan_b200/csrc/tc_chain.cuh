@@ -96,7 +96,9 @@ struct ChainSmem {
     alignas(16) float gam[2][256];      // double-buffered per-layer FiLM constants: gamma, gamma*bias + beta
     float cst[2][256];
     float heads[4][256];                // row 0: first head layer (sdf), rows 1..3: second head layer (rgb)
-    float hx[3][CH_TILE_M][4];          // head partial sums of column sub-blocks 1..3
+    float hx[3][CH_TILE_M][3];          // head partial sums of column sub-blocks 1..3
+    float stg_g[CH_EPI_THREADS];        // cp.async staging of the NEXT layer's raw FiLM inputs: gamma (one slot per epilogue thread),
+    float stg_b[256], stg_be[256];      // bias and beta (threads 256..511)
 };
 
 __host__ __device__ inline uint32_t chain_smem_bytes() {
@@ -130,6 +132,8 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8], uint32_t fmt) {
     return make_uint4(pack16(v[0], v[1], fmt), pack16(v[2], v[3], fmt), pack16(v[4], v[5], fmt), pack16(v[6], v[7], fmt));
 }
 
+// event log for scripts/gpu_dbg.sh; costs instructions in every chunk of the epilogue, so only with -DSDFG_CHAIN_DEBUG
+#ifdef SDFG_CHAIN_DEBUG
 #define CH_DBG(role, tag)                                                                                  \
     do {                                                                                                    \
         if (P.dbg && blockIdx.x == 0 && dbg_n < 1023) {                                                     \
@@ -138,6 +142,9 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8], uint32_t fmt) {
             dbg_n++;                                                                                        \
         }                                                                                                   \
     } while (0)
+#else
+#define CH_DBG(role, tag) do { } while (0)
+#endif
 
 // SAVE: a storer thread TMA-stores finished activation chunks (training: every layer; inference: the fp16 features).
 // COS (training only): FiLM layers also record sign(cos(gamma u + c)) as one bit per element (4 KB per tile and layer, bulk-stored
@@ -376,15 +383,27 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
         const uint32_t u0 = ((2 * sb) ^ (r & 7)) << 4, u1 = ((2 * sb + 1) ^ (r & 7)) << 4;
         uint32_t n = 0, stgen = 0;
         // FiLM constant of (layer, image) this thread publishes: threads 0..255 gamma (1 for a linear layer), 256..511 gamma*bias + beta.
-        // It is fetched one layer AHEAD so that its L2 latency hides behind the chunk loop instead of sitting between two layers.
-        auto film_const = [&](uint32_t i, uint32_t img) -> float {
-            const uint32_t col = etid & 255, act = P.layer[i].act, film = P.layer[i].film;
-            const float gm = act ? __ldg(P.gamma + (int64_t)img * P.gstride + film * 256 + col) : 1.f;
-            if (etid < 256) return gm;
-            const float b = __ldg(P.layer[i].bias + col);
-            return act ? fmaf(gm, b, __ldg(P.beta + (int64_t)img * P.gstride + film * 256 + col)) : b;
+        // Its raw inputs are fetched one layer AHEAD with cp.async into per-thread staging slots: no register waits on the L2
+        // latency, which therefore hides behind the chunk loop instead of sitting between two layers.
+        const uint32_t fcol = etid & 255;
+        const uint32_t stg_g_s = smem_u32(&S.stg_g[etid]), stg_b_s = smem_u32(&S.stg_b[fcol]), stg_be_s = smem_u32(&S.stg_be[fcol]);
+        auto cp_async4 = [](uint32_t dst, const float* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory"); };
+        auto film_fetch = [&](uint32_t i, uint32_t img) {
+            if (P.layer[i].act) {
+                const int64_t off = (int64_t)img * P.gstride + P.layer[i].film * 256 + fcol;
+                cp_async4(stg_g_s, P.gamma + off);
+                if (etid >= 256) cp_async4(stg_be_s, P.beta + off);
+            }
+            if (etid >= 256) cp_async4(stg_b_s, P.layer[i].bias + fcol);
         };
-        float pre = t_begin < t_end ? film_const(0, (t_begin * CH_TILE_M) / P.rows_per_image) : 0.f;
+        auto film_value = [&](uint32_t act) -> float {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            const float gm = act ? S.stg_g[etid] : 1.f;
+            if (etid < 256) return gm;
+            const float b = S.stg_b[fcol];
+            return act ? fmaf(gm, b, S.stg_be[fcol]) : b;
+        };
+        if (t_begin < t_end) film_fetch(0, (t_begin * CH_TILE_M) / P.rows_per_image);
         for (uint32_t t = t_begin; t < t_end; t++) {
             const uint64_t row = (uint64_t)t * CH_TILE_M + r;
             const bool valid = row < P.M_total;
@@ -393,16 +412,16 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
             for (uint32_t i = 0; i < nL; i++, n++) {
                 // layer description -> registers (constant-bank reads with a dynamic index are slow inside the chunk loop)
                 const uint32_t L_act = P.layer[i].act, L_nh = P.layer[i].nh, L_to_act = P.layer[i].to_act;
-                float* const o32 = P.layer[i].out_f32;
+                // fp32 copy of this layer's output (legacy feature output): row pointer once per layer, NULL when not wanted
+                float* const o32_row = (P.layer[i].out_f32 && valid) ? P.layer[i].out_f32 + row * P.layer[i].ld_out_f32 : nullptr;
                 const bool do_sgn = COS && P.layer[i].sgn != nullptr;
-                const int64_t ld32 = P.layer[i].ld_out_f32;
                 const uint32_t acc = n & 1, use = n >> 1, tb = n & 1;
                 const uint32_t gam_s = smem_u32(&S.gam[tb][0]), cst_s = smem_u32(&S.cst[tb][0]);
                 {   // publish this layer's FiLM constants (prefetched), then fetch the next layer's
-                    sts32((etid < 256 ? gam_s : cst_s) + (etid & 255) * 4, pre);
+                    sts32((etid < 256 ? gam_s : cst_s) + fcol * 4, film_value(L_act));
                     named_bar_sync(1, CH_EPI_THREADS);
-                    if (i + 1 < nL) pre = film_const(i + 1, img);
-                    else if (t + 1 < t_end) pre = film_const(0, ((t + 1) * CH_TILE_M) / P.rows_per_image);
+                    if (i + 1 < nL) film_fetch(i + 1, img);
+                    else if (t + 1 < t_end) film_fetch(0, ((t + 1) * CH_TILE_M) / P.rows_per_image);
                 }
                 const uint32_t heads_s = smem_u32(&S.heads[hrow][0]);
                 float hacc[3] = {0.f, 0.f, 0.f};
@@ -433,10 +452,15 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                             // sign of cos(u) = parity of rint(u / pi): one fma against the 1.5 * 2^23 magic constant puts that integer
                             // into the low mantissa bits.  Together with |cos| = sqrt(1 - sin^2) from the saved activation this is the
                             // whole derivative -- 16 bits per thread and chunk instead of a second fp16 tile and a second SFU op.
+                            // A funnel shift per element moves that bit into the mask: even elements first, then odd ones, so that
+                            // bit j = element 2j and bit 8 + j = element 2j + 1 (the order the backward chain's packed-half sign flip wants).
                             uint32_t m = 0;
 #pragma unroll
-                            for (int k = 0; k < 16; k++) m |= (__float_as_uint(fmaf(v[k], 0.31830988618379067f, 12582912.f)) & 1u) << k;
-                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(smem_u32(smSGN) + (((n & 1) * 16 + c * 4 + sb) * 128 + r) * 2), "h"((uint16_t)m) : "memory");
+                            for (int k = 0; k < 16; k++) {
+                                const int e = k < 8 ? 2 * k : 2 * (k - 8) + 1;
+                                m = __funnelshift_r(m, __float_as_uint(fmaf(v[e], 0.31830988618379067f, 12582912.f)), 1);
+                            }
+                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(smem_u32(smSGN) + (((n & 1) * 16 + c * 4 + sb) * 128 + r) * 2), "h"((uint16_t)(m >> 16)) : "memory");
                         }
 #pragma unroll
                         for (int k = 0; k < 16; k++) v[k] = __sinf(v[k]);
@@ -467,8 +491,8 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                         if (threadIdx.x == 0) CH_DBG(1, 500 + i * 16 + c);
                         if (lane == 0 && warp != 0) CH_DBG(4 + warp, 500 + i * 16 + c);
                     }
-                    if (o32 && valid) {
-                        float4* dst = reinterpret_cast<float4*>(o32 + row * ld32 + col);
+                    if (o32_row) {
+                        float4* dst = reinterpret_cast<float4*>(o32_row + col);
 #pragma unroll
                         for (int j = 0; j < 4; j++) dst[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
                     }
