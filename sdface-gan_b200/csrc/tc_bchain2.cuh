@@ -119,11 +119,14 @@ tc_chain_bwd2_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
         // ===================================================== weight producer (both CTAs): own half of every chunk, in MMA issue order
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            // every CTA re-reads the per-image weights (a few MB in total) for each of its tiles: keep them in L2 while the
+            // saved-activation reads and the du stores (GBs, touched once) stream past
+            const uint64_t keep = l2_policy_evict_last();
             auto put = [&](const CUtensorMap* m, uint32_t bytes, int32_t c0, int32_t c1) {
                 mbar_wait(&S.w_empty[stage], phase ^ 1);
                 if (leader) mbar_arrive_expect_tx(&S.w_full[stage], CG * bytes);
-                if (PAIR) tma_load_2d_2cta(smW + stage * W_BYTES, m, &S.w_full[stage], c0, c1);
-                else tma_load_2d(smW + stage * W_BYTES, m, &S.w_full[stage], c0, c1);
+                if (PAIR) tma_load_2d_2cta_hint(smW + stage * W_BYTES, m, &S.w_full[stage], c0, c1, keep);
+                else tma_load_2d_hint(smW + stage * W_BYTES, m, &S.w_full[stage], c0, c1, keep);
                 if (++stage == NW) { stage = 0; phase ^= 1; }
             };
             for (uint32_t u = u_begin; u < u_end; u++) {
@@ -140,13 +143,14 @@ tc_chain_bwd2_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
         // ===================================================== cos-tile producer (per CTA, local barriers): layer after layer, chunk by chunk
         if (lane == 0) {
             uint32_t cgen = 0;
+            const uint64_t stream = l2_policy_evict_first();
             for (uint32_t u = u_begin; u < u_end; u++) {
                 const int32_t row0 = (int32_t)((u * CG + rank) * CH_TILE_M);
                 for (uint32_t i = 0; i < nL; i++, cgen++)
                     for (uint32_t kc = 0; kc < 4; kc++) {
                         mbar_wait(&S.c_empty[kc], (cgen & 1) ^ 1);
                         mbar_arrive_expect_tx(&S.c_full[kc], CH_CHUNK_BYTES + (kc == 0 ? CH_SGN_TILE_BYTES : 0u));
-                        tma_load_2d(smC + kc * CH_CHUNK_BYTES, &maps.c[i], &S.c_full[kc], (int32_t)(kc * 64), row0);
+                        tma_load_2d_hint(smC + kc * CH_CHUNK_BYTES, &maps.c[i], &S.c_full[kc], (int32_t)(kc * 64), row0, stream);
                         // the layer's sign masks arrive with chunk 0 (double-buffered: the previous layer's may still be in use)
                         if (kc == 0) bulk_load(smSGN + (cgen & 1) * CH_SGN_TILE_BYTES, P.layer[i].sgn + (size_t)(u * CG + rank) * CH_SGN_TILE_BYTES, CH_SGN_TILE_BYTES, &S.c_full[0]);
                     }
@@ -197,6 +201,7 @@ tc_chain_bwd2_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
         if (STORE && lane == 0) {
             uint32_t gev = 0;
             uint64_t* pend = nullptr;                                   // one store group may still be reading G while the next is issued
+            const uint64_t stream = l2_policy_evict_first();
             for (uint32_t u = u_begin; u < u_end; u++) {
                 const int32_t row0 = (int32_t)((u * CG + rank) * CH_TILE_M);
                 const uint32_t n_ev = nL + (P.has_in ? 1u : 0u);
@@ -204,7 +209,7 @@ tc_chain_bwd2_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
                     const CUtensorMap* m = e < nL ? &maps.dz[e] : &maps.dh0;
                     for (uint32_t c = 0; c < 4; c++) {
                         mbar_wait(&S.g_ready_st[c], gev & 1);
-                        tma_store_2d(m, smG + c * CH_CHUNK_BYTES, (int32_t)(c * 64), row0);
+                        tma_store_2d_hint(m, smG + c * CH_CHUNK_BYTES, (int32_t)(c * 64), row0, stream);
                         tma_store_commit();
                         if (pend) { tma_store_wait_read_pending<1>(); mbar_arrive(pend); }
                         pend = &S.st_done[c];
