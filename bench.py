@@ -308,7 +308,7 @@ def run_ours(args):
                 "msamples_per_s": world * N / (ms * 1e-3) / 1e6,
                 "config": {"workload": "configs[1]: 64^2 SDF + hash-grid (ngp=1) generator forward+backward, stage-1 G step", "rays": R,
                            "samples_per_ray": S, "batch_per_gpu": B, "global_batch": world * B, "parallelism": "dp%d" % world,
-                           "l2": "per-step saved activations + gradient tiles (%.1f GB) exceed the 126 MB L2; no flush needed" % (N * 5.8e3 / 1e9)},
+                           "l2": "per-step saved activations + gradient tiles (%.1f GB) exceed the 126 MB L2; no flush needed" % (N * 5.3e3 / 1e9)},
                 "clocks": clk.summary(),
                 "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "roofline": roof, "inference": inf, "cpu_baseline": cpu}
