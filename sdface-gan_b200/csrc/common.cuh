@@ -61,6 +61,18 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// the same with an L2 eviction-priority policy (createpolicy): the table gradient should outlive traffic streaming past it
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void red_add_v2_hint(float* addr, float a, float b, uint64_t pol) {
+    asm volatile("red.global.add.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(addr), "f"(a), "f"(b), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_add_v4_hint(float* addr, float a, float b, float c, float d, uint64_t pol) {
+    asm volatile("red.global.add.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void red_add_f32(float* addr, float a) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }

@@ -135,6 +135,16 @@ __device__ __forceinline__ void red_feat(float* p, const float (&v)[C]) {
         for (uint32_t i = 0; i < C; i += 4) red_add_v4(p + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
     }
 }
+// the same with an L2 evict_last policy: the table gradient (tens of MB) stays L2-resident while other kernels stream GBs past it
+template <uint32_t C>
+__device__ __forceinline__ void red_feat_keep(float* p, const float (&v)[C], uint64_t pol) {
+    if constexpr (C == 1) { red_add_f32(p, v[0]); }
+    else if constexpr (C == 2) { red_add_v2_hint(p, v[0], v[1], pol); }
+    else {
+#pragma unroll
+        for (uint32_t i = 0; i < C; i += 4) red_add_v4_hint(p + i, v[i], v[i + 1], v[i + 2], v[i + 3], pol);
+    }
+}
 
 // One level of one sample: blend (and optional dy_dx).  Returns false (and zeros) when the sample is outside [0,1]^D.
 template <uint32_t D, uint32_t C, bool DYDX>
@@ -269,6 +279,7 @@ __global__ void __launch_bounds__(256) grid_backward_kernel(const float* __restr
 #pragma unroll
     for (uint32_t d = 0; d < D; d++) u[d] = 0.f;
     const bool active = n < N && load_unit<D>(inputs, n, bound, u);
+    const uint64_t keep = l2_keep_policy();
     for (uint32_t level = 0; level < L; level++) {
     const LevelInfo li = li_all[level];
     Feat<C> g;
@@ -314,7 +325,7 @@ __global__ void __launch_bounds__(256) grid_backward_kernel(const float* __restr
                     if (lane + o < end) v[c] += t;
                 }
             }
-            if (head && active) red_feat<C>(gt + (size_t)row * C, v);
+            if (head && active) red_feat_keep<C>(gt + (size_t)row * C, v, keep);
         }
     } else if (active) {
         // Fine levels scatter directly.  The two corners along x of a pair are adjacent table rows whenever the lower one is even
@@ -340,10 +351,10 @@ __global__ void __launch_bounds__(256) grid_backward_kernel(const float* __restr
 #pragma unroll
             for (uint32_t c = 0; c < C; c++) { v0[c] = w0 * g.v[c]; v1[c] = w1 * g.v[c]; }
             if constexpr (C == 2) {
-                if (r1 == r0 + 1 && (r0 & 1u) == 0) { red_add_v4(gt + (size_t)r0 * 2, v0[0], v0[1], v1[0], v1[1]); continue; }
+                if (r1 == r0 + 1 && (r0 & 1u) == 0) { red_add_v4_hint(gt + (size_t)r0 * 2, v0[0], v0[1], v1[0], v1[1], keep); continue; }
             }
-            red_feat<C>(gt + (size_t)r0 * C, v0);
-            red_feat<C>(gt + (size_t)r1 * C, v1);
+            red_feat_keep<C>(gt + (size_t)r0 * C, v0, keep);
+            red_feat_keep<C>(gt + (size_t)r1 * C, v1, keep);
         }
     }
     }   // levels

@@ -84,13 +84,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant_
         // ===================================================== TMA producer
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            const uint64_t stream = l2_policy_evict_first();            // du columns are read exactly once (x is shared with the partner CTA)
             for (uint32_t s = s_begin; s < s_end; s++) {
                 mbar_wait(&S.empty[stage], phase ^ 1);
                 mbar_arrive_expect_tx(&S.full[stage], stage_bytes);
                 uint8_t* base = smem + stage * stage_bytes;
                 const int32_t row = (int32_t)(s * WG_ROWS);
-                tma_load_2d(base, &tmDZ, &S.full[stage], (int32_t)(half * 128), row);
-                tma_load_2d(base + WG_BOX_BYTES, &tmDZ, &S.full[stage], (int32_t)(half * 128 + 64), row);
+                tma_load_2d_hint(base, &tmDZ, &S.full[stage], (int32_t)(half * 128), row, stream);
+                tma_load_2d_hint(base + WG_BOX_BYTES, &tmDZ, &S.full[stage], (int32_t)(half * 128 + 64), row, stream);
                 for (uint32_t b = 0; b < P.n_xbox; b++)
                     tma_load_2d(base + (2 + b) * WG_BOX_BYTES, &tmX, &S.full[stage], (int32_t)(b * 64), row);
                 if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }

@@ -76,9 +76,11 @@ class FiLMSiren(nn.Module):
 # the fused field as one autograd node
 
 _SIDE_STREAMS = {}
-# Two-stream backward (weight-gradient contractions on a side stream while the hash-table scatter runs): measured neutral on B200
-# (19.5-20.2 ms per step either way: the contractions already saturate HBM and push the table gradient out of L2), so it is
-# off unless SDFG_OVERLAP=1.
+# Two-stream backward (weight-gradient contractions on a side stream while the hash-table scatter runs): measured neutral on B200.
+# With a default-priority side stream the scatter's 12k short blocks fill every SM and the persistent contraction kernels only
+# start once it has drained; with a high-priority side stream they do run together (torch.profiler timeline), but both live on L2
+# bandwidth: the scatter stretches 2.0 -> 3.4 ms and the first contraction 0.56 -> 1.6 ms, the step ends at the same time
+# (16.8-17.4 ms either way).  Off unless SDFG_OVERLAP=1.
 _OVERLAP = os.environ.get("SDFG_OVERLAP", "0") == "1"
 
 
@@ -86,7 +88,9 @@ def _side_stream(device):
     """One extra stream per device for the weight-gradient contractions of the field backward (see _field.backward)."""
     key = torch.device(device).index
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+        # high priority: its persistent 1-CTA-per-SM kernels must get their slots while the scatter's thousands of short blocks
+        # keep every SM full (without it the block scheduler starts them only after the scatter has drained)
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device, priority=-1)
     return _SIDE_STREAMS[key]
 
 
