@@ -348,16 +348,18 @@ __global__ void __launch_bounds__(256) wgt_kernel(const float* __restrict__ W, i
     out[((size_t)b * Kuse + k) * 256 + j] = __half_as_ushort(__float2half_rn(g * __ldg(W + (int64_t)j * ldw + k)));
 }
 
-// finishing kernel of one layer's weight gradient: G [B, 256, ldg] -> dW, db, dgamma, dbeta   (block = neuron j, threads over k)
-__global__ void __launch_bounds__(128) wgrad_finish_kernel(const float* __restrict__ G, uint32_t ldg, uint32_t ones_col, uint32_t B,
+// finishing kernel of one layer's weight gradient: G [B, 256, ldg] -> dW, db, dgamma, dbeta   (block = neuron j)
+//   dW[j, k] += 1/s * sum_b gamma_b[j] G[b, j, k]                      threads over k, coalesced rows of G
+//   dgamma_b[j] += 1/s * (W[j, :] . G[b, j, :] + bias[j] * ones_b),  dbeta_b[j] += ones_b / s,  db[j] += sum_b gamma_b[j] ones_b / s
+//   (ones_b = G[b, j, ones_col], the column the weight-gradient GEMM accumulates against the constant-one operand)  warp per image
+__global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restrict__ G, uint32_t ldg, uint32_t ones_col, uint32_t B,
                                                             const float* __restrict__ W, int64_t ldw, uint32_t Kx, const float* __restrict__ bias,
                                                             const float* __restrict__ gamma, int64_t gstride, int film,
                                                             float* __restrict__ dW, float* __restrict__ db, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, const float* __restrict__ gscale) {
-    __shared__ float red[4];
-    const uint32_t j = blockIdx.x;
+    __shared__ float dbs[8];
+    const uint32_t j = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float inv_s = gscale ? __ldg(gscale + 1) : 1.f;      // G carries the loss scale of the fp16 gradients
-    float dbj = 0.f;
     for (uint32_t k = threadIdx.x; k < Kx; k += blockDim.x) {
         float acc = 0.f;
         for (uint32_t b = 0; b < B; b++) {
@@ -366,18 +368,16 @@ __global__ void __launch_bounds__(128) wgrad_finish_kernel(const float* __restri
         }
         dW[(int64_t)j * ldw + k] += inv_s * acc;
     }
-    for (uint32_t b = 0; b < B; b++) {
-        const float ones = inv_s * __ldg(G + ((size_t)b * 256 + j) * ldg + ones_col);
+    float dbj = 0.f;
+    for (uint32_t b = warp; b < B; b += 8) {
+        const float* Gr = G + ((size_t)b * 256 + j) * ldg;
+        const float ones = inv_s * __ldg(Gr + ones_col);
         if (film) {
             float part = 0.f;
-            for (uint32_t k = threadIdx.x; k < Kx; k += blockDim.x) part = fmaf(__ldg(W + (int64_t)j * ldw + k), __ldg(G + ((size_t)b * 256 + j) * ldg + k), part);
+            for (uint32_t k = lane; k < Kx; k += 32) part = fmaf(__ldg(W + (int64_t)j * ldw + k), __ldg(Gr + k), part);
             part = warp_sum(part);
-            __syncthreads();
-            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                const float tot = red[0] + red[1] + red[2] + red[3];
-                dgamma[(int64_t)b * gstride + j] += fmaf(__ldg(bias + j), ones, inv_s * tot);
+            if (lane == 0) {
+                dgamma[(int64_t)b * gstride + j] += fmaf(__ldg(bias + j), ones, inv_s * part);
                 dbeta[(int64_t)b * gstride + j] += ones;
             }
             dbj = fmaf(__ldg(gamma + (int64_t)b * gstride + j), ones, dbj);
@@ -385,7 +385,9 @@ __global__ void __launch_bounds__(128) wgrad_finish_kernel(const float* __restri
             dbj += ones;
         }
     }
-    if (threadIdx.x == 0) db[j] += dbj;
+    if (lane == 0) dbs[warp] = dbj;
+    __syncthreads();
+    if (threadIdx.x == 0) db[j] += ((dbs[0] + dbs[1]) + (dbs[2] + dbs[3])) + ((dbs[4] + dbs[5]) + (dbs[6] + dbs[7]));
 }
 
 // head weight gradient: dw[c, k] += sum_n dout[n, c] * h[n, k]   (h fp16 [*, 256], pitch ld), db[c] += sum_n dout[n, c].
@@ -666,7 +668,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
             if (cudaMemsetAsync(G, 0, (size_t)B * 256 * 336 * 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");
             uint32_t ldg, ones;
             if (int e = launch_wgrad((const h16*)(sc + SC.off_dz[l]), A(l), layer_Kx(l), layer_K(l), N, spi, G, &ldg, &ones, st, tc::FMT_F16)) return e;
-            wgrad_finish_kernel<<<256, 128, 0, st>>>(G, ldg, ones, B, p->film_w[l], layer_Kx(l), layer_Kx(l), p->film_b[l], p->gamma + (size_t)l * W,
+            wgrad_finish_kernel<<<256, 256, 0, st>>>(G, ldg, ones, B, p->film_w[l], layer_Kx(l), layer_Kx(l), p->film_b[l], p->gamma + (size_t)l * W,
                                                      gstride, 1, g->film_w[l], g->film_b[l], g->gamma + (size_t)l * W, g->beta + (size_t)l * W, gscale);
             if (int e = check_launch("wgrad_finish_kernel")) return e;
         }
@@ -674,7 +676,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
             if (cudaMemsetAsync(G, 0, (size_t)B * 256 * 336 * 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");
             uint32_t ldg, ones;
             if (int e = launch_wgrad(DH, (const h16*)(ws + L.off_x0), p->in_dim, L.Kp_in, N, spi, G, &ldg, &ones, st, tc::FMT_F16)) return e;
-            wgrad_finish_kernel<<<256, 128, 0, st>>>(G, ldg, ones, B, p->input_w, p->in_dim, p->in_dim, p->input_b, nullptr, 0, 0, g->input_w,
+            wgrad_finish_kernel<<<256, 256, 0, st>>>(G, ldg, ones, B, p->input_w, p->in_dim, p->in_dim, p->input_b, nullptr, 0, 0, g->input_w,
                                                      g->input_b, nullptr, nullptr, gscale);
             if (int e = check_launch("wgrad_finish_kernel")) return e;
         }
@@ -809,7 +811,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
             if (cudaMemsetAsync(G, 0, (size_t)B * 256 * 336 * 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");
             uint32_t ldg, ones;
             if (int e = launch_wgrad((const h16*)(sc + SC.off_dz[l]), A(l), layer_Kx(l), layer_K(l), N, spi, G, &ldg, &ones, st, tc::FMT_F16)) return e;
-            wgrad_finish_kernel<<<256, 128, 0, st>>>(G, ldg, ones, B, p->film_w[l], layer_Kx(l), layer_Kx(l), p->film_b[l], p->gamma + (size_t)l * W,
+            wgrad_finish_kernel<<<256, 256, 0, st>>>(G, ldg, ones, B, p->film_w[l], layer_Kx(l), layer_Kx(l), p->film_b[l], p->gamma + (size_t)l * W,
                                                      gstride, 1, g->film_w[l], g->film_b[l], g->gamma + (size_t)l * W, g->beta + (size_t)l * W, gscale);
             if (int e = check_launch("wgrad_finish_kernel")) return e;
         }
@@ -817,7 +819,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
             if (cudaMemsetAsync(G, 0, (size_t)B * 256 * 336 * 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");
             uint32_t ldg, ones;
             if (int e = launch_wgrad(DH, (const h16*)(ws + L.off_x0), p->in_dim, L.Kp_in, N, spi, G, &ldg, &ones, st, tc::FMT_F16)) return e;
-            wgrad_finish_kernel<<<256, 128, 0, st>>>(G, ldg, ones, B, p->input_w, p->in_dim, p->in_dim, p->input_b, nullptr, 0, 0, g->input_w,
+            wgrad_finish_kernel<<<256, 256, 0, st>>>(G, ldg, ones, B, p->input_w, p->in_dim, p->in_dim, p->input_b, nullptr, 0, 0, g->input_w,
                                                      g->input_b, nullptr, nullptr, gscale);
             if (int e = check_launch("wgrad_finish_kernel")) return e;
         }
@@ -840,7 +842,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         if (cudaMemsetAsync(G, 0, (size_t)B * 256 * 336 * 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");
         uint32_t ldg, ones;
         if (int e = launch_wgrad(DZ, A(l), layer_Kx(l), layer_K(l), N, spi, G, &ldg, &ones, st, tc::FMT_F16)) return e;
-        wgrad_finish_kernel<<<256, 128, 0, st>>>(G, ldg, ones, B, p->film_w[l], layer_Kx(l), layer_Kx(l), p->film_b[l], p->gamma + (size_t)l * W,
+        wgrad_finish_kernel<<<256, 256, 0, st>>>(G, ldg, ones, B, p->film_w[l], layer_Kx(l), layer_Kx(l), p->film_b[l], p->gamma + (size_t)l * W,
                                                  gstride, 1, g->film_w[l], g->film_b[l], g->gamma + (size_t)l * W, g->beta + (size_t)l * W, gscale);
         return check_launch("wgrad_finish_kernel");
     };
@@ -888,7 +890,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
             if (cudaMemsetAsync(G, 0, (size_t)B * 256 * 336 * 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");
             uint32_t ldg, ones;
             if (int e = launch_wgrad(DH, (const h16*)(ws + L.off_x0), p->in_dim, L.Kp_in, N, spi, G, &ldg, &ones, st, tc::FMT_F16)) return e;
-            wgrad_finish_kernel<<<256, 128, 0, st>>>(G, ldg, ones, B, p->input_w, p->in_dim, p->in_dim, p->input_b, nullptr, 0, 0, g->input_w,
+            wgrad_finish_kernel<<<256, 256, 0, st>>>(G, ldg, ones, B, p->input_w, p->in_dim, p->in_dim, p->input_b, nullptr, 0, 0, g->input_w,
                                                      g->input_b, nullptr, nullptr, gscale);
             if (int e = check_launch("wgrad_finish_kernel")) return e;
         }
