@@ -59,3 +59,28 @@ def average_gradients(module, bucket_bytes=64 << 20):
             off += n
         calls += 1
     return calls
+
+
+def data_parallel(module, device_ids=None, early_table_exchange=False, **ddp_kwargs):
+    """Wrap a Generator (or any module holding the SDF renderer) in DistributedDataParallel for one-process-per-GPU training.
+
+    With `early_table_exchange` the hash-table parameter(s) (`*.encoder.embeddings`, 93 % of the bytes exchanged in stage 1) are
+    taken out of DDP's buckets: autograd produces that gradient last, so its bucket could not overlap any compute.  The field's
+    backward node all-reduces (averages) it itself right after the scatter kernel is enqueued, concurrently with the
+    weight-gradient kernels (sdf_model._field.backward).  The parameter is broadcast from rank 0 here, as DDP would have done.
+    Only the renderer's own backward exchanges the table gradient in that mode: a loss that reaches the table through another
+    node (e.g. a smoothness term on `query_sdf`) must leave `early_table_exchange` off."""
+    from . import sdf_model
+    ddp = torch.nn.parallel.DistributedDataParallel
+    names = [n for n, _ in module.named_parameters() if n.endswith("encoder.embeddings")] if early_table_exchange else []
+    if names and dist.get_world_size() > 1:
+        ddp._set_params_and_buffers_to_ignore_for_model(module, names)
+        lookup = dict(module.named_parameters())
+        with torch.no_grad():
+            for n in names:
+                dist.broadcast(lookup[n].data, 0)
+        sdf_model._EARLY_TABLE_EXCHANGE["on"] = True
+    ddp_kwargs.setdefault("bucket_cap_mb", 64)
+    ddp_kwargs.setdefault("gradient_as_bucket_view", True)
+    return ddp(module, device_ids=device_ids, **ddp_kwargs)
+

@@ -82,6 +82,11 @@ _SIDE_STREAMS = {}
 # bandwidth: the scatter stretches 2.0 -> 3.4 ms and the first contraction 0.56 -> 1.6 ms, the step ends at the same time
 # (16.8-17.4 ms either way).  Off unless SDFG_OVERLAP=1.
 _OVERLAP = os.environ.get("SDFG_OVERLAP", "0") == "1"
+# Data-parallel training (distributed.data_parallel): the hash-table gradient (50.6 MB of the 54.6 MB exchanged per step) is the
+# LAST gradient autograd sees, so a DistributedDataParallel bucket holding it cannot overlap anything.  When this flag is set the
+# field node all-reduces it itself, as soon as the scatter kernel is enqueued, while the weight-gradient contractions still run
+# on the side stream; DistributedDataParallel is told to ignore the parameter.
+_EARLY_TABLE_EXCHANGE = {"on": False}
 
 
 def _side_stream(device):
@@ -158,7 +163,10 @@ class _field(Function):
             grads["beta"] = torch.zeros_like(beta)
         d_sdf, d_rgb, d_feat = cont(d_sdf), cont(d_rgb), cont(d_feat)
         want_dx = bool(ctx.needs_input_grad[2] or need_table)
-        side = _side_stream(x_in.device) if (need_table and need_param and meta["precision"] == _lib.PRECISION_TC16 and _OVERLAP) else None
+        early = (need_table and _EARLY_TABLE_EXCHANGE["on"] and torch.distributed.is_available() and torch.distributed.is_initialized()
+                 and torch.distributed.get_world_size() > 1)
+        side = (_side_stream(x_in.device)
+                if (need_table and need_param and meta["precision"] == _lib.PRECISION_TC16 and (_OVERLAP or early)) else None)
         res = ops.field_backward(spec, x_in, view_feat, gamma, beta, weights, meta["spi"], meta["spr"], ws,
                                  feat if meta["want_feat"] else None, d_sdf, d_rgb, d_feat, grads=grads,
                                  want_dx=want_dx, precision=meta["precision"], wgrad_stream=side)
@@ -168,8 +176,13 @@ class _field(Function):
             d_emb = torch.zeros_like(emb)
             ops.grid_encode_backward(dx, grid["pts"], emb, grid["offsets"], grid["S"], grid["H"], bound=grid["bound"], grad_embeddings=d_emb,
                                      gridtype=grid["gridtype"], align_corners=grid["align_corners"], interp=grid["interp"])
+        work = None
+        if early:
+            work = torch.distributed.all_reduce(d_emb, op=torch.distributed.ReduceOp.AVG, async_op=True)
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)      # joins before scratch / grads / upstream gradients are let go
+        if work is not None:
+            work.wait()                                        # stream-level: the current stream waits for the collective
         del scratch
         out = [None, None, dx if ctx.needs_input_grad[2] else None, None]
         if need_param:

@@ -60,3 +60,59 @@ def test_shard_sync_and_gradient_average_world2():
     assert abs(s0 - float(z[:4].sum())) < 1e-4 and abs(s1 - float(z[4:].sum())) < 1e-4
     assert ok0 and ok1
     assert c0 == c1 and 1 <= c0 <= 4                # 54.6 MB of fp32 gradients in a handful of bucketed collectives
+
+
+class _Toy(torch.nn.Module):
+    """Same parameter naming as the renderer: `...encoder.embeddings` is the table the field node exchanges itself."""
+
+    def __init__(self):
+        super().__init__()
+        self.encoder = torch.nn.Module()
+        self.encoder.embeddings = torch.nn.Parameter(torch.ones(16, 2))
+        self.lin = torch.nn.Linear(2, 1)
+
+    def forward(self, idx, scale):
+        return (self.lin(self.encoder.embeddings[idx]) * scale).sum()
+
+
+def _worker_dp(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import sdface_gan_b200 as sg
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(7 + rank)
+        toy = _Toy()
+        with torch.no_grad():
+            toy.encoder.embeddings.add_(float(rank))              # differs per rank before wrapping
+        model = sg.distributed.data_parallel(toy, early_table_exchange=True)
+        emb0 = toy.encoder.embeddings.detach().clone()             # rank 0's values everywhere after the wrap
+        w0 = toy.lin.weight.detach().clone()
+        loss = model(torch.arange(4) + 4 * rank, float(rank + 1))
+        loss.backward()
+        from sdface_gan_b200 import sdf_model
+        # plain lists: a tensor would travel as a shared-memory handle that dies with this process
+        q.put((rank, emb0.tolist(), w0.tolist(), toy.encoder.embeddings.grad.tolist(), toy.lin.weight.grad.tolist(),
+               sdf_model._EARLY_TABLE_EXCHANGE["on"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_takes_the_table_out_of_ddp_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_dp, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, e0, w0, ge0, gw0, on0), (_, e1, w1, ge1, gw1, on1) = [tuple(torch.tensor(x) if isinstance(x, list) else x for x in r) for r in res]
+    assert on0 and on1
+    assert torch.equal(e0, e1) and torch.equal(w0, w1)            # table broadcast by the helper, the rest by DDP
+    assert torch.allclose(gw0, gw1)                               # DDP averaged the ordinary parameter
+    assert not torch.allclose(ge0, ge1)                           # ...and left the table gradient to the field node (rank-local here)
+    assert ge0[:4].abs().sum() > 0 and ge0[4:].abs().sum() == 0 and ge1[4:8].abs().sum() > 0
