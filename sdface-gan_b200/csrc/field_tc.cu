@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
+#include <vector>
 
 #include "field.cuh"
 #include "tc_bchain.cuh"
@@ -27,6 +28,21 @@
 #include "tc_wgrad.cuh"
 
 namespace sdfg {
+
+// Opt a kernel in to `smem` bytes of dynamic shared memory.  The attribute is per (device, function); the cache is per host
+// thread and keyed by the current device, so a process that drives several GPUs from one thread configures each of them.
+static int optin_smem(const void* fn, uint32_t smem, const char* what) {
+    struct Done { int dev; const void* fn; uint32_t smem; };
+    static thread_local std::vector<Done> done;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "%s: cudaGetDevice failed", what);
+    for (const Done& d : done)
+        if (d.dev == dev && d.fn == fn && d.smem >= smem) return SDFG_OK;
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return set_error(SDFG_ERR_CUDA, "%s: cannot opt in to %u bytes of shared memory", what, smem);
+    done.push_back({dev, fn, smem});
+    return SDFG_OK;
+}
 
 using tc::LayerParams;
 
@@ -67,12 +83,7 @@ static int launch_layer(const void* a, uint64_t a_rows, uint32_t K, int64_t lda,
     P.tiles_per_cta = ceil_div<uint32_t>(P.n_tiles, ctas);
     const uint32_t grid = ceil_div<uint32_t>(P.n_tiles, P.tiles_per_cta);
     const uint32_t smem = tc::layer_smem_bytes(K, P.N_out);
-    static thread_local uint32_t configured[3] = {0, 0, 0};
-    if (configured[MODE] < smem) {
-        if (cudaFuncSetAttribute(tc::tc_layer_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return set_error(SDFG_ERR_CUDA, "%s: cannot opt in to %u bytes of shared memory", what, smem);
-        configured[MODE] = smem;
-    }
+    if (int e = optin_smem((const void*)tc::tc_layer_kernel<MODE>, smem, what)) return e;
     ProfScope prof(what, st);
     tc::tc_layer_kernel<MODE><<<grid, tc::LAYER_THREADS, smem, st>>>(tmA, tmB, P);
     return check_launch(what);
@@ -245,13 +256,7 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
     const uint32_t smem = tc::chain_smem_bytes();
     const bool storing = save || out_feat16;
     auto kern = save ? tc::tc_chain_fwd_kernel<true, true> : (storing ? tc::tc_chain_fwd_kernel<true, false> : tc::tc_chain_fwd_kernel<false, false>);
-    static thread_local bool configured[3] = {false, false, false};
-    const int kidx = save ? 2 : (storing ? 1 : 0);
-    if (!configured[kidx]) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return set_error(SDFG_ERR_CUDA, "tc_chain_fwd_kernel: cannot opt in to %u bytes of shared memory", smem);
-        configured[kidx] = true;
-    }
+    if (int e = optin_smem((const void*)kern, smem, "tc_chain_fwd_kernel")) return e;
     static const bool dbg_on = getenv("SDFG_CHAIN_DBG") != nullptr;     // debugging aid: event log of CTA 0 to stderr
     if (dbg_on) {
         static unsigned long long* dbuf = nullptr;
@@ -508,12 +513,7 @@ static int launch_wgrad(const h16* dz, const h16* x, uint32_t Kx, int64_t ldx, u
     if (int e = make_tensor_map_16(&tmDZ, dz, N, 256, 256, tc::WG_ROWS, 64, x_fmt)) return e;
     if (int e = make_tensor_map_16(&tmX, x, N, (uint64_t)ldx, (uint64_t)ldx, tc::WG_ROWS, 64, x_fmt)) return e;
     const uint32_t smem = tc::wgrad_smem_bytes(P.n_xbox);
-    static thread_local uint32_t configured = 0;
-    if (configured < smem) {
-        if (cudaFuncSetAttribute(tc::tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return set_error(SDFG_ERR_CUDA, "tc_wgrad_kernel: cannot opt in to %u bytes of shared memory", smem);
-        configured = smem;
-    }
+    if (int e = optin_smem((const void*)tc::tc_wgrad_kernel, smem, "tc_wgrad_kernel")) return e;
     ProfScope prof("tc_wgrad_kernel<gemm>", st);
     tc::tc_wgrad_kernel<<<grid, tc::WG_THREADS, smem, st>>>(tmDZ, tmX, P);
     return check_launch("tc_wgrad_kernel<gemm>");
@@ -628,13 +628,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         typedef void (*b2kern_t)(const tc::B2ChainMaps, const tc::B2ChainParams);
         const b2kern_t kern = cg == 2 ? (store ? (b2kern_t)tc::tc_chain_bwd2_kernel<true, 2> : (b2kern_t)tc::tc_chain_bwd2_kernel<false, 2>)
                                       : (store ? (b2kern_t)tc::tc_chain_bwd2_kernel<true, 1> : (b2kern_t)tc::tc_chain_bwd2_kernel<false, 1>);
-        static thread_local bool configured[4] = {false, false, false, false};
-        const int ki = (cg == 2 ? 2 : 0) + (store ? 1 : 0);
-        if (!configured[ki]) {
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-                return set_error(SDFG_ERR_CUDA, "tc_chain_bwd2_kernel: cannot opt in to %u bytes of shared memory", smem);
-            configured[ki] = true;
-        }
+        if (int e = optin_smem((const void*)kern, smem, "tc_chain_bwd2_kernel")) return e;
         {
             ProfScope prof("tc_chain_bwd2_kernel<gemm>", st);
             cudaLaunchConfig_t cfg = {};
@@ -749,13 +743,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         typedef void (*bkern_t)(const tc::BChainMaps, const tc::BChainParams);
         const bkern_t kern = cg == 2 ? (store ? (bkern_t)tc::tc_chain_bwd_kernel<true, 2> : (bkern_t)tc::tc_chain_bwd_kernel<false, 2>)
                                      : (store ? (bkern_t)tc::tc_chain_bwd_kernel<true, 1> : (bkern_t)tc::tc_chain_bwd_kernel<false, 1>);
-        static thread_local bool configured[4] = {false, false, false, false};
-        const int ki = (cg == 2 ? 2 : 0) + (store ? 1 : 0);
-        if (!configured[ki]) {
-            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-                return set_error(SDFG_ERR_CUDA, "tc_chain_bwd_kernel: cannot opt in to %u bytes of shared memory", smem);
-            configured[ki] = true;
-        }
+        if (int e = optin_smem((const void*)kern, smem, "tc_chain_bwd_kernel")) return e;
         auto launch = [&]() -> int {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
