@@ -23,6 +23,7 @@
 #include "field.cuh"
 #include "tc_bchain.cuh"
 #include "tc_bchain2.cuh"
+#include "tc_bchain3.cuh"
 #include "tc_chain.cuh"
 #include "tc_layer.cuh"
 #include "tc_wgrad.cuh"
@@ -624,10 +625,15 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         const uint32_t groups = std::min<uint32_t>((uint32_t)sm_count() / cg, P.n_units);
         P.units_per_cta = ceil_div<uint32_t>(P.n_units, groups);
         const uint32_t grid = cg * ceil_div<uint32_t>(P.n_units, P.units_per_cta);
-        const uint32_t smem = tc::bchain2_smem_bytes(cg);
+        // two tiles in flight per CTA (tc_bchain3.cuh): measured 4-5 % faster for the pass without stores (eikonal), 2 % slower with
+        // them.  SDFG_TC_PP=0 never, =2 always.
+        static const int pp_env = []() { const char* e = getenv("SDFG_TC_PP"); return e ? atoi(e) : 1; }();
+        const bool pingpong = cg == 2 && (pp_env == 2 || (pp_env == 1 && !store));
+        const uint32_t smem = pingpong ? tc::bchain3_smem_bytes() : tc::bchain2_smem_bytes(cg);
         typedef void (*b2kern_t)(const tc::B2ChainMaps, const tc::B2ChainParams);
-        const b2kern_t kern = cg == 2 ? (store ? (b2kern_t)tc::tc_chain_bwd2_kernel<true, 2> : (b2kern_t)tc::tc_chain_bwd2_kernel<false, 2>)
-                                      : (store ? (b2kern_t)tc::tc_chain_bwd2_kernel<true, 1> : (b2kern_t)tc::tc_chain_bwd2_kernel<false, 1>);
+        const b2kern_t kern = pingpong ? (store ? (b2kern_t)tc::tc_chain_bwd3_kernel<true> : (b2kern_t)tc::tc_chain_bwd3_kernel<false>)
+                            : cg == 2  ? (store ? (b2kern_t)tc::tc_chain_bwd2_kernel<true, 2> : (b2kern_t)tc::tc_chain_bwd2_kernel<false, 2>)
+                                       : (store ? (b2kern_t)tc::tc_chain_bwd2_kernel<true, 1> : (b2kern_t)tc::tc_chain_bwd2_kernel<false, 1>);
         if (int e = optin_smem((const void*)kern, smem, "tc_chain_bwd2_kernel")) return e;
         {
             ProfScope prof("tc_chain_bwd2_kernel<gemm>", st);
