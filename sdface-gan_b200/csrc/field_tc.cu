@@ -24,6 +24,7 @@
 #include "tc_bchain.cuh"
 #include "tc_bchain2.cuh"
 #include "tc_bchain3.cuh"
+#include "tc_bchain4.cuh"
 #include "tc_chain.cuh"
 #include "tc_layer.cuh"
 #include "tc_wgrad.cuh"
@@ -628,13 +629,24 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         // two tiles in flight per CTA (tc_bchain3.cuh): measured 4-5 % faster for the pass without stores (eikonal), 2 % slower with
         // them.  SDFG_TC_PP=0 never, =2 always.
         static const int pp_env = []() { const char* e = getenv("SDFG_TC_PP"); return e ? atoi(e) : 1; }();
-        const bool pingpong = cg == 2 && (pp_env == 2 || (pp_env == 1 && !store));
-        const uint32_t smem = pingpong ? tc::bchain3_smem_bytes() : tc::bchain2_smem_bytes(cg);
+        // SDFG_TC_TS=1: the pass without stores with the A operand in tensor memory (tc_bchain4.cuh; measured equal to the default)
+        static const bool ts_env = []() { const char* e = getenv("SDFG_TC_TS"); return e ? atoi(e) != 0 : false; }();
+        const bool a_in_tmem = cg == 2 && !store && ts_env && pp_env != 2;
+        const bool pingpong = !a_in_tmem && cg == 2 && (pp_env == 2 || (pp_env == 1 && !store));
+        const uint32_t smem = a_in_tmem ? tc::bchain4_smem_bytes() : pingpong ? tc::bchain3_smem_bytes() : tc::bchain2_smem_bytes(cg);
         typedef void (*b2kern_t)(const tc::B2ChainMaps, const tc::B2ChainParams);
-        const b2kern_t kern = pingpong ? (store ? (b2kern_t)tc::tc_chain_bwd3_kernel<true> : (b2kern_t)tc::tc_chain_bwd3_kernel<false>)
+        const b2kern_t kern = a_in_tmem ? (b2kern_t)tc::tc_chain_bwd4_kernel
+                            : pingpong ? (store ? (b2kern_t)tc::tc_chain_bwd3_kernel<true> : (b2kern_t)tc::tc_chain_bwd3_kernel<false>)
                             : cg == 2  ? (store ? (b2kern_t)tc::tc_chain_bwd2_kernel<true, 2> : (b2kern_t)tc::tc_chain_bwd2_kernel<false, 2>)
                                        : (store ? (b2kern_t)tc::tc_chain_bwd2_kernel<true, 1> : (b2kern_t)tc::tc_chain_bwd2_kernel<false, 1>);
         if (int e = optin_smem((const void*)kern, smem, "tc_chain_bwd2_kernel")) return e;
+        static const bool dbg4_on = getenv("SDFG_BCHAIN_DBG") != nullptr;   // debugging aid (-DSDFG_CHAIN_DEBUG build): phase sums of CTA 0, eikonal pass
+        static unsigned long long* dbuf4 = nullptr;
+        if (dbg4_on && a_in_tmem) {
+            if (!dbuf4) cudaMalloc(&dbuf4, 64 * 8);
+            cudaMemsetAsync(dbuf4, 0, 64 * 8, st);
+            P.dbg = dbuf4;
+        }
         {
             ProfScope prof("tc_chain_bwd2_kernel<gemm>", st);
             cudaLaunchConfig_t cfg = {};
@@ -645,6 +657,14 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
             cfg.attrs = attr; cfg.numAttrs = 1;
             if (cudaLaunchKernelEx(&cfg, kern, *maps, P) != cudaSuccess) { (void)check_launch("tc_chain_bwd2_kernel<gemm>"); return SDFG_ERR_CUDA; }
             if (int e = check_launch("tc_chain_bwd2_kernel<gemm>")) return e;
+        }
+        if (dbg4_on && a_in_tmem) {
+            cudaStreamSynchronize(st);
+            unsigned long long host[64];
+            cudaMemcpy(host, dbuf4, sizeof(host), cudaMemcpyDeviceToHost);
+            static int dumps = 0;
+            if (dumps++ == 2)
+                for (int k = 0; k < 19; k++) fprintf(stderr, "CHDBG %d %llu %llu\n", k / 8, host[2 * k], host[2 * k + 1]);
         }
         if (!g) return SDFG_OK;
         if (st_w != st) {                                               // see the note in the recompute chain below

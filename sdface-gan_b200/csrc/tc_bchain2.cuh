@@ -271,15 +271,28 @@ tc_chain_bwd2_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
                 if (STORE) mbar_arrive(&S.g_ready_st[c]);
             }
         };
+        // Per-row head gradients (d_rgb / d_sdf scalars) are fetched ONE UNIT AHEAD: as dependent loads at the start of a unit they
+        // exposed a full HBM round trip (~4000 clk, a fifth of the eikonal pass) before the first piece could be computed.
+        float rs_n[3] = {0.f, 0.f, 0.f}, ds_n = 0.f;
+        uint32_t i_dr = nL;                                            // the D layer whose epilogue adds a rank-1 term (at most one)
+        for (uint32_t i = 0; i < nL; i++)
+            if (P.layer[i].do_D && P.layer[i].d_rank) { i_dr = i; break; }
+        auto fetch_unit = [&](uint32_t u) {
+            const uint64_t row_n = (uint64_t)(u * CG + rank) * CH_TILE_M + r;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                if ((uint32_t)k < P.top_rank) rs_n[k] = ldg_early(P.top_rank_s + row_n * P.top_rank + k);
+            if (i_dr < nL) ds_n = ldg_early(P.layer[i_dr].d_rank_s + row_n);
+        };
+        if (u_begin < u_end) fetch_unit(u_begin);
         for (uint32_t u = u_begin; u < u_end; u++) {
             const uint32_t t = u * CG + rank;
             const uint64_t row = (uint64_t)t * CH_TILE_M + r;
             // ---------------- top: du_top = (rank terms + d_feat) * c_top
+            const float rs[3] = {gs * rs_n[0], gs * rs_n[1], gs * rs_n[2]};
+            const float ds_u = gs * ds_n;
+            if (u + 1 < u_end) fetch_unit(u + 1);
             {
-                float rs[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                for (int k = 0; k < 3; k++)
-                    if ((uint32_t)k < P.top_rank) rs[k] = gs * __ldg(P.top_rank_s + row * P.top_rank + k);
                 const uint32_t rvec_s = smem_u32(&S.vecs[P.top_vec0][0]);
 #pragma unroll 1
                 for (uint32_t c = 0; c < 4; c++) {
@@ -315,7 +328,7 @@ tc_chain_bwd2_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
                 if (!P.layer[i].do_D) continue;
                 const bool last = i + 1 == nL;                          // dh_0: no layer below inside the chain
                 const uint32_t d_rank = P.layer[i].d_rank;
-                const float ds = d_rank ? gs * __ldg(P.layer[i].d_rank_s + row) : 0.f;
+                const float ds = d_rank ? (i == i_dr ? ds_u : gs * __ldg(P.layer[i].d_rank_s + row)) : 0.f;
                 const uint32_t dvec_s = smem_u32(&S.vecs[P.layer[i].d_vec0][0]);
                 const uint32_t acc = ng & 1;
                 mbar_wait(&S.acc_full[acc], (ng >> 1) & 1);

@@ -10,11 +10,12 @@
 // of a 64 KB buffer and the weights through 2 x 16 KB stages (CTA pairs only: each CTA stages half of every weight chunk); both
 // are prefetched by dedicated producer threads, and a weight stall of up to (epilogue - GEMM) ~ 1000 clk per layer is free.
 //   shared memory: G_A, G_B 128 KB | sin ring 48 KB | weight ring 32 KB | sign planes 8 KB | barriers + head vectors 4.4 KB
-// Measured on B200 (N = 3.1 M): eikonal pass 1.95 -> 1.86 ms, backward with stores 3.13 -> 3.19 ms -- far from the ~1.7x the
-// latency picture promised.  With the GEMM fully concurrent the epilogue's chunks take ~1750 clk instead of ~1100: the MMA's
-// operand reads (12 KB per 128 x 256 x 16 step = 96 B/clk at the nominal rate) and the epilogue's ld/st.shared + TMA traffic share
-// the SM's 128 B/clk shared-memory port, so the two phases add up rather than overlap whatever the schedule.  The host uses this
-// kernel for the pass without stores only (field_tc.cu); the way forward is an A operand in tensor memory.
+// Measured on B200 (N = 3.1 M): eikonal pass 1.95 -> 1.83 ms, backward with stores 3.00 -> 3.11 ms -- far from the ~1.7x the
+// latency picture promised: with the GEMM fully concurrent the epilogue's pieces take longer (~1750 instead of ~1100 clk), so a layer
+// still costs about epilogue + GEMM.  It is not the shared-memory port (scripts/ubench/umma_rate.cu: the MMAs keep their nominal
+// 128 clk per step next to 70-100 B/clk of ld/st.shared traffic) and not the sin stream (the ring is full 88 % of the time); the
+// epilogue's own phases -- SFU-bound math a third, TMEM/mbarrier round trips the rest -- simply stretch when the tensor pipe is
+// busy.  The host uses this kernel for the pass without stores only (field_tc.cu).
 #pragma once
 #include "tc_bchain2.cuh"
 
@@ -253,8 +254,29 @@ tc_chain_bwd3_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
                 if (STORE) mbar_arrive(&S.g_ready_st[s][c]);
             }
         };
+        // Per-row head gradients (d_rgb / d_sdf scalars) of both tiles are fetched ONE PAIR AHEAD: as dependent loads at the start of
+        // a unit they exposed a full HBM round trip before the first piece could be computed (see tc_bchain2.cuh).
+        float rA[3] = {0.f, 0.f, 0.f}, rB[3] = {0.f, 0.f, 0.f}, dA = 0.f, dB = 0.f;
+        uint32_t i_dr = nL;                                            // the D layer whose epilogue adds a rank-1 term (at most one)
+        for (uint32_t i = 0; i < nL; i++)
+            if (P.layer[i].do_D && P.layer[i].d_rank) { i_dr = i; break; }
+        auto fetch_pair = [&](uint32_t p) {
+#pragma unroll
+            for (uint32_t s = 0; s < 2; s++) {
+                if (2 * p + s >= n_mine) break;
+                const uint64_t row_n = (uint64_t)((u_begin + 2 * p + s) * CG + rank) * CH_TILE_M + r;
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    if ((uint32_t)k < P.top_rank) (s ? rB[k] : rA[k]) = ldg_early(P.top_rank_s + row_n * P.top_rank + k);
+                if (i_dr < nL) (s ? dB : dA) = ldg_early(P.layer[i_dr].d_rank_s + row_n);
+            }
+        };
+        if (n_pairs) fetch_pair(0);
         for (uint32_t p = 0; p < n_pairs; p++) {
             const uint32_t n_act = (2 * p + 1 < n_mine) ? 2u : 1u;
+            const float rsA[3] = {gs * rA[0], gs * rA[1], gs * rA[2]}, rsB[3] = {gs * rB[0], gs * rB[1], gs * rB[2]};
+            const float dsA = gs * dA, dsB = gs * dB;
+            if (p + 1 < n_pairs) fetch_pair(p + 1);
             for (uint32_t e = 0; e < n_ev; e++)
                 for (uint32_t s = 0; s < n_act; s++) {
                     const uint32_t t = (u_begin + 2 * p + s) * CG + rank;
@@ -262,10 +284,7 @@ tc_chain_bwd3_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
                     const uint32_t n_g = p * n_ev + e;
                     if (e == 0) {
                         // ---------------- top: du_top = (rank terms + d_feat) * c_top
-                        float rs[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int k = 0; k < 3; k++)
-                            if ((uint32_t)k < P.top_rank) rs[k] = gs * __ldg(P.top_rank_s + row * P.top_rank + k);
+                        const float rs[3] = {s ? rsB[0] : rsA[0], s ? rsB[1] : rsA[1], s ? rsB[2] : rsA[2]};
                         const uint32_t rvec_s = smem_u32(&S.vecs[P.top_vec0][0]);
 #pragma unroll 1
                         for (uint32_t c = 0; c < 4; c++) {
@@ -300,7 +319,7 @@ tc_chain_bwd3_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
                         const uint32_t i = d_layer(e - 1);
                         const bool last = i + 1 == nL;                  // dh_0: no layer below inside the chain
                         const uint32_t d_rank = P.layer[i].d_rank;
-                        const float ds = d_rank ? gs * __ldg(P.layer[i].d_rank_s + row) : 0.f;
+                        const float ds = d_rank ? (i == i_dr ? (s ? dsB : dsA) : gs * __ldg(P.layer[i].d_rank_s + row)) : 0.f;
                         const uint32_t dvec_s = smem_u32(&S.vecs[P.layer[i].d_vec0][0]);
                         const uint32_t n_acc = p * n_gemm + (e - 1);
                         mbar_wait(&S.acc_full[s], n_acc & 1);

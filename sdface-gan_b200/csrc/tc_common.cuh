@@ -103,6 +103,13 @@ __device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, const vo
                  : "memory");
 }
 
+// global load issued HERE (volatile: not sunk to its first use) -- for values fetched an iteration ahead of their consumer
+__device__ __forceinline__ float ldg_early(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // L2 prefetch of a 2-D tile / of a contiguous range: no shared memory, no completion -- deepens the memory-level parallelism of a
 // stream whose shared-memory ring is too shallow to cover the HBM latency
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
@@ -253,6 +260,25 @@ __device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, 
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// the same with the A operand in TENSOR MEMORY (each CTA's own 128 rows: lane = row, one 32-bit column = two consecutive fp16 K
+// elements, low half first; a K = 16 step reads 8 columns starting at tmem_a): no shared-memory port traffic for A
+__device__ __forceinline__ void umma_f16_2cta_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// registers -> tensor memory, 32 lanes x 8 columns per warp (the warp's own lane quarter), and the wait that makes it visible
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrive on the barrier at this offset in every CTA of `mask` once all MMAs issued so far by this thread have completed
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),

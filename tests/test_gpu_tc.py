@@ -179,7 +179,7 @@ print("RESULT" + json.dumps(out))
 
 def test_tc_kernel_variants_agree():
     '''The fallback kernels must not rot: fused chains on CTA pairs (default), on single CTAs (SDFG_TC_CG=1), the recompute
-    backward chain (SDFG_TC_RECOMPUTE=1), the two-tiles-in-flight backward chain for every pass / for none (SDFG_TC_PP=2 / 0) and the per-layer kernels (SDFG_TC_CHAIN=0) are the same computation in the same number formats -- outputs and gradient norms of a
+    backward chain (SDFG_TC_RECOMPUTE=1), the two-tiles-in-flight backward chain for every pass / for none (SDFG_TC_PP=2 / 0), the eikonal pass with its A operand in tensor memory (SDFG_TC_TS=1) and the per-layer kernels (SDFG_TC_CHAIN=0) are the same computation in the same number formats -- outputs and gradient norms of a
     small training step agree to 1e-2 relative (different accumulation orders, atomics).  Env switches are read once per
     process, hence the subprocesses.'''
     import json, os, subprocess, sys
@@ -187,14 +187,14 @@ def test_tc_kernel_variants_agree():
     res = {}
     for name, env in (("pairs", {}), ("single", {"SDFG_TC_CG": "1"}), ("recompute", {"SDFG_TC_RECOMPUTE": "1"}),
                       ("recompute_single", {"SDFG_TC_RECOMPUTE": "1", "SDFG_TC_CG": "1"}), ("per_layer", {"SDFG_TC_CHAIN": "0"}),
-                      ("pingpong_all", {"SDFG_TC_PP": "2"}), ("pingpong_off", {"SDFG_TC_PP": "0"})):
+                      ("pingpong_all", {"SDFG_TC_PP": "2"}), ("pingpong_off", {"SDFG_TC_PP": "0"}), ("a_in_tmem", {"SDFG_TC_TS": "1"})):
         e = dict(os.environ, **env)
         r = subprocess.run([sys.executable, "-c", _VARIANT_SCRIPT % root], capture_output=True, text=True, env=e, timeout=300)
         assert r.returncode == 0, (name, r.stderr[-2000:])
         line = [l for l in r.stdout.splitlines() if l.startswith("RESULT")][-1]
         res[name] = json.loads(line[len("RESULT"):])
     ref = res["pairs"]
-    for name in ("single", "recompute", "recompute_single", "per_layer", "pingpong_all", "pingpong_off"):
+    for name in ("single", "recompute", "recompute_single", "per_layer", "pingpong_all", "pingpong_off", "a_in_tmem"):
         got = res[name]
         assert set(got) == set(ref)
         for k in ref:
