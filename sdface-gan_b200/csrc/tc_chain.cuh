@@ -96,6 +96,7 @@ struct ChainSmem {
     alignas(16) float gam[2][256];      // double-buffered per-layer FiLM constants: gamma, gamma*bias + beta
     float cst[2][256];
     float heads[4][256];                // row 0: first head layer (sdf), rows 1..3: second head layer (rgb)
+    float hbias[4];                     // their biases (a dependent global load per head layer and tile otherwise)
     float hx[3][CH_TILE_M][3];          // head partial sums of column sub-blocks 1..3
     float stg_g[CH_EPI_THREADS];        // cp.async staging of the NEXT layer's raw FiLM inputs: gamma (one slot per epilogue thread),
     float stg_b[256], stg_be[256];      // bias and beta (threads 256..511)
@@ -201,6 +202,7 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
         for (uint32_t i = 0; i < nL; i++) {
             const uint32_t nh = P.layer[i].nh;
             for (uint32_t k = threadIdx.x; k < nh * 256 && hrow + nh <= 4; k += blockDim.x) S.heads[hrow + k / 256][k % 256] = __ldg(P.layer[i].head_w + k);
+            if (threadIdx.x < nh && hrow + nh <= 4) S.hbias[hrow + threadIdx.x] = __ldg(P.layer[i].head_b + threadIdx.x);
             hrow += nh;
         }
         // zero the activation-side small tile once (its padding columns are never written again)
@@ -404,6 +406,12 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
             return act ? fmaf(gm, b, S.stg_be[fcol]) : b;
         };
         if (t_begin < t_end) film_fetch(0, (t_begin * CH_TILE_M) / P.rows_per_image);
+#ifdef SDFG_CHAIN_DEBUG
+        uint32_t ph[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; uint32_t tph = (uint32_t)clock();
+#define PHF(k) do { const uint32_t now_ = (uint32_t)clock(); ph[k] += now_ - tph; tph = now_; } while (0)
+#else
+#define PHF(k) do { } while (0)
+#endif
         for (uint32_t t = t_begin; t < t_end; t++) {
             const uint64_t row = (uint64_t)t * CH_TILE_M + r;
             const bool valid = row < P.M_total;
@@ -417,17 +425,22 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                 const bool do_sgn = COS && P.layer[i].sgn != nullptr;
                 const uint32_t acc = n & 1, use = n >> 1, tb = n & 1;
                 const uint32_t gam_s = smem_u32(&S.gam[tb][0]), cst_s = smem_u32(&S.cst[tb][0]);
+                PHF(9);
                 {   // publish this layer's FiLM constants (prefetched), then fetch the next layer's
+                    // (tables of all layers resident per image, without this per-layer barrier, measured 2-5 % SLOWER in training:
+                    // the time reappears as waiting for the accumulator, and the warps drift apart)
                     sts32((etid < 256 ? gam_s : cst_s) + fcol * 4, film_value(L_act));
                     named_bar_sync(1, CH_EPI_THREADS);
                     if (i + 1 < nL) film_fetch(i + 1, img);
                     else if (t + 1 < t_end) film_fetch(0, ((t + 1) * CH_TILE_M) / P.rows_per_image);
                 }
+                PHF(0);
                 const uint32_t heads_s = smem_u32(&S.heads[hrow][0]);
                 float hacc[3] = {0.f, 0.f, 0.f};
                 if (threadIdx.x == 0) CH_DBG(1, 300 + i * 16);
                 mbar_wait(&S.acc_full[acc], use & 1);
                 tc_fence_after();
+                PHF(1);
                 if (threadIdx.x == 0) CH_DBG(1, 400 + i * 16);
                 const uint32_t taddr = tmem_base + ((q * 32) << 16) + acc * 256 + sb * 16;
                 uint32_t raw[2][16];
@@ -436,6 +449,7 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                 for (uint32_t c = 0; c < 4; c++) {
                     const uint32_t col = c * 64 + sb * 16;
                     tmem_ld_wait16(raw[c & 1]);
+                    PHF(2);
                     if (c < 3) tmem_ld16_issue(taddr + (c + 1) * 64, raw[(c + 1) & 1]);
                     float v[16];
 #pragma unroll
@@ -478,16 +492,20 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                             }
                         }
                     }
+                    PHF(3);
                     if (L_to_act) {
                         const uint4 h0 = make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
                         const uint4 h1 = make_uint4(pack_f16(v[8], v[9]), pack_f16(v[10], v[11]), pack_f16(v[12], v[13]), pack_f16(v[14], v[15]));
                         if (SAVE) mbar_wait(&S.st_done[c], (stgen & 1) ^ 1);   // the previous contents of the chunk have been stored
+                        PHF(4);
                         const uint32_t chunk = act_row + c * CH_CHUNK_BYTES;
                         sts128(chunk + u0, h0);
                         sts128(chunk + u1, h1);
                         fence_proxy_async();
+                        PHF(5);
                         __syncwarp();
                         if (lane == 0) mbar_arrive(i + 1 == nL ? &S.fin_ready[c] : &S.act_ready[c]);
+                        PHF(6);
                         if (threadIdx.x == 0) CH_DBG(1, 500 + i * 16 + c);
                         if (lane == 0 && warp != 0) CH_DBG(4 + warp, 500 + i * 16 + c);
                     }
@@ -497,6 +515,7 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
                         for (int j = 0; j < 4; j++) dst[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
                     }
                 }
+                PHF(7);
                 if (L_to_act) stgen++;
                 // every TMEM read of this layer has completed (wait::ld): hand the accumulator back to the MMA thread
                 tc_fence_before();
@@ -507,18 +526,22 @@ tc_chain_fwd_kernel(const __grid_constant__ ChainMaps maps, const __grid_constan
 #pragma unroll
                         for (int hd = 0; hd < 3; hd++) S.hx[sb - 1][r][hd] = hacc[hd];
                     }
-                    named_bar_sync(2, CH_EPI_THREADS);
+                    named_bar_sync(2 + q, 128);                       // only the four warps that share these rows (one per column sub-block)
                     if (sb == 0 && valid) {
                         float* oh = P.layer[i].out_head;
-                        const float* hb = P.layer[i].head_b;
 #pragma unroll
                         for (int hd = 0; hd < 3; hd++)
-                            if ((uint32_t)hd < L_nh) oh[row * L_nh + hd] = hacc[hd] + S.hx[0][r][hd] + S.hx[1][r][hd] + S.hx[2][r][hd] + __ldg(hb + hd);
+                            if ((uint32_t)hd < L_nh) oh[row * L_nh + hd] = hacc[hd] + S.hx[0][r][hd] + S.hx[1][r][hd] + S.hx[2][r][hd] + S.hbias[hrow + hd];
                     }
                     hrow += L_nh;
                 }
             }
         }
+#ifdef SDFG_CHAIN_DEBUG
+        PHF(8);
+        if (threadIdx.x == 0 && P.dbg && blockIdx.x == 0)
+            for (int k = 0; k < 10; k++) { P.dbg[4 * 2048 + 2 * k] = 1000 + k; P.dbg[4 * 2048 + 2 * k + 1] = ph[k] + 1; }      // role 4 = 4 + warp 0: unused
+#endif
     }
     // teardown: the epilogue consumed the last accumulator, so every MMA and TMA load issued has completed
     tc_fence_before();
