@@ -168,8 +168,8 @@ typedef struct {
 uint64_t sdfg_field_workspace_bytes(const sdfg_field_params* p, uint64_t N, int save_for_backward, int precision);
 
 #define SDFG_PRECISION_FP32 0   /* SIMT fp32 FMA path: parity <= 1e-3 max-abs with the reference fp32 path */
-#define SDFG_PRECISION_TC16 1   /* tcgen05 path: bf16 operands, fp32 accumulate in TMEM (sm_100a); needs width == 256 and
-                                   samples_per_image % 128 == 0 */
+#define SDFG_PRECISION_TC16 1   /* tcgen05 path: fp16 operands (activations, weights, loss-scaled gradients), fp32 accumulate in
+                                   TMEM (sm_100a); needs width == 256 and samples_per_image % 128 == 0 */
 
 /* forward.  x_in [N,in_dim]; view_feat [N/S, view_dim]; out_sdf [N]; out_rgb [N,3] (NULL ok); out_feat [N,W] (NULL ok);
  * workspace as sized above (kept by the caller until backward). */
@@ -201,14 +201,29 @@ int sdfg_field_backward_2s(const sdfg_field_params* p, const sdfg_field_grads* g
                            uint64_t N, const float* d_sdf, const float* d_rgb, const float* d_feat, const float* out_feat,
                            const void* workspace, void* scratch, float* d_x_in, int precision, void* stream, void* wgrad_stream);
 
-/* probe of the tcgen05 pipeline for the parity tests: out[M,N] (fp32) = bf16(x)[M,K] * bf16(w)[N,K]^T with fp32 accumulation.
+/* two-call variant (the two-stream variant's ordering on ONE stream): `phases` selects SDFG_BWD_CHAIN (loss scale, gradient chain
+ * through the layers -> d_x_in, and the gradient tiles the second phase reads from `scratch`), SDFG_BWD_WGRAD (parameter
+ * gradients into g) or both.  A data-parallel caller runs CHAIN, enqueues the hash-table scatter of d_x_in, starts the
+ * all-reduce of the table gradient and then calls WGRAD with the same arguments: the exchange overlaps the weight-gradient
+ * kernels, and scatter and contractions never contend for L2.  `g` must be the same in both calls (NULL = no parameter
+ * gradients at all).  Paths whose two halves interleave (fp32 path, per-layer tensor-core kernels) do all their work in the call
+ * that carries SDFG_BWD_CHAIN and nothing in a WGRAD-only call. */
+#define SDFG_BWD_CHAIN 1
+#define SDFG_BWD_WGRAD 2
+#define SDFG_BWD_BOTH 3
+int sdfg_field_backward_phase(const sdfg_field_params* p, const sdfg_field_grads* g, const float* x_in, const float* view_feat,
+                              uint64_t N, const float* d_sdf, const float* d_rgb, const float* d_feat, const float* out_feat,
+                              const void* workspace, void* scratch, float* d_x_in, int precision, int phases, void* stream);
+
+/* probe of the tcgen05 pipeline for the parity tests: out[M,N] (fp32) = fp16(x)[M,K] * fp16(w)[N,K]^T with fp32 accumulation.
  * N multiple of 32 in 32..256, K <= 320. */
 uint64_t sdfg_tc_linear_probe_workspace_bytes(uint32_t M, uint32_t K, uint32_t N);
 int sdfg_tc_linear_probe(const float* x, const float* w, float* out, uint32_t M, uint32_t K, uint32_t N, void* workspace,
                          void* stream);
 
 /* probe of the sample-axis (MN-major) weight-gradient contraction: G [B, 256, *ldg] (pre-zeroed, B = N / rows_per_image)
- * G[b,j,k<Kx] = sum_{n in image b} bf16(dz)[n,j] * x16(x)[n,k];  G[b,j,*ones_col] = sum_n bf16(dz)[n,j].  x_fmt: 0 fp16, 1 bf16.
+ * G[b,j,k<Kx] = sum_{n in image b} x16(dz)[n,j] * x16(x)[n,k];  G[b,j,*ones_col] = sum_n x16(dz)[n,j].  x_fmt (both operands): 0 fp16
+ * (what the backward uses), 1 bf16.
  * workspace >= 2*N*(256 + Kx + 8) + 512 bytes. */
 int sdfg_tc_wgrad_probe(const float* dz, const float* x, float* G, uint32_t N, uint32_t Kx, uint32_t rows_per_image, uint32_t x_fmt,
                         uint32_t* ldg, uint32_t* ones_col, void* workspace, void* stream);

@@ -3,7 +3,7 @@
 Import through the alias module at the repo root (``import sdface_gan_b200``) or
 ``importlib.import_module("sdface-gan_b200")``.  See DESIGN.md for the path and INTEGRATION.md for the drop-in boundary.
 """
-from . import _lib, distributed, ops  # noqa: F401
+from . import _lib, compat_backend, distributed, ops  # noqa: F401
 from .gridencoder import GridEncoder, grid_encode  # noqa: F401
 from .shencoder import SHEncoder, sh_encode  # noqa: F401
 from .sdf_model import (FCGenerator, FiLMSiren, Generator, LinearLayer, MappingLinear, NGPSIRENGenerator, SirenGenerator,  # noqa: F401

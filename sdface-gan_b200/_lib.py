@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsdfg.so")
 SDFG_MAX_FILM = 9
 LAYOUT_NLC, LAYOUT_LNC = 0, 1
 PRECISION_FP32, PRECISION_TC16 = 0, 1
+BWD_CHAIN, BWD_WGRAD, BWD_BOTH = 1, 2, 3
 
 c_f = ctypes.POINTER(ctypes.c_float)
 vp = ctypes.c_void_p
@@ -59,6 +60,8 @@ PROTOTYPES = {
     "sdfg_field_forward_h": (i32, [ctypes.POINTER(FieldParams), vp, vp, u64, vp, vp, vp, vp, vp]),
     "sdfg_field_backward": (i32, [ctypes.POINTER(FieldParams), ctypes.POINTER(FieldGrads), vp, vp, u64, vp, vp, vp, vp, vp, vp,
                                   vp, i32, vp]),
+    "sdfg_field_backward_phase": (i32, [ctypes.POINTER(FieldParams), ctypes.POINTER(FieldGrads), vp, vp, u64, vp, vp, vp, vp, vp, vp,
+                                        vp, i32, i32, vp]),
     "sdfg_field_backward_2s": (i32, [ctypes.POINTER(FieldParams), ctypes.POINTER(FieldGrads), vp, vp, u64, vp, vp, vp, vp, vp, vp,
                                      vp, i32, vp, vp]),
     "sdfg_tc_linear_probe_workspace_bytes": (u64, [u32, u32, u32]),
@@ -82,19 +85,26 @@ def _declare(lib):
     return lib
 
 
+def _build_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_sdfg_build", os.path.join(_HERE, "_build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def load(build_if_missing=True):
-    """Return the loaded library (building it in-tree first if necessary).  Raises RuntimeError when impossible."""
+    """Return the loaded library.  A missing OR STALE binary (lib/libsdfg.stamp does not match the hash of csrc/, include/sdfg.h
+    and the build flags) is rebuilt in-tree first -- under a file lock, so the ranks of one job build it once -- and refused
+    with a RuntimeError when that is impossible (no nvcc) or not allowed (build_if_missing=False)."""
     global _lib
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
+        mod = _build_module()
+        if mod.is_stale():
             if not build_if_missing:
-                raise RuntimeError("libsdfg.so is missing (%s); run `python sdface-gan_b200/_build.py`" % LIB_PATH)
-            import importlib.util
-            spec = importlib.util.spec_from_file_location("_sdfg_build", os.path.join(_HERE, "_build.py"))
-            mod = importlib.util.module_from_spec(spec)
-            spec.loader.exec_module(mod)
+                raise RuntimeError("libsdfg.so is missing or stale (%s); run `python sdface-gan_b200/_build.py`" % LIB_PATH)
             mod.build()
         try:
             _lib = _declare(ctypes.CDLL(LIB_PATH))

@@ -51,6 +51,20 @@ extern "C" int sdfg_field_backward(const sdfg_field_params* p, const sdfg_field_
     return set_error(SDFG_ERR_UNSUPPORTED, "field_backward: unknown precision %d", precision);
 }
 
+extern "C" int sdfg_field_backward_phase(const sdfg_field_params* p, const sdfg_field_grads* g, const float* x_in, const float* view_feat,
+                                         uint64_t N, const float* d_sdf, const float* d_rgb, const float* d_feat, const float* out_feat,
+                                         const void* workspace, void* scratch, float* d_x_in, int precision, int phases, void* stream) {
+    SDFG_REQUIRE((phases & SDFG_BWD_BOTH) && !(phases & ~SDFG_BWD_BOTH), SDFG_ERR_INVALID, "field_backward_phase: phases must be CHAIN, WGRAD or both");
+    if (precision != SDFG_PRECISION_TC16) {      // the fp32 path interleaves both halves: all of it runs with the CHAIN phase
+        if (!(phases & SDFG_BWD_CHAIN)) return field_check_params(p, N);
+        return sdfg_field_backward(p, g, x_in, view_feat, N, d_sdf, d_rgb, d_feat, out_feat, workspace, scratch, d_x_in, precision, stream);
+    }
+    if (int e = field_check_params(p, N)) return e;
+    if (N == 0) return SDFG_OK;
+    SDFG_REQUIRE(x_in && workspace && scratch, SDFG_ERR_INVALID, "field_backward: null pointer");
+    return field_backward_tc(p, g, x_in, view_feat, N, d_sdf, d_rgb, d_feat, workspace, scratch, d_x_in, (cudaStream_t)stream, (cudaStream_t)stream, phases);
+}
+
 extern "C" int sdfg_field_backward_2s(const sdfg_field_params* p, const sdfg_field_grads* g, const float* x_in, const float* view_feat,
                                       uint64_t N, const float* d_sdf, const float* d_rgb, const float* d_feat, const float* out_feat,
                                       const void* workspace, void* scratch, float* d_x_in, int precision, void* stream, void* wgrad_stream) {

@@ -21,10 +21,8 @@
 #include <vector>
 
 #include "field.cuh"
-#include "tc_bchain.cuh"
 #include "tc_bchain2.cuh"
 #include "tc_bchain3.cuh"
-#include "tc_bchain4.cuh"
 #include "tc_chain.cuh"
 #include "tc_layer.cuh"
 #include "tc_wgrad.cuh"
@@ -542,12 +540,13 @@ uint64_t field_backward_scratch_bytes_tc(const sdfg_field_params* p, uint64_t N)
 
 int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, const float* x_in, const float* view_feat, uint64_t N,
                       const float* d_sdf, const float* d_rgb, const float* d_feat, const void* workspace, void* scratch, float* d_x_in,
-                      cudaStream_t st, cudaStream_t st_w) {
+                      cudaStream_t st, cudaStream_t st_w, int phases) {
     (void)x_in; (void)view_feat;
     if (int e = check_tc(p, N)) return e;
     SDFG_REQUIRE(d_sdf || d_rgb || d_feat, SDFG_ERR_INVALID, "field_backward: no output gradient given");
     SDFG_REQUIRE(!d_x_in || (p->has_input_linear && p->in_dim % 32 == 0), SDFG_ERR_UNSUPPORTED,
                  "tc field_backward: d_x_in needs an input_linear layer and in_dim %% 32 == 0");
+    SDFG_REQUIRE(phases & SDFG_BWD_BOTH, SDFG_ERR_INVALID, "field_backward: no phase requested");
     const TcLayout L = tc_layout(p, N, 1);
     const TcScratch SC = tc_scratch(p, N);
     const uint8_t* ws = (const uint8_t*)workspace;
@@ -559,7 +558,6 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
     h16* WGT = (h16*)(sc + SC.off_wgt[0]);
     float* G = (float*)(sc + SC.off_g);
     float* gscale = (float*)(sc + SC.off_scale) + 2;      // {s, 1/s}; [0] of the slot holds the absmax bits
-    if (int e = compute_loss_scale(d_sdf, N, d_rgb, N * 3, d_feat, N * 256, (uint32_t*)(sc + SC.off_scale), gscale, st)) return e;
     const uint32_t W = L.W, nf = L.n_film;
     const uint32_t B = (uint32_t)ceil_div<uint64_t>(N, p->samples_per_image);
     const int64_t gstride = (int64_t)(nf + 1) * W;
@@ -568,111 +566,98 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
     auto layer_K = [&](uint32_t l) { return l == nf ? L.Kp_v : ((l == 0 && !p->has_input_linear) ? L.Kp_in : W); };      // padded
     auto layer_Kx = [&](uint32_t l) { return l == nf ? W + p->view_dim : ((l == 0 && !p->has_input_linear) ? p->in_dim : W); };
 
-    static const bool recompute_env = getenv("SDFG_TC_RECOMPUTE") != nullptr;      // force the recompute chain (tc_bchain.cuh)
     const bool has_views = d_rgb || d_feat;
-    if (chain_enabled() && bchain_eligible(p, d_x_in) && chain_eligible(p, true) && !recompute_env) {
-        // ---------------------------------------------------------------- backward chain on the saved cos tiles (tc_bchain2.cuh)
-        // (chain_eligible(with views): whatever outputs the forward produced, it was the fused chain -- the one that saves cos(gamma u + c))
+    if (chain_enabled() && bchain_eligible(p, d_x_in) && chain_eligible(p, true)) {
+        // ---------------------------------------------------------------- backward chain on the saved activations + sign planes (tc_bchain2.cuh)
+        // (chain_eligible(with views): whatever outputs the forward produced, it was the fused chain -- the one that saves the sign planes)
         const bool store = g != nullptr;
-        const bool need_dh0 = p->has_input_linear && (d_x_in || (g && g->input_w));
-        static const int cg_env = []() { const char* e = getenv("SDFG_TC_CG"); return e ? atoi(e) : 2; }();
-        const int cg = (cg_env == 2 && spi % 256 == 0 && (N / tc::CH_TILE_M) % 2 == 0 && (!p->has_input_linear || p->in_dim % 32 == 0)) ? 2 : 1;
-        const uint32_t wrows = 256 / cg;
-        std::unique_ptr<tc::B2ChainMaps> maps(new tc::B2ChainMaps);
-        tc::B2ChainParams P = {};
-        P.M_total = (uint32_t)N; P.rows_per_image = spi; P.gscale = gscale;
-        P.vecs[0] = p->sigma_w;
-        if (p->rgb_w) { P.vecs[1] = p->rgb_w; P.vecs[2] = p->rgb_w + W; P.vecs[3] = p->rgb_w + 2 * W; }
-        uint32_t nl = 0;
-        auto add_layer = [&](uint32_t l) -> int {                      // FiLM layer l (nf = views) becomes chain layer nl
-            tc::B2Layer& Y = P.layer[nl];
-            Y.do_D = l == nf ? 1u : ((l > 0 || need_dh0) ? 1u : 0u);
-            // the layer's OUTPUT sin(gamma u + c) as saved for the next layer / the rgb head, and the sign masks of its cos
-            const h16* sin_l = l == nf ? (const h16*)(ws + L.off_hv) : A(l + 1);
-            const uint64_t ld_sin = (l == nf || l + 1 != nf) ? W : L.Kp_v;
-            if (int e = make_tensor_map_16(&maps->c[nl], sin_l, N, W, ld_sin, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
-            Y.sgn = ws + L.off_c[l];
-            if (Y.do_D) {
-                h16* wgt = (h16*)(sc + SC.off_wgt[l]);
-                wgt_kernel<<<dim3(W, B), 256, 0, st>>>(p->film_w[l], layer_Kx(l), p->gamma + (size_t)l * W, gstride, wgt, W, B);
-                if (int e = check_launch("wgt_kernel")) return e;
-                if (int e = make_tensor_map_16(&maps->wgt[nl], wgt, (uint64_t)B * W, W, W, wrows, 64, tc::FMT_F16)) return e;
+        if (phases & SDFG_BWD_CHAIN) {
+            if (int e = compute_loss_scale(d_sdf, N, d_rgb, N * 3, d_feat, N * 256, (uint32_t*)(sc + SC.off_scale), gscale, st)) return e;
+            const bool need_dh0 = p->has_input_linear && (d_x_in || (g && g->input_w));
+            static const int cg_env = []() { const char* e = getenv("SDFG_TC_CG"); return e ? atoi(e) : 2; }();
+            const int cg = (cg_env == 2 && spi % 256 == 0 && (N / tc::CH_TILE_M) % 2 == 0 && (!p->has_input_linear || p->in_dim % 32 == 0)) ? 2 : 1;
+            const uint32_t wrows = 256 / cg;
+            std::unique_ptr<tc::B2ChainMaps> maps(new tc::B2ChainMaps);
+            tc::B2ChainParams P = {};
+            P.M_total = (uint32_t)N; P.rows_per_image = spi; P.gscale = gscale;
+            P.vecs[0] = p->sigma_w;
+            if (p->rgb_w) { P.vecs[1] = p->rgb_w; P.vecs[2] = p->rgb_w + W; P.vecs[3] = p->rgb_w + 2 * W; }
+            uint32_t nl = 0;
+            auto add_layer = [&](uint32_t l) -> int {                      // FiLM layer l (nf = views) becomes chain layer nl
+                tc::B2Layer& Y = P.layer[nl];
+                Y.do_D = l == nf ? 1u : ((l > 0 || need_dh0) ? 1u : 0u);
+                // the layer's OUTPUT sin(gamma u + c) as saved for the next layer / the rgb head, and the sign masks of its cos
+                const h16* sin_l = l == nf ? (const h16*)(ws + L.off_hv) : A(l + 1);
+                const uint64_t ld_sin = (l == nf || l + 1 != nf) ? W : L.Kp_v;
+                if (int e = make_tensor_map_16(&maps->c[nl], sin_l, N, W, ld_sin, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
+                Y.sgn = ws + L.off_c[l];
+                if (Y.do_D) {
+                    h16* wgt = (h16*)(sc + SC.off_wgt[l]);
+                    wgt_kernel<<<dim3(W, B), 256, 0, st>>>(p->film_w[l], layer_Kx(l), p->gamma + (size_t)l * W, gstride, wgt, W, B);
+                    if (int e = check_launch("wgt_kernel")) return e;
+                    if (int e = make_tensor_map_16(&maps->wgt[nl], wgt, (uint64_t)B * W, W, W, wrows, 64, tc::FMT_F16)) return e;
+                }
+                if (store)
+                    if (int e = make_tensor_map_16(&maps->dz[nl], (h16*)(sc + SC.off_dz[l]), N, W, W, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
+                nl++;
+                return SDFG_OK;
+            };
+            if (has_views) {
+                if (int e = add_layer(nf)) return e;
+                P.top_rank = d_rgb ? 3 : 0; P.top_vec0 = 1; P.top_rank_s = d_rgb; P.top_dfeat = d_feat;
+                P.layer[0].d_rank = d_sdf ? 1 : 0; P.layer[0].d_vec0 = 0; P.layer[0].d_rank_s = d_sdf;
+            } else {
+                P.top_rank = 1; P.top_vec0 = 0; P.top_rank_s = d_sdf;
             }
-            if (store)
-                if (int e = make_tensor_map_16(&maps->dz[nl], (h16*)(sc + SC.off_dz[l]), N, W, W, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
-            nl++;
-            return SDFG_OK;
-        };
-        if (has_views) {
-            if (int e = add_layer(nf)) return e;
-            P.top_rank = d_rgb ? 3 : 0; P.top_vec0 = 1; P.top_rank_s = d_rgb; P.top_dfeat = d_feat;
-            P.layer[0].d_rank = d_sdf ? 1 : 0; P.layer[0].d_vec0 = 0; P.layer[0].d_rank_s = d_sdf;
-        } else {
-            P.top_rank = 1; P.top_vec0 = 0; P.top_rank_s = d_sdf;
+            for (int l = (int)nf - 1; l >= 0; l--)
+                if (int e = add_layer((uint32_t)l)) return e;
+            P.n_layers = nl;
+            if (need_dh0) {
+                P.has_in = 1; P.in_dim = p->in_dim; P.d_x_in = d_x_in;
+                h16* wgt_in = (h16*)(sc + SC.off_wgt_in);
+                wgt_kernel<<<dim3(p->in_dim, 1), 256, 0, st>>>(p->input_w, p->in_dim, nullptr, 0, wgt_in, p->in_dim, 1);
+                if (int e = check_launch("wgt_kernel")) return e;
+                if (int e = make_tensor_map_16(&maps->wgt_in, wgt_in, p->in_dim, W, W, p->in_dim / cg, 64, tc::FMT_F16)) return e;
+                if (store)
+                    if (int e = make_tensor_map_16(&maps->dh0, DH, N, W, W, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
+            }
+            P.n_units = (uint32_t)(N / (tc::CH_TILE_M * cg));
+            const uint32_t groups = std::min<uint32_t>((uint32_t)sm_count() / cg, P.n_units);
+            P.units_per_cta = ceil_div<uint32_t>(P.n_units, groups);
+            const uint32_t grid = cg * ceil_div<uint32_t>(P.n_units, P.units_per_cta);
+            // two tiles in flight per CTA (tc_bchain3.cuh): measured 4-5 % faster for the pass without stores (eikonal), 2 % slower with
+            // them.  SDFG_TC_PP=0 never, =2 always.
+            static const int pp_env = []() { const char* e = getenv("SDFG_TC_PP"); return e ? atoi(e) : 1; }();
+            const bool pingpong = cg == 2 && (pp_env == 2 || (pp_env == 1 && !store));
+            const uint32_t smem = pingpong ? tc::bchain3_smem_bytes() : tc::bchain2_smem_bytes(cg);
+            typedef void (*b2kern_t)(const tc::B2ChainMaps, const tc::B2ChainParams);
+            const b2kern_t kern = pingpong ? (store ? (b2kern_t)tc::tc_chain_bwd3_kernel<true> : (b2kern_t)tc::tc_chain_bwd3_kernel<false>)
+                                : cg == 2  ? (store ? (b2kern_t)tc::tc_chain_bwd2_kernel<true, 2> : (b2kern_t)tc::tc_chain_bwd2_kernel<false, 2>)
+                                           : (store ? (b2kern_t)tc::tc_chain_bwd2_kernel<true, 1> : (b2kern_t)tc::tc_chain_bwd2_kernel<false, 1>);
+            if (int e = optin_smem((const void*)kern, smem, "tc_chain_bwd2_kernel")) return e;
+            {
+                ProfScope prof("tc_chain_bwd2_kernel<gemm>", st);
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = (unsigned)cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                if (cudaLaunchKernelEx(&cfg, kern, *maps, P) != cudaSuccess) { (void)check_launch("tc_chain_bwd2_kernel<gemm>"); return SDFG_ERR_CUDA; }
+                if (int e = check_launch("tc_chain_bwd2_kernel<gemm>")) return e;
+            }
         }
-        for (int l = (int)nf - 1; l >= 0; l--)
-            if (int e = add_layer((uint32_t)l)) return e;
-        P.n_layers = nl;
-        if (need_dh0) {
-            P.has_in = 1; P.in_dim = p->in_dim; P.d_x_in = d_x_in;
-            h16* wgt_in = (h16*)(sc + SC.off_wgt_in);
-            wgt_kernel<<<dim3(p->in_dim, 1), 256, 0, st>>>(p->input_w, p->in_dim, nullptr, 0, wgt_in, p->in_dim, 1);
-            if (int e = check_launch("wgt_kernel")) return e;
-            if (int e = make_tensor_map_16(&maps->wgt_in, wgt_in, p->in_dim, W, W, p->in_dim / cg, 64, tc::FMT_F16)) return e;
-            if (store)
-                if (int e = make_tensor_map_16(&maps->dh0, DH, N, W, W, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
-        }
-        P.n_units = (uint32_t)(N / (tc::CH_TILE_M * cg));
-        const uint32_t groups = std::min<uint32_t>((uint32_t)sm_count() / cg, P.n_units);
-        P.units_per_cta = ceil_div<uint32_t>(P.n_units, groups);
-        const uint32_t grid = cg * ceil_div<uint32_t>(P.n_units, P.units_per_cta);
-        // two tiles in flight per CTA (tc_bchain3.cuh): measured 4-5 % faster for the pass without stores (eikonal), 2 % slower with
-        // them.  SDFG_TC_PP=0 never, =2 always.
-        static const int pp_env = []() { const char* e = getenv("SDFG_TC_PP"); return e ? atoi(e) : 1; }();
-        // SDFG_TC_TS=1: the pass without stores with the A operand in tensor memory (tc_bchain4.cuh; measured equal to the default)
-        static const bool ts_env = []() { const char* e = getenv("SDFG_TC_TS"); return e ? atoi(e) != 0 : false; }();
-        const bool a_in_tmem = cg == 2 && !store && ts_env && pp_env != 2;
-        const bool pingpong = !a_in_tmem && cg == 2 && (pp_env == 2 || (pp_env == 1 && !store));
-        const uint32_t smem = a_in_tmem ? tc::bchain4_smem_bytes() : pingpong ? tc::bchain3_smem_bytes() : tc::bchain2_smem_bytes(cg);
-        typedef void (*b2kern_t)(const tc::B2ChainMaps, const tc::B2ChainParams);
-        const b2kern_t kern = a_in_tmem ? (b2kern_t)tc::tc_chain_bwd4_kernel
-                            : pingpong ? (store ? (b2kern_t)tc::tc_chain_bwd3_kernel<true> : (b2kern_t)tc::tc_chain_bwd3_kernel<false>)
-                            : cg == 2  ? (store ? (b2kern_t)tc::tc_chain_bwd2_kernel<true, 2> : (b2kern_t)tc::tc_chain_bwd2_kernel<false, 2>)
-                                       : (store ? (b2kern_t)tc::tc_chain_bwd2_kernel<true, 1> : (b2kern_t)tc::tc_chain_bwd2_kernel<false, 1>);
-        if (int e = optin_smem((const void*)kern, smem, "tc_chain_bwd2_kernel")) return e;
-        static const bool dbg4_on = getenv("SDFG_BCHAIN_DBG") != nullptr;   // debugging aid (-DSDFG_CHAIN_DEBUG build): phase sums of CTA 0, eikonal pass
-        static unsigned long long* dbuf4 = nullptr;
-        if (dbg4_on && a_in_tmem) {
-            if (!dbuf4) cudaMalloc(&dbuf4, 64 * 8);
-            cudaMemsetAsync(dbuf4, 0, 64 * 8, st);
-            P.dbg = dbuf4;
-        }
-        {
-            ProfScope prof("tc_chain_bwd2_kernel<gemm>", st);
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = (unsigned)cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr; cfg.numAttrs = 1;
-            if (cudaLaunchKernelEx(&cfg, kern, *maps, P) != cudaSuccess) { (void)check_launch("tc_chain_bwd2_kernel<gemm>"); return SDFG_ERR_CUDA; }
-            if (int e = check_launch("tc_chain_bwd2_kernel<gemm>")) return e;
-        }
-        if (dbg4_on && a_in_tmem) {
-            cudaStreamSynchronize(st);
-            unsigned long long host[64];
-            cudaMemcpy(host, dbuf4, sizeof(host), cudaMemcpyDeviceToHost);
-            static int dumps = 0;
-            if (dumps++ == 2)
-                for (int k = 0; k < 19; k++) fprintf(stderr, "CHDBG %d %llu %llu\n", k / 8, host[2 * k], host[2 * k + 1]);
-        }
-        if (!g) return SDFG_OK;
-        if (st_w != st) {                                               // see the note in the recompute chain below
+        if (!g || !(phases & SDFG_BWD_WGRAD)) return SDFG_OK;
+        // ---- parameter gradients from the stored du tiles (sample-axis contractions) and the fp32 head gradients.  They only depend
+        // on the chain's outputs, and the caller's next step (hash-grid scatter of d_x_in) does not depend on them: a caller may run
+        // them as a second call (phases = SDFG_BWD_WGRAD) after it has enqueued the scatter and started the table-gradient exchange,
+        // or on a second stream (st_w).
+        if (st_w != st) {
             cudaEvent_t ev;
             if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: event");
             cudaEventRecord(ev, st);
             cudaStreamWaitEvent(st_w, ev, 0);
-            cudaEventDestroy(ev);
+            cudaEventDestroy(ev);                                      // released once the wait has consumed it
             st = st_w;
         }
         if (has_views && g->rgb_w && d_rgb) {
@@ -702,144 +687,12 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         }
         return SDFG_OK;
     }
-    if (chain_enabled() && bchain_eligible(p, d_x_in)) {
-        // ---------------------------------------------------------------- fused backward chain (tc_bchain.cuh)
-        const bool views = d_rgb || d_feat;
-        const bool store = g != nullptr;
-        const bool need_dh0 = p->has_input_linear && (d_x_in || (g && g->input_w));
-        tc::BChainMaps* maps = new tc::BChainMaps;                     // 5 KB of tensor maps: off the stack
-        std::unique_ptr<tc::BChainMaps> maps_guard(maps);
-        tc::BChainParams P = {};
-        // CTA pairs (cta_group::2) when two adjacent tiles always belong to one image and the input stage splits evenly
-        static const int cg_env = []() { const char* e = getenv("SDFG_TC_CG"); return e ? atoi(e) : 2; }();
-        const int cg = (cg_env == 2 && spi % 256 == 0 && (N / tc::CH_TILE_M) % 2 == 0 && (!p->has_input_linear || p->in_dim % 32 == 0)) ? 2 : 1;
-        const uint32_t wrows = 256 / cg;
-        P.M_total = (uint32_t)N; P.rows_per_image = spi;
-        P.gamma = p->gamma; P.beta = p->beta; P.gstride = gstride; P.gscale = gscale;
-        P.vecs[0] = p->sigma_w;
-        if (p->rgb_w) { P.vecs[1] = p->rgb_w; P.vecs[2] = p->rgb_w + W; P.vecs[3] = p->rgb_w + 2 * W; }
-        uint32_t nl = 0;
-        auto add_layer = [&](uint32_t l) -> int {                      // FiLM layer l (nf = views) becomes chain layer nl
-            tc::BLayer& Y = P.layer[nl];
-            const uint32_t Kp = layer_K(l);
-            Y.nk = ceil_div<uint32_t>(Kp, 64);
-            Y.last_ksteps = ceil_div<uint32_t>(Kp - (Y.nk - 1) * 64, 16);
-            Y.film = l; Y.bias = p->film_b[l];
-            Y.do_D = l == nf ? 1u : ((l > 0 || need_dh0) ? 1u : 0u);
-            if (int e = make_tensor_map_16(&maps->a[nl], A(l), N, Kp, Kp, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
-            if (int e = make_tensor_map_16(&maps->w[nl], Wb(1 + l), W, Kp, Kp, wrows, 64, tc::FMT_F16)) return e;
-            if (Y.do_D) {
-                h16* wgt = (h16*)(sc + SC.off_wgt[l]);
-                wgt_kernel<<<dim3(W, B), 256, 0, st>>>(p->film_w[l], layer_Kx(l), p->gamma + (size_t)l * W, gstride, wgt, W, B);
-                if (int e = check_launch("wgt_kernel")) return e;
-                if (int e = make_tensor_map_16(&maps->wgt[nl], wgt, (uint64_t)B * W, W, W, wrows, 64, tc::FMT_F16)) return e;
-            }
-            if (store)
-                if (int e = make_tensor_map_16(&maps->dz[nl], (h16*)(sc + SC.off_dz[l]), N, W, W, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
-            nl++;
-            return SDFG_OK;
-        };
-        if (views) {
-            if (int e = add_layer(nf)) return e;
-            tc::BLayer& Y = P.layer[0];
-            Y.r_src_g = 0; Y.r_rank = d_rgb ? 3 : 0; Y.r_vec0 = 1; Y.r_rank_s = d_rgb; Y.r_dfeat = d_feat;
-            Y.d_rank = d_sdf ? 1 : 0; Y.d_vec0 = 0; Y.d_rank_s = d_sdf;
-        }
-        for (int l = (int)nf - 1; l >= 0; l--) {
-            if (int e = add_layer((uint32_t)l)) return e;
-            tc::BLayer& Y = P.layer[nl - 1];
-            if (!views && l == (int)nf - 1) { Y.r_src_g = 0; Y.r_rank = 1; Y.r_vec0 = 0; Y.r_rank_s = d_sdf; }
-            else Y.r_src_g = 1;
-        }
-        P.n_layers = nl;
-        if (need_dh0) {
-            P.has_in = 1; P.in_dim = p->in_dim; P.d_x_in = d_x_in;
-            h16* wgt_in = (h16*)(sc + SC.off_wgt_in);
-            wgt_kernel<<<dim3(p->in_dim, 1), 256, 0, st>>>(p->input_w, p->in_dim, nullptr, 0, wgt_in, p->in_dim, 1);
-            if (int e = check_launch("wgt_kernel")) return e;
-            if (int e = make_tensor_map_16(&maps->wgt_in, wgt_in, p->in_dim, W, W, p->in_dim / cg, 64, tc::FMT_F16)) return e;
-            if (store)
-                if (int e = make_tensor_map_16(&maps->dh0, DH, N, W, W, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
-        }
-        P.n_units = (uint32_t)(N / (tc::CH_TILE_M * cg));
-        const uint32_t groups = std::min<uint32_t>((uint32_t)sm_count() / cg, P.n_units);      // CTAs (CG = 1) or CTA pairs
-        P.units_per_cta = ceil_div<uint32_t>(P.n_units, groups);
-        const uint32_t grid = cg * ceil_div<uint32_t>(P.n_units, P.units_per_cta);
-        const uint32_t smem = tc::bchain_smem_bytes(cg);
-        typedef void (*bkern_t)(const tc::BChainMaps, const tc::BChainParams);
-        const bkern_t kern = cg == 2 ? (store ? (bkern_t)tc::tc_chain_bwd_kernel<true, 2> : (bkern_t)tc::tc_chain_bwd_kernel<false, 2>)
-                                     : (store ? (bkern_t)tc::tc_chain_bwd_kernel<true, 1> : (bkern_t)tc::tc_chain_bwd_kernel<false, 1>);
-        if (int e = optin_smem((const void*)kern, smem, "tc_chain_bwd_kernel")) return e;
-        auto launch = [&]() -> int {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::CH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = (unsigned)cg; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr; cfg.numAttrs = 1;
-            if (cudaLaunchKernelEx(&cfg, kern, *maps, P) != cudaSuccess) { (void)check_launch("tc_chain_bwd_kernel<gemm>"); return SDFG_ERR_CUDA; }
-            return check_launch("tc_chain_bwd_kernel<gemm>");
-        };
-        static const bool dbg_on = getenv("SDFG_BCHAIN_DBG") != nullptr;    // debugging aid: event log of CTA 0 to stderr
-        if (dbg_on && store) {
-            static unsigned long long* dbuf = nullptr;
-            if (!dbuf) cudaMalloc(&dbuf, 4 * 2048 * 8);
-            cudaMemsetAsync(dbuf, 0, 4 * 2048 * 8, st);
-            P.dbg = dbuf;
-            if (int e = launch()) return e;
-            cudaStreamSynchronize(st);
-            static unsigned long long host[4 * 2048];
-            cudaMemcpy(host, dbuf, sizeof(host), cudaMemcpyDeviceToHost);
-            static int dumps = 0;
-            if (dumps++ == 2)
-                for (int role = 0; role < 4; role++)
-                    for (int k = 0; k < 1024 && host[role * 2048 + 2 * k + 1]; k++)
-                        fprintf(stderr, "CHDBG %d %llu %llu\n", role, host[role * 2048 + 2 * k], host[role * 2048 + 2 * k + 1]);
-        } else {
-            ProfScope prof("tc_chain_bwd_kernel<gemm>", st);
-            if (int e = launch()) return e;
-        }
-        if (!g) return SDFG_OK;
-        // ---- parameter gradients from the stored du tiles (sample-axis contractions) and the fp32 head gradients.
-        // They only depend on the chain's outputs, the caller's next step (hash-grid backward of d_x_in) does not depend on them:
-        // when the caller passes a second stream they run there, overlapping the L2-atomic-bound scatter with these HBM-bound
-        // contractions.  The caller joins the streams (sdfg.h).
-        if (st_w != st) {
-            cudaEvent_t ev;
-            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: event");
-            cudaEventRecord(ev, st);
-            cudaStreamWaitEvent(st_w, ev, 0);
-            cudaEventDestroy(ev);                                      // released once the wait has consumed it
-            st = st_w;
-        }
-        if (views && g->rgb_w && d_rgb) {
-            head_wgrad16_kernel<3><<<(unsigned)ceil_div<uint64_t>(N, 512), 256, 0, st>>>(d_rgb, (const h16*)(ws + L.off_hv), W, g->rgb_w, g->rgb_b, N, 512);
-            if (int e = check_launch("head_wgrad16_kernel<3>")) return e;
-        }
-        if (g->sigma_w && d_sdf) {
-            head_wgrad16_kernel<1><<<(unsigned)ceil_div<uint64_t>(N, 512), 256, 0, st>>>(d_sdf, A(nf), L.Kp_v, g->sigma_w, g->sigma_b, N, 512);
-            if (int e = check_launch("head_wgrad16_kernel<1>")) return e;
-        }
-        for (int l = views ? (int)nf : (int)nf - 1; l >= 0; l--) {
-            if (!g->film_w[l]) continue;
-            if (cudaMemsetAsync(G, 0, (size_t)B * 256 * 336 * 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");
-            uint32_t ldg, ones;
-            if (int e = launch_wgrad((const h16*)(sc + SC.off_dz[l]), A(l), layer_Kx(l), layer_K(l), N, spi, G, &ldg, &ones, st, tc::FMT_F16)) return e;
-            wgrad_finish_kernel<<<256, 256, 0, st>>>(G, ldg, ones, B, p->film_w[l], layer_Kx(l), layer_Kx(l), p->film_b[l], p->gamma + (size_t)l * W,
-                                                     gstride, 1, g->film_w[l], g->film_b[l], g->gamma + (size_t)l * W, g->beta + (size_t)l * W, gscale);
-            if (int e = check_launch("wgrad_finish_kernel")) return e;
-        }
-        if (p->has_input_linear && g->input_w) {
-            if (cudaMemsetAsync(G, 0, (size_t)B * 256 * 336 * 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");
-            uint32_t ldg, ones;
-            if (int e = launch_wgrad(DH, (const h16*)(ws + L.off_x0), p->in_dim, L.Kp_in, N, spi, G, &ldg, &ones, st, tc::FMT_F16)) return e;
-            wgrad_finish_kernel<<<256, 256, 0, st>>>(G, ldg, ones, B, p->input_w, p->in_dim, p->in_dim, p->input_b, nullptr, 0, 0, g->input_w,
-                                                     g->input_b, nullptr, nullptr, gscale);
-            if (int e = check_launch("wgrad_finish_kernel")) return e;
-        }
-        return SDFG_OK;
-    }
 
+    // ---------------------------------------------------------------- per-layer kernels (tc_layer.cuh): shapes the fused chains do not
+    // take (in_dim > 32, view_dim > 16, SDFG_TC_CHAIN=0).  Gradient GEMMs and weight gradients interleave layer by layer, so the two
+    // phases cannot be separated: everything runs in the call that carries SDFG_BWD_CHAIN.
+    if (!(phases & SDFG_BWD_CHAIN)) return SDFG_OK;
+    if (int e = compute_loss_scale(d_sdf, N, d_rgb, N * 3, d_feat, N * 256, (uint32_t*)(sc + SC.off_scale), gscale, st)) return e;
     // R: DZ = dh * cos(z_l), z recomputed from A_l
     auto run_R = [&](uint32_t l, const h16* dh16, const float* dh32, int rank, const float* rs, const float* rv) -> int {
         LayerParams P = {};
@@ -871,8 +724,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         return launch_layer<tc::MODE_D>(DZ, N, W, W, WGT, (uint64_t)B * Kout, W, P, st, "tc_layer_kernel<D,gemm>");
     };
 
-    const h16* dh16 = nullptr;      // where d(h of the last trunk layer) lives, if in memory
-    bool rank1_sdf = false;         // ... or whether it is the rank-1 term d_sdf * w_sigma
+    bool rank1_sdf = false;         // d(h of the last trunk layer) is the rank-1 term d_sdf * w_sigma (no views gradient)
     const h16* h_last = A(nf);      // last trunk output (pitch Kp_v)
     if (d_rgb || d_feat) {
         if (int e = run_R(nf, nullptr, d_feat, d_rgb ? 3 : 0, d_rgb, p->rgb_w)) return e;
@@ -882,7 +734,6 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         }
         if (int e = run_W(nf)) return e;
         if (int e = run_D(nf, W, d_sdf, p->sigma_w)) return e;
-        dh16 = DH;
     } else {
         rank1_sdf = true;
     }
@@ -898,7 +749,6 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         if (need_dx)
             if (int e = run_D((uint32_t)l, W, nullptr, nullptr)) return e;
     }
-    (void)dh16;
     if (p->has_input_linear) {
         if (g && g->input_w) {
             if (cudaMemsetAsync(G, 0, (size_t)B * 256 * 336 * 4, st) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: memset failed");

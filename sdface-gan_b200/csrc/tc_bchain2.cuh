@@ -1,5 +1,6 @@
-// Backward chain WITHOUT recompute: the forward chain saved c_l = cos(gamma u_l + c) per FiLM layer (fp16, tc_chain.cuh), so the
-// gradient of a 128-sample tile flows through the layers with ONE GEMM per layer and a light epilogue:
+// Backward chain: the forward chain saved every FiLM layer's output s_l = sin(gamma u_l + c) (fp16) and the sign of its derivative
+// cos(gamma u_l + c) as one bit per element (tc_chain.cuh), so the gradient of a 128-sample tile flows through the layers with ONE
+// GEMM per layer and a light epilogue (cos = +-sqrt(1 - s^2)):
 //
 //   du_top = (head rank terms + d_feat) * c_top                                   (first epilogue, no GEMM)
 //   for l = top .. bottom:   D_l: dh = du_l (gamma o W_l)   ->   epilogue: du_{l-1} = (dh [+ d_sdf w_sigma]) * c_{l-1}  -> G (fp16)
@@ -9,17 +10,33 @@
 // started from d_sdf = 1 this is the eikonal chain of get_eikonal_term :224-229).  dh never leaves TMEM in fp16: the epilogue
 // reads the fp32 accumulator, multiplies by the cos tile (64 KB shared-memory buffer, TMA-prefetched chunk by chunk as the
 // previous layer's epilogue releases it) and writes the next GEMM's A operand in place into G; D_{l-1}'s MMAs trail the
-// epilogue at 64-column chunk granularity into the other accumulator.  Compared with tc_bchain.cuh (recompute): no R GEMM,
-// no W_l stream, no MUFU, no FiLM constant tables.
-// CG = 2: CTA pairs with tcgen05.mma.cta_group::2, exactly as in tc_bchain.cuh (leader-issued MMAs, multicast commits, the
-// peer's epilogue arrives on the leader's barriers); cos tiles are per-CTA data and complete on local barriers.
+// epilogue at 64-column chunk granularity into the other accumulator.  Nothing is recomputed: no second GEMM per layer, no
+// W_l stream, no FiLM constant tables.
+// CG = 2: two CTAs of a cluster run one tcgen05.mma.cta_group::2 (M = 256) per K-step: each stages its own 128 rows of G and HALF
+// of every weight chunk, so the L2 -> SM weight stream (~1.3 MB per tile, the measured bound of a single-CTA chain) is halved.
+// The leader CTA's MMA thread issues for the pair, commits are multicast to both CTAs, the peer's epilogue warps arrive on the
+// leader's barriers through the cluster (mapa + mbarrier.arrive.shared::cluster); cos tiles are per-CTA data on local barriers.
+// Gradients are fp16 with the power-of-two loss scale of field_tc.cu (gscale = {s, 1/s}); stores saturate.
 // With STORE the du tiles (and dh_0) are TMA-stored for the weight-gradient kernels (tc_wgrad.cuh).
 // Algorithmic HBM traffic per sample and layer: 512 B (c_l) in, 512 B (du_l) out.
 #pragma once
-#include "tc_bchain.cuh"
+#include "tc_chain.cuh"
 
 namespace sdfg {
 namespace tc {
+
+constexpr uint32_t BC_MAX_LAYERS = SDFG_MAX_FILM;            // FiLM layers incl. views
+// weight ring: chunks ([256 / CG rows] x 64 fp16) of (gamma o W_l)^T in issue order (L2 hits); a CTA pair stages half of every chunk per CTA
+__host__ __device__ constexpr uint32_t bc_w_bytes(int cg) { return 32768u / (uint32_t)cg; }
+__host__ __device__ constexpr uint32_t bc_w_stages(int cg) { return cg == 2 ? 5u : 2u; }
+constexpr uint32_t BC_MAX_W_STAGES = 5;
+constexpr uint32_t BC_G_BYTES = 4 * CH_CHUNK_BYTES;          // gradient tile [128 x 256] fp16
+
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
 
 struct B2Layer {
     uint32_t do_D;              // run D (the layer below, or the input stage, needs the gradient)

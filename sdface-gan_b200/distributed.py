@@ -61,26 +61,32 @@ def average_gradients(module, bucket_bytes=64 << 20):
     return calls
 
 
-def data_parallel(module, device_ids=None, early_table_exchange=False, **ddp_kwargs):
+def data_parallel(module, device_ids=None, early_table_exchange=True, process_group=None, **ddp_kwargs):
     """Wrap a Generator (or any module holding the SDF renderer) in DistributedDataParallel for one-process-per-GPU training.
 
-    With `early_table_exchange` the hash-table parameter(s) (`*.encoder.embeddings`, 93 % of the bytes exchanged in stage 1) are
-    taken out of DDP's buckets: autograd produces that gradient last, so its bucket could not overlap any compute.  The field's
-    backward node all-reduces (averages) it itself right after the scatter kernel is enqueued, concurrently with the
-    weight-gradient kernels (sdf_model._field.backward).  The parameter is broadcast from rank 0 here, as DDP would have done.
-    Only the renderer's own backward exchanges the table gradient in that mode: a loss that reaches the table through another
-    node (e.g. a smoothness term on `query_sdf`) must leave `early_table_exchange` off."""
-    from . import sdf_model
+    With `early_table_exchange` (default) the hash-table parameter(s) (`*.encoder.embeddings`, 93 % of the bytes exchanged in
+    stage 1) are taken out of DDP's buckets: autograd produces that gradient last, so its bucket could not overlap any compute.
+    The field's backward node all-reduces (averages) it itself right after the scatter kernel is enqueued, while the
+    weight-gradient kernels run behind it on the same stream (sdf_model._field.backward).  The switch is an attribute of the
+    wrapped module's field networks (`_table_exchange`), not process-global state: other models in the process, and backward
+    passes that only some ranks run, are unaffected.  The parameter is broadcast from rank 0 here, as DDP would have done.
+    Both autograd nodes that produce a table gradient exchange it in that mode: the renderer's fused field node and
+    `GridEncoder`'s own node (`network.query_sdf`, the reference's smoothness term, smoothLoss.py:5-25)."""
     ddp = torch.nn.parallel.DistributedDataParallel
+    world = dist.get_world_size(process_group)
     names = [n for n, _ in module.named_parameters() if n.endswith("encoder.embeddings")] if early_table_exchange else []
-    if names and dist.get_world_size() > 1:
+    if names and world > 1:
         ddp._set_params_and_buffers_to_ignore_for_model(module, names)
         lookup = dict(module.named_parameters())
+        mods = dict(module.named_modules())
         with torch.no_grad():
             for n in names:
-                dist.broadcast(lookup[n].data, 0)
-        sdf_model._EARLY_TABLE_EXCHANGE["on"] = True
+                dist.broadcast(lookup[n].data, 0, group=process_group)
+                owner = n[:-len("encoder.embeddings")].rstrip(".")
+                mods[owner]._table_exchange = {"group": process_group}                       # the field network (sdf_model._field)
+                mods[(owner + "." if owner else "") + "encoder"]._table_exchange = {"group": process_group}   # GridEncoder's own node (query_sdf)
     ddp_kwargs.setdefault("bucket_cap_mb", 64)
     ddp_kwargs.setdefault("gradient_as_bucket_view", True)
+    if process_group is not None:
+        ddp_kwargs.setdefault("process_group", process_group)
     return ddp(module, device_ids=device_ids, **ddp_kwargs)
-

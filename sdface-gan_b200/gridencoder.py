@@ -12,6 +12,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from . import ops
 
@@ -22,7 +23,7 @@ _interp_to_id = {"linear": 0, "smoothstep": 1}
 class _grid_encode(Function):
     @staticmethod
     def forward(ctx, inputs, embeddings, offsets, per_level_scale, base_resolution, calc_grad_inputs=False, gridtype=0,
-                align_corners=False, interpolation=0, bound=0.0):
+                align_corners=False, interpolation=0, bound=0.0, exchange=None):
         # inputs [B, D] in [0,1] (or in [-bound, bound] when bound > 0); embeddings [sO, C]; offsets [L+1] int32 -> [B, L*C]
         inputs = inputs.contiguous().float()
         S = ops.log2_scale(per_level_scale)
@@ -31,9 +32,11 @@ class _grid_encode(Function):
                                                  interp=interpolation)
         ctx.save_for_backward(inputs, embeddings, offsets, dy_dx)
         ctx.meta = (S, base_resolution, gridtype, align_corners, interpolation, bound)
+        ctx.exchange = exchange
         return outputs
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad):
         inputs, embeddings, offsets, dy_dx = ctx.saved_tensors
         S, H, gridtype, align_corners, interpolation, bound = ctx.meta
@@ -43,7 +46,14 @@ class _grid_encode(Function):
         _, grad_inputs = ops.grid_encode_backward(grad, inputs, embeddings, offsets, S, H, bound=bound, dy_dx=dy_dx if want_gi else None,
                                                   grad_embeddings=grad_embeddings, want_grad_inputs=want_gi, gridtype=gridtype,
                                                   align_corners=align_corners, interp=interpolation)
-        return grad_inputs, grad_embeddings, None, None, None, None, None, None, None, None
+        ex = ctx.exchange
+        if ex is not None and grad_embeddings is not None and torch.distributed.is_available() and torch.distributed.is_initialized():
+            # data-parallel training with the table outside DistributedDataParallel's buckets (distributed.data_parallel)
+            world = torch.distributed.get_world_size(ex["group"])
+            if world > 1:
+                torch.distributed.all_reduce(grad_embeddings, op=torch.distributed.ReduceOp.SUM, group=ex["group"])
+                grad_embeddings.div_(world)
+        return grad_inputs, grad_embeddings, None, None, None, None, None, None, None, None, None
 
 
 grid_encode = _grid_encode.apply
@@ -67,6 +77,7 @@ class GridEncoder(nn.Module):
         self.interpolation = interpolation
         self.interp_id = _interp_to_id[interpolation]
         self.align_corners = align_corners
+        self._table_exchange = None       # distributed.data_parallel(early_table_exchange=True) sets {"group": ...}
 
         # level table (grid.py:117-131): entries per level capped at 2^log2_hashmap_size and rounded up to a multiple of 8
         self.max_params = 2 ** log2_hashmap_size
@@ -97,7 +108,7 @@ class GridEncoder(nn.Module):
         prefix_shape = list(inputs.shape[:-1])
         flat = inputs.reshape(-1, self.input_dim)
         outputs = grid_encode(flat, self.embeddings, self.offsets, self.per_level_scale, self.base_resolution, flat.requires_grad,
-                              self.gridtype_id, self.align_corners, self.interp_id, float(bound))
+                              self.gridtype_id, self.align_corners, self.interp_id, float(bound), self._table_exchange)
         return outputs.view(prefix_shape + [self.output_dim])
 
     @torch.no_grad()

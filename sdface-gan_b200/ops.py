@@ -227,12 +227,15 @@ def field_forward(spec, x_in, view_feat, gamma, beta, weights, samples_per_image
 
 
 def field_backward(spec, x_in, view_feat, gamma, beta, weights, samples_per_image, samples_per_ray, workspace, out_feat,
-                   d_sdf, d_rgb, d_feat, grads=None, want_dx=False, precision=_lib.PRECISION_FP32, wgrad_stream=None):
+                   d_sdf, d_rgb, d_feat, grads=None, want_dx=False, precision=_lib.PRECISION_FP32, wgrad_stream=None,
+                   phases=_lib.BWD_BOTH, state=None):
     """grads: None (no parameter gradients) or dict like `weights` + gamma/beta of pre-zeroed (or live .grad) buffers that are
     accumulated into.  Returns d_x_in [N,in_dim] or None.
     wgrad_stream (torch.cuda.Stream): the parameter gradients are produced on that stream (sdfg_field_backward_2s) while d_x_in is
     ready in the current stream's order; returns (d_x_in, scratch) -- the caller must keep `scratch` alive and make the current
-    stream wait for wgrad_stream before it lets go of scratch / grads / the upstream gradients."""
+    stream wait for wgrad_stream before it lets go of scratch / grads / the upstream gradients.
+    phases (sdfg_field_backward_phase): BWD_CHAIN returns (d_x_in, state); a later call with phases=BWD_WGRAD, state=state and
+    otherwise identical arguments produces the parameter gradients (the caller enqueues whatever should run in between)."""
     lib = _lib.load()
     N = x_in.shape[0]
     dev = x_in.device
@@ -253,17 +256,27 @@ def field_backward(spec, x_in, view_feat, gamma, beta, weights, samples_per_imag
         if grads.get("rgb_w") is not None:
             g.rgb_w = _chk(grads["rgb_w"], "d_rgb_w").data_ptr()
             g.rgb_b = _chk(grads["rgb_b"], "d_rgb_b").data_ptr()
-    nbytes = int(lib.sdfg_field_backward_scratch_bytes(ctypes.byref(p), N, int(precision)))
-    scratch = torch.empty(max(nbytes, 16) // 4, device=dev, dtype=torch.float32)
-    dx = torch.empty(N, spec.in_dim, device=dev) if want_dx else None
+    if state is not None:
+        scratch, dx = state
+    else:
+        nbytes = int(lib.sdfg_field_backward_scratch_bytes(ctypes.byref(p), N, int(precision)))
+        scratch = torch.empty(max(nbytes, 16) // 4, device=dev, dtype=torch.float32)
+        dx = torch.empty(N, spec.in_dim, device=dev) if want_dx else None
+    gref = ctypes.byref(g) if g is not None else None
     with torch.cuda.device(dev):
+        if phases != _lib.BWD_BOTH:
+            _lib.check(lib.sdfg_field_backward_phase(ctypes.byref(p), gref, _ptr(x_in), _ptr(view_feat), N,
+                                                     _ptr(_chk(d_sdf, "d_sdf")), _ptr(_chk(d_rgb, "d_rgb")), _ptr(_chk(d_feat, "d_feat")),
+                                                     _ptr(out_feat), _ptr(workspace), _ptr(scratch), _ptr(dx), int(precision), int(phases),
+                                                     _stream()), "sdfg_field_backward_phase")
+            return dx, (scratch, dx)
         if wgrad_stream is not None:
-            _lib.check(lib.sdfg_field_backward_2s(ctypes.byref(p), ctypes.byref(g) if g is not None else None, _ptr(x_in), _ptr(view_feat), N,
+            _lib.check(lib.sdfg_field_backward_2s(ctypes.byref(p), gref, _ptr(x_in), _ptr(view_feat), N,
                                                   _ptr(_chk(d_sdf, "d_sdf")), _ptr(_chk(d_rgb, "d_rgb")), _ptr(_chk(d_feat, "d_feat")),
                                                   _ptr(out_feat), _ptr(workspace), _ptr(scratch), _ptr(dx), int(precision), _stream(),
                                                   ctypes.c_void_p(wgrad_stream.cuda_stream)), "sdfg_field_backward_2s")
             return dx, scratch
-        _lib.check(lib.sdfg_field_backward(ctypes.byref(p), ctypes.byref(g) if g is not None else None, _ptr(x_in), _ptr(view_feat), N,
+        _lib.check(lib.sdfg_field_backward(ctypes.byref(p), gref, _ptr(x_in), _ptr(view_feat), N,
                                            _ptr(_chk(d_sdf, "d_sdf")), _ptr(_chk(d_rgb, "d_rgb")), _ptr(_chk(d_feat, "d_feat")),
                                            _ptr(out_feat), _ptr(workspace), _ptr(scratch), _ptr(dx), int(precision), _stream()),
                    "sdfg_field_backward")
@@ -271,7 +284,7 @@ def field_backward(spec, x_in, view_feat, gamma, beta, weights, samples_per_imag
 
 
 def tc_linear_probe(x, w):
-    """out = bf16(x) @ bf16(w).T with fp32 accumulation, through the tcgen05 layer pipeline (parity-test probe)."""
+    """out = fp16(x) @ fp16(w).T with fp32 accumulation, through the tcgen05 layer pipeline (parity-test probe)."""
     lib = _lib.load()
     _chk(x, "x"); _chk(w, "w")
     M, K = x.shape
@@ -284,7 +297,7 @@ def tc_linear_probe(x, w):
 
 
 def tc_wgrad_probe(dz, x, rows_per_image, x_fmt=0):
-    """G[b, j, k] = sum_{n in image b} bf16(dz)[n, j] * x16(x)[n, k] plus the ones column; returns (G [B,256,Kx], colsum [B,256])."""
+    """G[b, j, k] = sum_{n in image b} x16(dz)[n, j] * x16(x)[n, k] plus the ones column; returns (G [B,256,Kx], colsum [B,256])."""
     lib = _lib.load()
     _chk(dz, "dz"); _chk(x, "x")
     N, Kx = x.shape

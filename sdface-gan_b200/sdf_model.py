@@ -9,13 +9,14 @@ sample), the field as a fused sequence of layer kernels (csrc/field_*.cu) and on
 instead of ~45 + the [N,272]/[N,260] concatenations.  There is no CPU path: tensors must live on a CUDA device.
 """
 import math
-import os
+import warnings
 
 import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from . import _lib, ops
 from .gridencoder import GridEncoder
@@ -75,40 +76,26 @@ class FiLMSiren(nn.Module):
 # --------------------------------------------------------------------------------------------------------------------------
 # the fused field as one autograd node
 
-_SIDE_STREAMS = {}
-# Two-stream backward (weight-gradient contractions on a side stream while the hash-table scatter runs): measured neutral on B200.
-# With a default-priority side stream the scatter's 12k short blocks fill every SM and the persistent contraction kernels only
-# start once it has drained; with a high-priority side stream they do run together (torch.profiler timeline), but both live on L2
-# bandwidth: the scatter stretches 2.0 -> 3.4 ms and the first contraction 0.56 -> 1.6 ms, the step ends at the same time
-# (16.8-17.4 ms either way).  Off unless SDFG_OVERLAP=1.
-_OVERLAP = os.environ.get("SDFG_OVERLAP", "0") == "1"
-# Data-parallel training (distributed.data_parallel): the hash-table gradient (50.6 MB of the 54.6 MB exchanged per step) is the
-# LAST gradient autograd sees, so a DistributedDataParallel bucket holding it cannot overlap anything.  When this flag is set the
-# field node all-reduces it itself, as soon as the scatter kernel is enqueued, while the weight-gradient contractions still run
-# on the side stream; DistributedDataParallel is told to ignore the parameter.
-_EARLY_TABLE_EXCHANGE = {"on": False}
-
-
-def _side_stream(device):
-    """One extra stream per device for the weight-gradient contractions of the field backward (see _field.backward)."""
-    key = torch.device(device).index
-    if key not in _SIDE_STREAMS:
-        # high priority: its persistent 1-CTA-per-SM kernels must get their slots while the scatter's thousands of short blocks
-        # keep every SM full (without it the block scheduler starts them only after the scatter has drained)
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device, priority=-1)
-    return _SIDE_STREAMS[key]
-
-
 class _field(Function):
     """(x_in [N,in_dim], view_feat [N/S,V], gamma/beta [B,n+1,W], emb, weights...) -> (sdf [N], rgb [N,3], feat [N,W], dsdf_dx [N,in_dim]).
 
     `emb` is the hash table when the caller computed x_in = grid_encode(meta["grid"]["pts"], emb) itself (without autograd):
-    the node then also owns the table gradient, which lets its backward overlap the L2-atomic-bound scatter (main stream)
-    with the HBM-bound weight-gradient contractions (side stream).  emb = None: x_in is an ordinary differentiable input."""
+    the node then also owns the table gradient, so its backward can order the work as
+        gradient chain -> table scatter -> [async all-reduce of the table gradient] -> weight-gradient kernels
+    on ONE stream: in data-parallel training (distributed.data_parallel) the 50.6 MB table gradient -- 93 % of the bytes
+    exchanged per step, and the LAST gradient autograd would hand to a DistributedDataParallel bucket -- travels while the
+    HBM-bound weight-gradient contractions run, and the L2-atomic-bound scatter never shares the chip with them.
+    emb = None: x_in is an ordinary differentiable input.
+
+    First order only: the backward is `once_differentiable` (a double backward raises instead of silently returning zeros), and
+    the view feature gets no gradient (asking for one raises)."""
 
     @staticmethod
     def forward(ctx, spec, meta, x_in, view_feat, gamma, beta, emb, *wts):
         ctx.set_materialize_grads(False)
+        if ctx.needs_input_grad[3]:
+            raise RuntimeError("the fused field has no gradient for the view feature (view directions / SH features must not "
+                               "require grad; the reference never differentiates them either, SURVEY.md 2.3 kernel_sh_backward)")
         x_in = x_in.contiguous()
         view_feat = view_feat.contiguous()
         gamma = gamma.contiguous()
@@ -140,6 +127,7 @@ class _field(Function):
         return outs
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, d_sdf, d_rgb, d_feat, _d_dsdf):
         spec, meta = ctx.spec, ctx.meta
         x_in, view_feat, gamma, beta, feat, ws, emb = ctx.saved_tensors[:7]
@@ -163,27 +151,27 @@ class _field(Function):
             grads["beta"] = torch.zeros_like(beta)
         d_sdf, d_rgb, d_feat = cont(d_sdf), cont(d_rgb), cont(d_feat)
         want_dx = bool(ctx.needs_input_grad[2] or need_table)
-        early = (need_table and _EARLY_TABLE_EXCHANGE["on"] and torch.distributed.is_available() and torch.distributed.is_initialized()
-                 and torch.distributed.get_world_size() > 1)
-        side = (_side_stream(x_in.device)
-                if (need_table and need_param and meta["precision"] == _lib.PRECISION_TC16 and (_OVERLAP or early)) else None)
-        res = ops.field_backward(spec, x_in, view_feat, gamma, beta, weights, meta["spi"], meta["spr"], ws,
-                                 feat if meta["want_feat"] else None, d_sdf, d_rgb, d_feat, grads=grads,
-                                 want_dx=want_dx, precision=meta["precision"], wgrad_stream=side)
-        dx, scratch = res if side is not None else (res, None)
-        d_emb = None
+        args = (spec, x_in, view_feat, gamma, beta, weights, meta["spi"], meta["spr"], ws, feat if meta["want_feat"] else None,
+                d_sdf, d_rgb, d_feat)
+        # phase 1: loss scale + gradient chain through the layers -> d x_in (and the gradient tiles phase 2 contracts)
+        dx, state = ops.field_backward(*args, grads=grads, want_dx=want_dx, precision=meta["precision"], phases=_lib.BWD_CHAIN)
+        d_emb, work, world = None, None, 1
         if need_table:
             d_emb = torch.zeros_like(emb)
             ops.grid_encode_backward(dx, grid["pts"], emb, grid["offsets"], grid["S"], grid["H"], bound=grid["bound"], grad_embeddings=d_emb,
                                      gridtype=grid["gridtype"], align_corners=grid["align_corners"], interp=grid["interp"])
-        work = None
-        if early:
-            work = torch.distributed.all_reduce(d_emb, op=torch.distributed.ReduceOp.AVG, async_op=True)
-        if side is not None:
-            torch.cuda.current_stream().wait_stream(side)      # joins before scratch / grads / upstream gradients are let go
+            ex = meta.get("exchange")
+            if ex is not None and torch.distributed.is_available() and torch.distributed.is_initialized():
+                world = torch.distributed.get_world_size(ex["group"])
+                if world > 1:      # SUM + divide: ReduceOp.AVG exists for NCCL only
+                    work = torch.distributed.all_reduce(d_emb, op=torch.distributed.ReduceOp.SUM, group=ex["group"], async_op=True)
+        # phase 2: parameter gradients (HBM-bound contractions) while the table gradient travels
+        if need_param:
+            ops.field_backward(*args, grads=grads, want_dx=want_dx, precision=meta["precision"], phases=_lib.BWD_WGRAD, state=state)
         if work is not None:
-            work.wait()                                        # stream-level: the current stream waits for the collective
-        del scratch
+            work.wait()                                        # stream-level for NCCL: the current stream waits for the collective
+            d_emb.div_(world)
+        del state
         out = [None, None, dx if ctx.needs_input_grad[2] else None, None]
         if need_param:
             out += [grads["gamma"], grads["beta"], d_emb] + list(gw)
@@ -215,18 +203,43 @@ def _unpack_weights(spec, w):
     return d
 
 
+_WARNED = set()
+
+
+def _warn_once(key, msg):
+    if key not in _WARNED:
+        _WARNED.add(key)
+        warnings.warn(msg, RuntimeWarning, stacklevel=3)
+
+
 class _FieldNetwork(nn.Module):
     """Shared driver of SirenGenerator / NGPSIRENGenerator: evaluates the whole network through `_field`."""
 
-    # "auto": the tcgen05 path (fp16 activations / bf16 gradients, fp32 accumulate) whenever its shape constraints hold
-    # (width 256, samples per image a multiple of 128), else the fp32 SIMT path.  Both are CUDA; neither falls back to the CPU.
+    # "auto": the tcgen05 path (fp16 activations and loss-scaled fp16 gradients, fp32 accumulate) whenever its shape constraints
+    # hold (width 256, samples per image a multiple of 128, and -- when d sdf / d x_in is wanted -- an input_linear layer with
+    # in_dim % 32 == 0), else the fp32 SIMT path, with a one-time warning (the fp32 path is ~13x slower).  Both are CUDA; neither
+    # falls back to the CPU.
     precision = "auto"
+    _table_exchange = None      # set by distributed.data_parallel(early_table_exchange=True): {"group": process group or None}
 
-    def _pick_precision(self, samples_per_image):
+    def _pick_precision(self, samples_per_image, want_dx=False):
         if self.precision != "auto":
             return _PRECISIONS[self.precision]
-        ok = self._spec.width == 256 and samples_per_image % 128 == 0 and (not self._spec.has_input_linear or self._spec.in_dim % 32 == 0)
-        return _lib.PRECISION_TC16 if ok else _lib.PRECISION_FP32
+        spec = self._spec
+        why = None
+        if spec.width != 256:
+            why = "width %d != 256" % spec.width
+        elif samples_per_image % 128 != 0:
+            why = "samples per image (%d) not a multiple of 128" % samples_per_image
+        elif spec.has_input_linear and spec.in_dim % 32 != 0:
+            why = "in_dim %d not a multiple of 32" % spec.in_dim
+        elif want_dx and not spec.has_input_linear:
+            why = "d sdf / d points through a network without input_linear"
+        if why is None:
+            return _lib.PRECISION_TC16
+        _warn_once(("fp32", why), "sdface-gan_b200: precision='auto' uses the fp32 SIMT field kernels instead of the tcgen05 path (%s); "
+                   "this is the slow, <= 1e-3-parity path" % why)
+        return _lib.PRECISION_FP32
 
     def _modulation(self, styles):
         layers = list(self.pts_linears) + [self.views_linears]
@@ -238,9 +251,11 @@ class _FieldNetwork(nn.Module):
                    feat_f16=False, emb=None, grid=None):
         spec = self._spec
         gamma, beta = self._modulation(styles)
+        want_dx = bool(want_dsdf) or (torch.is_grad_enabled() and x_in.requires_grad)
         meta = dict(spi=int(samples_per_image), spr=int(samples_per_ray), want_rgb=bool(want_rgb), want_feat=bool(want_feat),
-                    want_dsdf=bool(want_dsdf), precision=self._pick_precision(int(samples_per_image)),
-                    grad=torch.is_grad_enabled(), feat_f16=bool(feat_f16), grid=grid)   # Function.forward itself always runs with grad mode off
+                    want_dsdf=bool(want_dsdf), precision=self._pick_precision(int(samples_per_image), want_dx),
+                    grad=torch.is_grad_enabled(), feat_f16=bool(feat_f16), grid=grid,   # Function.forward itself always runs with grad mode off
+                    exchange=self._table_exchange)
         sdf, rgb, feat, dsdf = _field.apply(spec, meta, x_in, view_feat, gamma, beta, emb, *_pack_weights(spec, self))
         return sdf, (rgb if rgb.numel() else None), (feat if feat.numel() else None), (dsdf if dsdf.numel() else None)
 
@@ -293,6 +308,32 @@ class SirenGenerator(_FieldNetwork):
 
     def _dsdf_to_points(self, dsdf, flat_pts, grid_ctx):
         return dsdf
+
+    def _trunk_sdf_torch(self, pts, styles, spi):
+        """sdf(pts) through plain torch ops (ref :121-131): the second-order-capable evaluation behind the eikonal LOSS GRADIENT."""
+        B = styles.shape[0]
+        h = pts.view(B, spi, -1)
+        for l in self.pts_linears:
+            g, b = l.modulation(styles)
+            h = torch.sin(g[:, None, :] * F.linear(h, l.weight, l.bias) + b[:, None, :])
+        return self.sigma_linear(h).reshape(-1)
+
+    def forward_rays(self, npts, viewdirs, styles, want_rgb=True, want_feat=True, want_dsdf=False, feat_f16=False):
+        """With `--ngp 0` the reference's eikonal term carries a real second-order gradient into the SIREN weights
+        (autograd.grad(..., create_graph=True), ref :224-229) -- unlike `--ngp 1`, where the opaque hash-grid backward cuts it
+        (SURVEY.md finding 4).  The fused kernels are first order, so while gradients are enabled the term is evaluated here
+        through torch autograd on the trunk (cuBLAS, differentiable twice); outputs and first-order gradients still come from
+        the fused kernels.  Under no_grad the fused first-order kernel path provides it (fp32 kernels: no input_linear)."""
+        if not (want_dsdf and torch.is_grad_enabled()):
+            return super().forward_rays(npts, viewdirs, styles, want_rgb, want_feat, want_dsdf, feat_f16)
+        _warn_once("siren-eik", "sdface-gan_b200: SirenGenerator evaluates the DIFFERENTIABLE eikonal term (--ngp 0 training) through torch "
+                   "autograd on the trunk; the fused kernels provide outputs and first-order gradients only")
+        sdf, rgb, feat, _ = super().forward_rays(npts, viewdirs, styles, want_rgb, want_feat, False, feat_f16)
+        B, R1, R2, S, _ = npts.shape
+        pts = npts.detach().reshape(-1, 3).requires_grad_(True)
+        sdf_t = self._trunk_sdf_torch(pts, styles, R1 * R2 * S)
+        dsdf = torch.autograd.grad(sdf_t, pts, torch.ones_like(sdf_t), create_graph=True)[0]
+        return sdf, rgb, feat, dsdf
 
 
 def get_encoder(encoding, input_dim=3, multires=6, degree=4, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19,
@@ -462,6 +503,7 @@ class _composite(Function):
         return outs
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, d_rgb_map, d_feat_map, d_xyz, d_mask):
         sdf, rgb, feat, sigmoid_beta, z_vals, rays_d, pts, noise = ctx.saved_tensors
         S, with_sdf, force_background, want_xyz = ctx.cfg
@@ -638,7 +680,7 @@ _DECODER_FACTORY = None
 
 def register_decoder(factory):
     """Plug the (out-of-scope) StyleGAN2 decoder class of the host project: factory(model_opt) -> nn.Module with the
-    reference Decoder's forward/mean_latent signature (ref :786-1056)."""
+    reference Decoder's forward/mean_latent signature (ref :883-1056)."""
     global _DECODER_FACTORY
     _DECODER_FACTORY = factory
 

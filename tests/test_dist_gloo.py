@@ -65,9 +65,12 @@ def test_shard_sync_and_gradient_average_world2():
 class _Toy(torch.nn.Module):
     """Same parameter naming as the renderer: `...encoder.embeddings` is the table the field node exchanges itself."""
 
+    _table_exchange = None
+
     def __init__(self):
         super().__init__()
         self.encoder = torch.nn.Module()
+        self.encoder._table_exchange = None
         self.encoder.embeddings = torch.nn.Parameter(torch.ones(16, 2))
         self.lin = torch.nn.Linear(2, 1)
 
@@ -91,10 +94,10 @@ def _worker_dp(rank, world, port, q):
         w0 = toy.lin.weight.detach().clone()
         loss = model(torch.arange(4) + 4 * rank, float(rank + 1))
         loss.backward()
-        from sdface_gan_b200 import sdf_model
+        # the switch is scoped to the wrapped module (owner of the table + its encoder), nothing process-global
+        scoped = toy._table_exchange is not None and toy.encoder._table_exchange is not None and _Toy()._table_exchange is None
         # plain lists: a tensor would travel as a shared-memory handle that dies with this process
-        q.put((rank, emb0.tolist(), w0.tolist(), toy.encoder.embeddings.grad.tolist(), toy.lin.weight.grad.tolist(),
-               sdf_model._EARLY_TABLE_EXCHANGE["on"]))
+        q.put((rank, emb0.tolist(), w0.tolist(), toy.encoder.embeddings.grad.tolist(), toy.lin.weight.grad.tolist(), scoped))
     finally:
         dist.destroy_process_group()
 

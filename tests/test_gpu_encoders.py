@@ -212,6 +212,70 @@ def test_sh_matches_unmodified_reference_extension():
         assert (dd - dd_ref).abs().max().item() < 1e-4
 
 
+def _ref_style_grid_function(backend, inputs, embeddings, offsets, per_level_scale, H, grad_out):
+    """The call sequence of the reference's `_grid_encode` autograd.Function (gridencoder/grid.py:24-89) against a `_backend`
+    object: forward with dy_dx, permute to [B, L*C], then backward of `grad_out` incl. grad_inputs.  Written from the reference's
+    documented contract (caller allocates, [L,B,C] layout, pre-zeroed sinks) so that any `_backend` can be dropped in."""
+    B, D = inputs.shape
+    L, C = offsets.shape[0] - 1, embeddings.shape[1]
+    S = float(np.log2(per_level_scale))
+    outputs = torch.empty(L, B, C, device=inputs.device)
+    dy_dx = torch.empty(B, L * D * C, device=inputs.device)
+    backend.grid_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, dy_dx, 0, False, 0)
+    out = outputs.permute(1, 0, 2).reshape(B, L * C)
+    grad = grad_out.view(B, L, C).permute(1, 0, 2).contiguous()
+    grad_embeddings = torch.zeros_like(embeddings)
+    grad_inputs = torch.zeros_like(inputs)
+    backend.grid_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, S, H, dy_dx, grad_inputs, 0, False, 0)
+    return out, grad_embeddings, grad_inputs
+
+
+def test_compat_backend_is_a_drop_in_for_the_reference_extension_modules():
+    """INTEGRATION.md section 2, executed: `compat_backend.grid_backend` / `sh_backend` (ctypes over libsdfg.so) driven through the
+    reference wrappers' call sequence side by side with the UNMODIFIED reference extensions (oracle/_ref, the same pybind API)."""
+    ref = _load_ref("_gridencoder_ref")
+    sg = _sg()
+    offsets, pls, _ = _ngp_grid()
+    dev = "cuda"
+    rs = np.random.RandomState(11)
+    table = torch.from_numpy(rs.uniform(-1, 1, (offsets[-1], 2)).astype(np.float32)).to(dev)
+    u = ((torch.from_numpy(_inputs(60001, seed=5)).to(dev) + 2.0) / 4.0).contiguous()
+    ot = torch.from_numpy(offsets).to(dev)
+    g = torch.randn(u.shape[0], 32, device=dev)
+    o_r, ge_r, gi_r = _ref_style_grid_function(ref, u, table, ot, pls, 16, g)
+    o_s, ge_s, gi_s = _ref_style_grid_function(sg.compat_backend.grid_backend, u, table, ot, pls, 16, g)
+    torch.cuda.synchronize()
+    assert torch.equal(o_s, o_r)
+    assert (ge_s - ge_r).abs().max().item() <= 1e-5 * max(1.0, ge_r.abs().max().item())
+    assert (gi_s - gi_r).abs().max().item() <= 1e-4 * max(1.0, gi_r.abs().max().item())
+    # total-variation gradient (grid.py:165-185)
+    tv_r, tv_s = torch.zeros_like(table), torch.zeros_like(table)
+    B = 50000
+    ref.grad_total_variation(u[:B].contiguous(), table, tv_r, ot, 0.5, B, 3, 2, 16, float(np.log2(pls)), 16, 0, False)
+    sg.compat_backend.grid_backend.grad_total_variation(u[:B].contiguous(), table, tv_s, ot, 0.5, B, 3, 2, 16, float(np.log2(pls)), 16, 0, False)
+    torch.cuda.synchronize()
+    assert (tv_s - tv_r).abs().max().item() <= 1e-4 * max(1.0, tv_r.abs().max().item())
+    # spherical harmonics: forward + dy_dx + backward (shencoder/sphere_harmonics.py:14-58)
+    refs = _load_ref("_shencoder_ref")
+    d = torch.nn.functional.normalize(torch.randn(30000, 3, device=dev), dim=-1)
+    gs = torch.randn(30000, 16, device=dev)
+    res = []
+    for be in (refs, sg.compat_backend.sh_backend):
+        out = torch.empty(30000, 16, device=dev)
+        dd = torch.empty(30000, 48, device=dev)
+        be.sh_encode_forward(d, out, 30000, 3, 4, dd)
+        gi = torch.zeros(30000, 3, device=dev)
+        be.sh_encode_backward(gs, d, 30000, 3, 4, dd, gi)
+        res.append((out, gi))
+    torch.cuda.synchronize()
+    assert (res[1][0] - res[0][0]).abs().max().item() < 1e-5
+    assert (res[1][1] - res[0][1]).abs().max().item() < 1e-4 * max(1.0, res[0][1].abs().max().item())
+    # error behaviour: CPU tensors raise RuntimeError, like TORCH_CHECK in the reference (gridencoder.cu:15-18)
+    with pytest.raises(RuntimeError):
+        sg.compat_backend.grid_backend.grid_encode_forward(u.cpu(), table, ot, torch.empty(16, u.shape[0], 2, device=dev), u.shape[0], 3, 2, 16,
+                                                           float(np.log2(pls)), 16, None, 0, False, 0)
+
+
 def test_sh_matches_oracle_and_golden():
     sg = _sg()
     z = H.load_fixture("sh_deg8")

@@ -58,32 +58,32 @@ def test_generator_forward_matches_reference_fixture(name):
             assert H.max_abs(out[k], z["out_" + k]) < 1e-3, k
 
 
-@pytest.mark.parametrize("name", ["ngp_train", "ngp_train_feat", "siren_train"])
-def test_generator_training_step_matches_reference_fixture(name):
+def check_training_fixture(name, precision, out_tol, eik_tol):
     """Forward incl. sdf + eikonal, then the fixture's seeded linear loss; every parameter gradient is compared with the
-    reference's digest (L2 norm, random projection, 16 strided samples) at 1e-2 relative."""
+    REFERENCE's digest (L2 norm, random projection, 16 strided samples) at the north star's 1e-2 relative."""
     z = H.load_fixture(name)
-    g = H.product_generator(z, DEV)
+    g = H.product_generator(z, DEV, precision=precision)
     inp = H.fixture_inputs(z, DEV)
     kw = _gen_kwargs(z)
-    if name == "siren_train":
-        kw.pop("return_eikonal", None)      # double backward through the SIREN trunk is outside the accelerated path (DESIGN.md)
     out = dict(zip(_tuple_names(kw), g([inp["z"]], inp["cam"], inp["focal"], inp["near"], inp["far"], t_rand=inp["t_rand"], **kw)))
-    assert H.max_abs(out["thumb_rgb"], z["out_thumb_rgb"]) < 1e-3
+    assert H.max_abs(out["thumb_rgb"], z["out_thumb_rgb"]) < out_tol
     if "sdf" in out:
-        assert H.max_abs(out["sdf"], z["out_sdf"]) < 1e-3
+        assert H.max_abs(out["sdf"], z["out_sdf"]) < out_tol * max(1.0, float(np.abs(z["out_sdf"]).max()))
     if "eikonal" in out:
         ref = z["out_eikonal"]
-        assert H.max_abs(out["eikonal"], ref) < 1e-3 * max(1.0, float(np.abs(ref).max()))
-        assert not out["eikonal"].requires_grad      # SURVEY finding 4: constant w.r.t. the parameters in ngp mode
+        assert H.max_abs(out["eikonal"], ref) < eik_tol * max(1.0, float(np.abs(ref).max()))
+        if name.startswith("ngp"):
+            assert not out["eikonal"].requires_grad      # SURVEY finding 4: constant w.r.t. the parameters in ngp mode
+        else:
+            assert out["eikonal"].requires_grad          # --ngp 0: a real second-order term (ref :224-229), torch autograd on the trunk
     loss = 0
     for k in ("thumb_rgb", "sdf"):
         if "lossw_" + k in z.files and k in out:
             loss = loss + (torch.from_numpy(z["lossw_" + k]).to(DEV) * out[k]).sum() / out[k].numel() ** 0.5
-    assert abs(float(loss) - float(z["loss"])) < 1e-3
+    assert abs(float(loss) - float(z["loss"])) < max(out_tol, 1e-3) * max(1.0, abs(float(z["loss"])))
     g.zero_grad()
     loss.backward()
-    checked = 0
+    checked, worst = 0, (0.0, None)
     for pname, p in g.named_parameters():
         if "g_norm_" + pname not in z.files:
             continue
@@ -92,6 +92,7 @@ def test_generator_training_step_matches_reference_fixture(name):
             assert ref_norm == 0.0, pname
             continue
         d = pf.grad_digest(pname, p.grad.cpu().numpy())
+        worst = max(worst, (abs(d["norm"] - ref_norm) / max(ref_norm, 1e-30), pname))
         assert abs(d["norm"] - ref_norm) <= 1e-2 * ref_norm + 1e-9, (pname, d["norm"], ref_norm)
         assert abs(d["proj"] - float(z["g_proj_" + pname])) <= 1e-2 * ref_norm + 1e-9, pname
         assert np.abs(d["val"] - z["g_val_" + pname]).max() <= 1e-2 * max(np.abs(z["g_val_" + pname]).max(), ref_norm / np.sqrt(p.numel())) + 1e-9, pname
@@ -101,6 +102,66 @@ def test_generator_training_step_matches_reference_fixture(name):
         flat = dict(g.named_parameters())["renderer.network.encoder.embeddings"].grad.reshape(-1).cpu().numpy()
         ref = z["g_top_val_embeddings"]
         assert np.abs(flat[z["g_top_idx_embeddings"]] - ref).max() <= 1e-2 * np.abs(ref).max()
+    return worst
+
+
+@pytest.mark.parametrize("name", ["ngp_train", "ngp_train_feat", "siren_train"])
+def test_generator_training_step_matches_reference_fixture(name):
+    """fp32 kernels: rendered maps max-abs 1e-3, gradients 1e-2 relative vs the reference's digests.  `siren_train` includes the
+    eikonal output with precision='auto' semantics covered separately (test_siren_eikonal_auto_precision_and_second_order)."""
+    check_training_fixture(name, "fp32", 1e-3, 1e-3)
+
+
+def test_siren_eikonal_auto_precision_and_second_order():
+    """`--ngp 0` + return_eikonal with the DEFAULT precision='auto' must run (no input_linear -> the first-order kernel
+    path must not be asked for d sdf / d x on the tensor-core kernels) and the eikonal loss must reach the SIREN weights."""
+    z = H.load_fixture("siren_train")
+    g = H.product_generator(z, DEV, precision="auto")
+    inp = H.fixture_inputs(z, DEV)
+    _, thumb, sdf, eik = g([inp["z"]], inp["cam"], inp["focal"], inp["near"], inp["far"], t_rand=inp["t_rand"], return_sdf=True, return_eikonal=True)
+    ref = z["out_eikonal"]
+    assert H.max_abs(eik, ref) < 1e-3 * max(1.0, float(np.abs(ref).max()))
+    assert eik.requires_grad
+    g.zero_grad()
+    ((eik.norm(dim=-1) - 1) ** 2).mean().backward()      # the eikonal LOSS alone
+    w = g.renderer.network.pts_linears[3].weight.grad
+    assert w is not None and float(w.abs().sum()) > 0
+    # oracle: the same second-order gradient through torch autograd on the CPU restatement
+    params = H.fixture_params(z, requires_grad=True)
+    rp, sp = H.oracle_param_dicts(params)
+    ci = H.fixture_inputs(z)
+    o = fo.render(rp, ci["cam"], ci["focal"], ci["near"], ci["far"], fo.mapping(sp, ci["z"]), t_rand=ci["t_rand"], return_eikonal=True,
+                  **H.render_kwargs(H.fixture_cfg(z)))
+    ((o[5].norm(dim=-1) - 1) ** 2).mean().backward()
+    for n in ("renderer.network.pts_linears.3.weight", "renderer.network.pts_linears.0.gamma.weight", "style.1.weight"):
+        got = dict(g.named_parameters())[n].grad
+        assert H.rel_err(got, params[n].grad) < 1e-2, n
+    # under no_grad the fused first-order kernels provide the term
+    with torch.no_grad():
+        _, _, _, eik2 = g([inp["z"]], inp["cam"], inp["focal"], inp["near"], inp["far"], t_rand=inp["t_rand"], return_sdf=True, return_eikonal=True)
+    assert H.max_abs(eik2, ref) < 1e-3 * max(1.0, float(np.abs(ref).max()))
+
+
+def test_field_node_is_first_order_and_refuses_view_gradients():
+    """double backward through the fused nodes raises (once_differentiable) instead of returning zeros; a view feature
+    that requires grad is refused."""
+    import sdface_gan_b200 as sg
+    torch.manual_seed(0)
+    mo, ro = sg.default_options("ngp", renderer_res=8, n_samples=16, perturb=0.)
+    g = sg.Generator(mo, ro, full_pipeline=False).to(DEV)
+    g.renderer.network.encoder.embeddings.data.uniform_(-0.5, 0.5)
+    cam, focal, near, far, _ = sg.generate_camera_params(8, DEV, batch=1)
+    _, thumb = g([torch.randn(1, 256, device=DEV)], cam, focal, near, far)
+    w = g.renderer.network.pts_linears[1].weight
+    (gw,) = torch.autograd.grad(thumb.sum(), w, create_graph=True)
+    with pytest.raises(RuntimeError, match="once_differentiable|differentiable"):
+        gw.square().sum().backward()
+    net = g.renderer.network
+    npts = torch.rand(1, 8, 8, 16, 3, device=DEV)
+    sh = torch.randn(64, 16, device=DEV, requires_grad=True)
+    x_in = torch.randn(8 * 8 * 16, 32, device=DEV)
+    with pytest.raises(RuntimeError, match="view feature"):
+        net._run_field(x_in, sh, torch.randn(1, 256, device=DEV), 8 * 8 * 16, 16)
 
 
 def test_init_pass_matches_reference_fixture():
