@@ -170,10 +170,10 @@ def run_ours(args):
     if world > 1:      # identical weights on every rank
         for p_ in g.parameters():
             dist.broadcast(p_.data, 0)
-    # SDFG_EARLY_EXCHANGE=1: the hash-table gradient is exchanged by the field's backward node itself, overlapped with the weight-
-    # gradient kernels (measured on 2 x B200: 17.3-17.5 ms vs 17.1-17.3 ms with plain DDP buckets -- the side stream's L2 contention
-    # costs what the hidden all-reduce saves, so plain DDP stays the default)
-    model = sg.distributed.data_parallel(g, device_ids=[local], early_table_exchange=os.environ.get("SDFG_EARLY_EXCHANGE", "0") == "1") if world > 1 else g
+    # The hash-table gradient (50.6 of the 54.6 MB exchanged) is all-reduced by the field's backward node itself, between the table
+    # scatter and the weight-gradient kernels on the same stream (sdf_model._field.backward); SDFG_EARLY_EXCHANGE=0 leaves it to
+    # DistributedDataParallel's last bucket instead (nothing left to overlap with: +0.7-1.0 ms per step in round 1).
+    model = sg.distributed.data_parallel(g, device_ids=[local], early_table_exchange=os.environ.get("SDFG_EARLY_EXCHANGE", "1") == "1") if world > 1 else g
     opt = torch.optim.Adam(g.parameters(), lr=2e-5, betas=(0.0, 0.9), fused=True)      # im2scene/config.py:196-204 (stage 1); one fused update kernel
 
     # synthetic inputs: resident copies for `value`, pinned host copies for `e2e`

@@ -66,6 +66,55 @@ out["grid_forward_dydx"] = {"ms": ms_fd, "hbm_GBps": N * (140 + 384) / ms_fd / 1
                             "frac_of_l2_gather_probe": N * 128 / ms_fd / 1e6 / probe}
 out["grid_backward"] = {"ms": ms_b, "Greductions_8B_per_s": N * 128 / ms_b / 1e6, "frac_of_l2_gather_probe": N * 128 / ms_b / 1e6 / probe}
 
+# --- the reference's own kernels (gridencoder.cu / shencoder.cu compiled UNCHANGED for sm_100a into oracle/_ref/, same box, same
+#     inputs): SURVEY 2.3 sets "beat the reference kernel recompiled for sm_100a" as the bar
+import importlib.util
+import numpy as np
+
+
+def _load_ref(name):
+    path = os.path.join(ROOT, "oracle", "_ref", name + ".so")
+    if not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+ref_g, ref_s = _load_ref("_gridencoder_ref"), _load_ref("_shencoder_ref")
+if ref_g is not None:
+    u = ((pts + 2.0) / 4.0).contiguous()                  # the reference maps to [0,1] in Python (grid.py:149): not timed
+    S_ref = float(np.log2(enc.per_level_scale))
+    o_ref = torch.empty(16, N, 2, device=dev)
+    dd_ref = torch.empty(N, 96, device=dev)
+    g_ref = grad.view(N, 16, 2).permute(1, 0, 2).contiguous()
+    ge_ref = torch.zeros_like(tab)
+    gi_ref = torch.zeros(N, 3, device=dev)
+    r_f = timed(lambda: ref_g.grid_encode_forward(u, tab, enc.offsets, o_ref, N, 3, 2, 16, S_ref, H, None, 0, False, 0))
+    r_fd = timed(lambda: ref_g.grid_encode_forward(u, tab, enc.offsets, o_ref, N, 3, 2, 16, S_ref, H, dd_ref, 0, False, 0))
+    r_perm = timed(lambda: o_ref.permute(1, 0, 2).reshape(N, 32))        # grid.py:57, the transposing copy the reference adds
+    r_b = timed(lambda: ref_g.grid_encode_backward(g_ref, u, tab, enc.offsets, ge_ref, N, 3, 2, 16, S_ref, H, None, None, 0, False, 0))
+    r_bi = timed(lambda: ref_g.grid_encode_backward(g_ref, u, tab, enc.offsets, ge_ref, N, 3, 2, 16, S_ref, H, dd_ref, gi_ref, 0, False, 0))
+    dsdf = torch.randn(N, 32, device=dev)
+    ms_ib = timed(lambda: ops.grid_encode_backward(dsdf, pts, tab, enc.offsets, Sg, H, bound=2.0, dy_dx=dy, grad_embeddings=None, want_grad_inputs=True))
+    out["reference_kernels_same_box"] = {
+        "kernel_grid_ms": r_f, "kernel_grid_dydx_ms": r_fd, "permute_copy_ms": r_perm, "kernel_grid_backward_ms": r_b,
+        "kernel_grid_backward_plus_input_ms": r_bi,
+        "ours_grid_forward_ms": ms_f, "ours_grid_forward_dydx_ms": ms_fd, "ours_grid_backward_ms": ms_b, "ours_grid_input_backward_ms": ms_ib,
+        "speedup_forward": (r_f + r_perm) / ms_f, "speedup_forward_dydx": (r_fd + r_perm) / ms_fd, "speedup_backward": r_b / ms_b,
+        "speedup_input_backward": (r_bi - r_b) / ms_ib}
+    del o_ref, dd_ref, g_ref, ge_ref, gi_ref, u
+if ref_s is not None:
+    vd_ray = smp["viewdirs"].reshape(-1, 3).contiguous()
+    vd_smp = vd_ray[:, None, :].expand(-1, S, 3).reshape(-1, 3).contiguous()      # the reference encodes every SAMPLE (sdf_model.py:304)
+    so_ref = torch.empty(N, 16, device=dev)
+    r_sh = timed(lambda: ref_s.sh_encode_forward(vd_smp, so_ref, N, 3, 4, None))
+    ms_sh = timed(lambda: ops.sh_encode_forward(vd_ray, 4))
+    out.setdefault("reference_kernels_same_box", {}).update({"kernel_sh_per_sample_ms": r_sh, "ours_sh_per_ray_ms": ms_sh, "speedup_sh": r_sh / ms_sh})
+    del so_ref, vd_smp
+torch.cuda.empty_cache()
+
 # --- compositing: full-feature inference variant (fp16 features from the field chain) and the stage-1 variant (no features)
 sdf = torch.randn(N, device=dev) * 0.05
 rgb = torch.randn(N, 3, device=dev)
