@@ -48,9 +48,9 @@ struct B2Layer {
 
 struct B2ChainParams {
     uint32_t M_total, rows_per_image, n_units, units_per_cta, n_layers;
-    uint32_t has_in, in_dim;
+    uint32_t has_in, in_dim;            // input stage: d x_in = (last gradient tile) * wgt_in  -- dh_0 W_in, or, when the host collapsed
+    uint32_t in_per_image;              // input_linear into the first FiLM layer, du_0 (gamma_b o W_0 W_in) with per-image weights
     uint32_t top_rank, top_vec0;        // first epilogue: dh_top = sum_r gs * top_rank_s[row*top_rank + r] * vecs[top_vec0 + r] + gs * top_dfeat
-    uint32_t pad;
     const float* top_rank_s;
     const float* top_dfeat;             // fp32 [M, 256] or NULL
     float* d_x_in;
@@ -64,7 +64,7 @@ struct alignas(64) B2ChainMaps {
     CUtensorMap c[BC_MAX_LAYERS];       // sin tile of layer l (its saved output)  [M, 256]  box 128 x 64
     CUtensorMap wgt[BC_MAX_LAYERS];     // (gamma o W_l)^T per image    [B*256, 256]  box (256/CG) x 64
     CUtensorMap dz[BC_MAX_LAYERS];      // du store                     [M, 256]      box 128 x 64
-    CUtensorMap wgt_in;                 // W_in^T                       [in_dim, 256] box (in_dim/CG) x 64
+    CUtensorMap wgt_in;                 // W_in^T [in_dim, 256] or per image [B*in_dim, 256]; box (in_dim/CG) x 64
     CUtensorMap dh0;                    // dh_0 store                   [M, 256]      box 128 x 64
 };
 
@@ -153,7 +153,8 @@ tc_chain_bwd2_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
                     if (P.layer[i].do_D)
                         for (uint32_t kc = 0; kc < 4; kc++) put(&maps.wgt[i], W_BYTES, (int32_t)(kc * 64), img * 256 + (int32_t)(rank * W_ROWS));
                 if (P.has_in)
-                    for (uint32_t kc = 0; kc < 4; kc++) put(&maps.wgt_in, in_box_bytes, (int32_t)(kc * 64), (int32_t)(rank * in_rows));
+                    for (uint32_t kc = 0; kc < 4; kc++)
+                        put(&maps.wgt_in, in_box_bytes, (int32_t)(kc * 64), (int32_t)((P.in_per_image ? img * (int32_t)P.in_dim : 0) + rank * in_rows));
             }
         }
     } else if (warp == CH_WARP_LOAD) {
@@ -205,7 +206,8 @@ tc_chain_bwd2_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
             for (uint32_t u = u_begin; u < u_end; u++) {
                 for (uint32_t i = 0; i < nL; i++) {
                     if (P.layer[i].do_D) gemm(idesc);
-                    else {                                              // du of the bottom layer: written for the storer only
+                    else if (!P.has_in) {                               // du of the bottom layer: written for the storer only (with an input
+                                                                        // stage it is the A operand of that GEMM, below)
                         for (uint32_t kc = 0; kc < 4; kc++) mbar_wait(&S.g_ready[kc], gev & 1);
                         gev++;
                     }
@@ -221,7 +223,7 @@ tc_chain_bwd2_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
             const uint64_t stream = l2_policy_evict_first();
             for (uint32_t u = u_begin; u < u_end; u++) {
                 const int32_t row0 = (int32_t)((u * CG + rank) * CH_TILE_M);
-                const uint32_t n_ev = nL + (P.has_in ? 1u : 0u);
+                const uint32_t n_ev = 1 + nD;                          // top, then one per D epilogue
                 for (uint32_t e = 0; e < n_ev; e++, gev++) {
                     const CUtensorMap* m = e < nL ? &maps.dz[e] : &maps.dh0;
                     for (uint32_t c = 0; c < 4; c++) {

@@ -61,9 +61,10 @@ tc_chain_bwd3_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
     const uint32_t n_mine = u_end > u_begin ? u_end - u_begin : 0u;
     const uint32_t n_pairs = (n_mine + 1) / 2;                         // pair p = units (u_begin + 2p, u_begin + 2p + 1); the last may lack B
     const uint32_t nL = P.n_layers;
-    const uint32_t n_ev = nL + (P.has_in ? 1u : 0u);                   // G events per unit: top, then one per D epilogue
-    const uint32_t n_gemm = n_ev - 1 + (P.has_in ? 1u : 0u);           // GEMMs per unit = accumulator reads per unit
-    const uint32_t nD = n_ev - 1;                                      // D GEMMs per unit (layers with do_D; host guarantees the count)
+    uint32_t nD = 0;                                                   // D GEMMs per unit (layers with do_D; only the bottom layer can lack one)
+    for (uint32_t i = 0; i < nL; i++) nD += P.layer[i].do_D ? 1u : 0u;
+    const uint32_t n_ev = 1 + nD;                                      // G events per unit: top, then one per D epilogue
+    const uint32_t n_gemm = nD + (P.has_in ? 1u : 0u);                 // GEMMs per unit = accumulator reads per unit; GEMM g consumes event g
 
     if (threadIdx.x == 0) {
         for (uint32_t i = 0; i < B3_NC; i++) { mbar_init(&S.c_full[i], 1); mbar_init(&S.c_empty[i], CH_EPI_WARPS); }
@@ -120,7 +121,8 @@ tc_chain_bwd3_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
                         if (g < nD) {
                             for (uint32_t kc = 0; kc < 4; kc++) put(&maps.wgt[li], B3_W_BYTES, (int32_t)(kc * 64), img * 256 + (int32_t)(rank * 128));
                         } else {
-                            for (uint32_t kc = 0; kc < 4; kc++) put(&maps.wgt_in, in_box_bytes, (int32_t)(kc * 64), (int32_t)(rank * in_rows));
+                            for (uint32_t kc = 0; kc < 4; kc++)
+                                put(&maps.wgt_in, in_box_bytes, (int32_t)(kc * 64), (int32_t)((P.in_per_image ? img * (int32_t)P.in_dim : 0) + rank * in_rows));
                         }
                     }
                 }

@@ -100,17 +100,21 @@ def test_full_size_forward_backward_matches_oracle(table_amp, features, precisio
     loss = _loss(thumb, sdf, feat, lw)
     loss.backward()
     errs = {}
+    # floor of the relative error: a gradient that is itself a rounding-level residue of cancelling terms (sigmoid_beta with the
+    # reference's 1e-4 table init: |d beta| ~ 1e-9 of the other gradients, and the fp32 CUDA path vs the CPU oracle already differ
+    # by 100 % on it) is measured against 1e-6 of the largest gradient norm instead of its own
+    floor = 1e-6 * max(float(r.double().norm()) for r in ref["grads"].values())
     for n, p in g.named_parameters():
         r = ref["grads"].get(n)
         if r is None or float(r.abs().max()) == 0.0:
             continue
         assert p.grad is not None, n
-        errs[n] = H.rel_err(p.grad, r)
+        errs[n] = float((p.grad.detach().cpu().double() - r.double()).norm() / max(float(r.double().norm()), floor))
     g.to("cpu")
     worst = max(errs.items(), key=lambda kv: kv[1])
     print("%s table %g features %d: worst gradient rel err %.3e (%s) over %d tensors" % (precision, table_amp, features, worst[1], worst[0], len(errs)))
     assert len(errs) >= 30
-    assert worst[1] < 1e-2, sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+    assert worst[1] < 1e-2, [(n, e, float(ref["grads"][n].double().norm())) for n, e in sorted(errs.items(), key=lambda kv: -kv[1])[:5]]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tc16"])

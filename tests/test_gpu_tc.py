@@ -4,6 +4,8 @@ Tolerances (north star): rendered maps / features / sdf within 2e-2 relative whe
 1e-2 relative of the REFERENCE (fixture digests, test_tc_training_step_matches_reference_fixture; full-size oracle comparison in
 test_gpu_fullsize.py).  The raw GEMM probe is compared against an fp32 matmul of the same fp16-rounded operands, where only the
 accumulation order differs (1e-3 relative to the row scale).  Why fp16 and not bf16: tests/test_operand_precision.py."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -119,8 +121,8 @@ def test_tc_training_step_matches_reference_fixture(name):
     """The BENCHMARKED path (tc16) against the reference's own gradient digests at the north star's 1e-2 -- not against the repo's
     fp32 kernels.  8 x 8 rays x 24 samples = 1536 = 12 x 128 samples per image: tensor-core eligible."""
     from test_gpu_render import check_training_fixture
-    worst = check_training_fixture(name, "tc16", 2e-2, 2e-2)
-    print("worst |grad norm| deviation vs reference: %.3e (%s)" % worst)
+    worst, worst_val = check_training_fixture(name, "tc16", 2e-2, 2e-2, val_tol=float(os.environ.get("SDFG_TEST_VAL_TOL", "1e-2")))
+    print("worst |grad norm| deviation vs reference: %.3e (%s); worst sampled-entry deviation: %.3e (%s)" % (worst + worst_val))
 
 
 def _train_step(g, z, inp, kw):
