@@ -236,6 +236,7 @@ int sdfg_tc_wgrad_probe(const float* dz, const float* x, float* G, uint32_t N, u
  *   sigmoid_beta: device pointer to the learnable scalar (sdf_model.py:163-164)
  *   outputs: rgb_map [NR,3]; feat_map [NR,F] or NULL; xyz_map [NR,3] or NULL; mask [NR] or NULL;
  *            weights [NR,S] or NULL (kept for backward)
+ *   rgb == rgb_map == NULL: sdf-only query (sdf_mesh.py's surface pass needs xyz / mask / sdf only).
  */
 int sdfg_composite_forward(const float* sdf, const float* rgb, const float* feat, const float* z_vals,
                            const float* rays_d, const float* pts, const float* noise, const float* sigmoid_beta,
@@ -255,6 +256,16 @@ int sdfg_composite_backward(const float* sdf, const float* rgb, const float* fea
                             uint64_t NR, uint32_t S, uint32_t F, int with_sdf, int force_background,
                             const float* d_rgb_map, const float* d_feat_map, const float* d_xyz_map, const float* d_mask,
                             float* d_sdf, float* d_rgb, float* d_feat, float* d_pts, float* d_sigmoid_beta, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Frustum -> box resampling of an SDF volume for marching cubes.
+ * ref: align_volume sdf_utils.py:164-184 (torch.meshgrid + F.grid_sample(padding_mode="border", align_corners=True) + the
+ *      out-of-frustum fill with 1).  volume, out: [B, H, W, D, C] fp32 (the renderer's `sdf` output has C = 1).
+ *      out[b,y,x,z,:] = trilinear sample of volume at (x', y', z) with x' = lin(x) * k(z), y' = lin(y) * k(z),
+ *      k(z) = linspace(far/near, 1, D)[z], lin = linspace(-1, 1, .); cells with |x'| > 1 or |y'| > 1 are set to 1.
+ */
+int sdfg_align_volume(const float* volume, float* out, uint32_t B, uint32_t H, uint32_t W, uint32_t D, uint32_t C, float near_, float far_,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -287,3 +287,20 @@ def mlp_init_pass(p, cam_poses, focal, near, far, style, t_rand, *, res=64, S=24
     sdf = raw[..., 3]
     target = pts.detach().norm(dim=-1) - ((far - near) / 4).view(-1, 1, 1, 1)
     return sdf, target
+
+
+def align_volume(volume, near=0.88, far=1.12):
+    """align_volume, sdf_utils.py:164-184: frustum -> box resampling of an sdf volume [b,h,w,d,c] for marching cubes.
+    x/y sampling positions are stretched by linspace(far/near, 1, d) along depth, the volume is resampled trilinearly
+    (grid_sample, align_corners=True, border padding) and cells whose stretched position leaves [-1, 1] are set to 1."""
+    b, h, w, d, c = volume.shape
+    ys, xs, zs = torch.meshgrid(torch.linspace(-1, 1, h), torch.linspace(-1, 1, w), torch.linspace(-1, 1, d), indexing="ij")
+    stretch = torch.linspace(far / near, 1, d).view(1, 1, 1, d)
+    pos = torch.stack([xs.unsqueeze(0) * stretch, ys.unsqueeze(0) * stretch, zs.unsqueeze(0).expand(1, h, w, d)], -1)   # [1,h,w,d,(x,y,z)]
+    outside = ((pos < -1) | (pos > 1)).any(-1, keepdim=True)                                      # :174
+    sample_at = pos.permute(0, 3, 1, 2, 4).contiguous().expand(b, d, h, w, 3)                     # :175  (grid_sample wants [N,D,H,W,3])
+    vol = volume.permute(0, 4, 3, 1, 2).contiguous()                                              # :176  [b,c,d,h,w]
+    res = F.grid_sample(vol, sample_at, padding_mode="border", align_corners=True)                # :177
+    res = res.permute(0, 3, 4, 2, 1).contiguous()                                                 # :178  back to [b,h,w,d,c]
+    res[outside.expand_as(res)] = 1                                                               # :181
+    return res

@@ -101,10 +101,12 @@ __global__ void __launch_bounds__(256) composite_forward_kernel(
         if (s < S) {
             const float w = st.w[i];
             if (weights) weights[base + s] = w;
-            const float* c = rgb + (base + s) * 3;
-            acc[0] = fmaf(w, sigmoidf_(__ldg(c)), acc[0]);
-            acc[1] = fmaf(w, sigmoidf_(__ldg(c + 1)), acc[1]);
-            acc[2] = fmaf(w, sigmoidf_(__ldg(c + 2)), acc[2]);
+            if (rgb) {                                          // NULL: sdf-only query (xyz / mask from the weights alone)
+                const float* c = rgb + (base + s) * 3;
+                acc[0] = fmaf(w, sigmoidf_(__ldg(c)), acc[0]);
+                acc[1] = fmaf(w, sigmoidf_(__ldg(c + 1)), acc[1]);
+                acc[2] = fmaf(w, sigmoidf_(__ldg(c + 2)), acc[2]);
+            }
             if (xyz_map) {
                 const float* p = pts + (base + s) * 3;
                 acc[3] = fmaf(w, __ldg(p), acc[3]);
@@ -117,9 +119,11 @@ __global__ void __launch_bounds__(256) composite_forward_kernel(
 #pragma unroll
     for (int k = 0; k < 6; k++) acc[k] = warp_sum(acc[k]);
     if (lane == 0) {
-        rgb_map[ray * 3 + 0] = -1.f + 2.f * acc[0];
-        rgb_map[ray * 3 + 1] = -1.f + 2.f * acc[1];
-        rgb_map[ray * 3 + 2] = -1.f + 2.f * acc[2];
+        if (rgb_map) {
+            rgb_map[ray * 3 + 0] = -1.f + 2.f * acc[0];
+            rgb_map[ray * 3 + 1] = -1.f + 2.f * acc[1];
+            rgb_map[ray * 3 + 2] = -1.f + 2.f * acc[2];
+        }
         if (xyz_map) { xyz_map[ray * 3] = acc[3]; xyz_map[ray * 3 + 1] = acc[4]; xyz_map[ray * 3 + 2] = acc[5]; }
     }
     if (feat_map) {
@@ -339,7 +343,8 @@ extern "C" int sdfg_composite_forward(const float* sdf, const float* rgb, const 
                                       float* feat_map, float* xyz_map, float* mask, float* weights, void* stream) {
     if (int e = check_composite(S, F, feat)) return e;
     if (NR == 0) return SDFG_OK;
-    SDFG_REQUIRE(sdf && rgb && z_vals && rays_d && rgb_map, SDFG_ERR_INVALID, "composite_forward: null pointer");
+    SDFG_REQUIRE(sdf && z_vals && rays_d && (rgb_map || xyz_map || mask || weights), SDFG_ERR_INVALID, "composite_forward: null pointer");
+    SDFG_REQUIRE((rgb != nullptr) == (rgb_map != nullptr), SDFG_ERR_INVALID, "composite_forward: rgb and rgb_map go together (both NULL = sdf-only query)");
     SDFG_REQUIRE(!with_sdf || sigmoid_beta, SDFG_ERR_INVALID, "composite_forward: sdf mode needs sigmoid_beta");
     SDFG_REQUIRE(!xyz_map || pts, SDFG_ERR_INVALID, "composite_forward: xyz_map needs pts");
     SDFG_REQUIRE(!feat_map || feat, SDFG_ERR_INVALID, "composite_forward: feat_map needs feat");

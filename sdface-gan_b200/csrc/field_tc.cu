@@ -133,7 +133,7 @@ static TcLayout tc_layout(const sdfg_field_params* p, uint64_t N, int save) {
     {   // chain layers: [input_linear | first FiLM layer on x] (small chunk only, 64 columns), then K = 256 + 64 each
         const uint64_t B = ceil_div<uint64_t>(N, std::max(1u, p->samples_per_image));
         const uint32_t n_chain = L.n_layers + (p->has_input_linear ? 1u : 0u);
-        for (uint32_t i = 0; i < n_chain; i++) L.off_wf[i] = take(B * 256 * (i == 0 ? 64 : 320) * 2);
+        for (uint32_t i = 0; i < n_chain; i++) L.off_wf[i] = take(B * 256 * (i == 0 ? 128 : 320) * 2);
         L.off_w10 = take((uint64_t)256 * (p->in_dim + 1) * 4);
     }
     L.total = off;
@@ -290,6 +290,10 @@ static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, co
     return check_launch("tc_chain_fwd_kernel<gemm>");
 }
 
+static bool split_enabled() {
+    static const bool on = []() { const char* e = getenv("SDFG_TC_SPLIT"); return !(e && e[0] == '0'); }();      // SDFG_TC_SPLIT=0: plain fp16 x part
+    return on;
+}
 static bool fchain_enabled() {
     static const bool on = []() { const char* e = getenv("SDFG_TC_FWD"); return !(e && e[0] == 'o'); }();      // SDFG_TC_FWD=old: tc_chain.cuh
     return on;
@@ -377,7 +381,8 @@ struct FoldLayer {
     int film;                   // row of gamma / beta, -1: plain linear layer (gamma = 1, beta = 0)
     uint32_t n_main;            // 4: columns [0, 256) of W are the main part; 0: none
     uint32_t x_cols, x_off, v_cols, v_off;   // W[:, x_off .. x_off + x_cols) -> x part of the small chunk, likewise the view part
-    uint32_t Kp;                // n_main * 64 + 64
+    uint32_t Kp;                // n_main * 64 + 64 (+ 64 with split: a second small chunk holding the fp16 residual of the x columns)
+    uint32_t split;
     h16* out;                   // [B * 256, Kp]
 };
 struct FoldParams {
@@ -390,7 +395,7 @@ struct FoldParams {
 
 // out[b][j][:] = fp16 of [ g W[j, :256] | g W[j, x cols] .. | g W[j, view cols] .. | c_hi c_lo 0 .. ],  g = gamma_b[j], c = g bias[j] + beta_b[j]
 // grid (256 neurons, B images, layers); a thread writes two adjacent columns
-__global__ void __launch_bounds__(160) fold_weights_kernel(const __grid_constant__ FoldParams P) {
+__global__ void __launch_bounds__(192) fold_weights_kernel(const __grid_constant__ FoldParams P) {
     const FoldLayer& Y = P.layer[blockIdx.z];
     const uint32_t j = blockIdx.x, b = blockIdx.y;
     const uint32_t k0 = 2 * threadIdx.x;
@@ -404,7 +409,13 @@ __global__ void __launch_bounds__(160) fold_weights_kernel(const __grid_constant
         const uint32_t k = k0 + e;
         float x = 0.f;
         if (k < main_cols) x = g * __ldg(Wr + k);
-        else {
+        else if (k >= main_cols + 64) {                                 // split: W_lo = fp16(w - fp16(w)) under the x columns
+            const uint32_t s = k - main_cols - 64;
+            if (s < Y.x_cols) {
+                const float w = g * __ldg(Wr + Y.x_off + s);
+                x = w - __half2float(__float2half_rn(w));
+            }
+        } else {
             const uint32_t s = k - main_cols;
             if (s < Y.x_cols) x = g * __ldg(Wr + Y.x_off + s);
             else if (s >= xs && s - xs < Y.v_cols) x = g * __ldg(Wr + Y.v_off + (s - xs));
@@ -452,7 +463,10 @@ static int field_forward_fchain(const sdfg_field_params* p, const TcLayout& L, c
         FoldLayer& Z = F.layer[nl];
         Y.n_main = n_main; Y.use_x = use_x; Y.use_v = use_v; Y.act = film >= 0;
         Y.small_mask = one_mask | (use_x ? x_mask : 0u) | (use_v ? v_mask : 0u);
-        Z.W = Wm; Z.ldw = ldw; Z.bias = bias; Z.film = film; Z.n_main = n_main; Z.Kp = n_main * 64 + 64;
+        const bool split = use_x && film >= 0 && split_enabled();       // the gamma-amplified first layer; a plain input_linear keeps fp16
+        Y.split_x = split; Z.split = split;
+        if (split) P.split_x = 1;
+        Z.W = Wm; Z.ldw = ldw; Z.bias = bias; Z.film = film; Z.n_main = n_main; Z.Kp = n_main * 64 + 64 + (split ? 64 : 0);
         Z.x_cols = use_x ? p->in_dim : 0; Z.x_off = 0; Z.v_cols = use_v ? p->view_dim : 0; Z.v_off = W;
         Z.out = (h16*)(ws + L.off_wf[nl]);
         if (film >= 0 && save) Y.sgn = ws + L.off_c[film];
@@ -501,7 +515,7 @@ static int field_forward_fchain(const sdfg_field_params* p, const TcLayout& L, c
     }
     P.n_layers = nl;
     for (uint32_t i = 0; i < nl; i++) P.layer[i].to_act = (i + 1 < nl || P.layer[i].store) ? 1 : 0;
-    fold_weights_kernel<<<dim3(256, B, nl), 160, 0, st>>>(F);
+    fold_weights_kernel<<<dim3(256, B, nl), 192, 0, st>>>(F);
     if (int e = check_launch("fold_weights_kernel")) return e;
 
     const uint32_t n_tiles = (uint32_t)ceil_div<uint64_t>(N, tc::CH_TILE_M);

@@ -19,6 +19,9 @@
 //   epilogue      16 warps (4 per TMEM lane quarter, 16 columns of every 64-column chunk each): tcgen05.ld (prefetched one chunk
 //                 ahead) -> [sign(cos u) bit masks for the backward] -> sin -> head dot products -> fp16 -> st.shared into ACT in place
 //   storer        (SAVE) TMA-stores finished ACT chunks (saved activations / fp16 features)
+// The first FiLM layer (K = in_dim <= 32, |W| ~ 1/3, gamma ~ 30) is where 16-bit operand rounding hurts: with split_x its x part runs
+// as hi + lo pairs -- x = x_hi + x_lo (a second small operand tile), W = W_hi + W_lo (a second weight chunk), three products
+// W_hi x_hi + W_hi x_lo + W_lo x_hi -- i.e. ~fp32 operands for 4 extra K-steps per tile (tests/test_operand_precision.py).
 // The sine: MUFU.SIN runs at 16 / clk / SM -- 2048 clk per layer and SM, exactly the layer's MMA time -- so CH_POLY_PAIRS of the 8
 // element pairs of every piece take the FMA pipe instead: r = u - k pi with k = rint(u / pi) (the same fma against 1.5 * 2^23 that
 // yields the sign bit), an odd degree-7 minimax polynomial on [-pi/2, pi/2] (max error 1e-6, the level of sin.approx) in packed
@@ -45,6 +48,7 @@ struct FLayer {
     uint32_t n_main;            // 4: K = 256 part (A = ACT, chunks 0..3 of the layer's matrix); 0: small chunk only
     uint32_t small_mask;        // K-steps (of 16 columns) of SMALL / of the small chunk this layer multiplies
     uint32_t use_x, use_v;      // the small chunk reads the x / view part (loader hand-shake)
+    uint32_t split_x;           // x part as hi + lo pairs: a second weight chunk (W_lo) follows the small chunk, SMALL2 holds x_lo
     uint32_t act;               // 1: sin, 0: linear
     uint32_t to_act;            // write the fp16 output into ACT (input of the next layer and / or source of the TMA store)
     uint32_t store;             // SAVE: TMA-store the output with tensor map st[layer]
@@ -60,6 +64,7 @@ struct FLayer {
 struct FChainParams {
     uint32_t M_total, rows_per_image, rows_per_ray, n_units, units_per_cta, n_layers;   // unit = CG adjacent 128-row tiles
     uint32_t in_dim, view_dim, x_nk, v_nk;     // v_nk = 0: no view part
+    uint32_t split_x, pad0;                    // the loader also fills SMALL2 with x_lo = fp16(x - fp16(x))
     const float* x_in;          // [M, in_dim] fp32
     const float* view_feat;     // [M / rows_per_ray, view_dim] fp32
     uint16_t* x16;              // SAVE: fp16 copy of x, [M, kp_x] zero padded (NULL ok)
@@ -88,7 +93,7 @@ struct FChainSmem {
 };
 
 __host__ __device__ inline uint32_t fchain_smem_bytes(int cg) {
-    return 1024 + CH_ACT_BYTES + CH_CHUNK_BYTES + fc_w_stages(cg) * fc_w_bytes(cg) + 2 * CH_SGN_TILE_BYTES + (uint32_t)sizeof(FChainSmem);
+    return 1024 + CH_ACT_BYTES + 2 * CH_CHUNK_BYTES + fc_w_stages(cg) * fc_w_bytes(cg) + 2 * CH_SGN_TILE_BYTES + (uint32_t)sizeof(FChainSmem);
 }
 
 // packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 -- two lanes of fp32 per issue slot)
@@ -123,7 +128,8 @@ tc_fchain_fwd_kernel(const __grid_constant__ FChainMaps maps, const __grid_const
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smACT = smem;
     uint8_t* smSMALL = smACT + CH_ACT_BYTES;
-    uint8_t* smRING = smSMALL + CH_CHUNK_BYTES;
+    uint8_t* smSMALL2 = smSMALL + CH_CHUNK_BYTES;                       // x_lo (split_x)
+    uint8_t* smRING = smSMALL2 + CH_CHUNK_BYTES;
     uint8_t* smSGN = smRING + NW * W_BYTES;                             // two sign-mask tiles (double-buffered by layer)
     FChainSmem& S = *reinterpret_cast<FChainSmem*>(smSGN + 2 * CH_SGN_TILE_BYTES);
 
@@ -161,7 +167,7 @@ tc_fchain_fwd_kernel(const __grid_constant__ FChainMaps maps, const __grid_const
             hrow += nh;
         }
         // SMALL: zero once (padding columns are never written again), then the two constant-one columns of every row
-        for (uint32_t i = threadIdx.x; i < CH_CHUNK_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(smSMALL)[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = threadIdx.x; i < 2 * CH_CHUNK_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(smSMALL)[i] = make_uint4(0, 0, 0, 0);
         __syncthreads();
         for (uint32_t r = threadIdx.x; r < CH_TILE_M; r += blockDim.x)
             *reinterpret_cast<uint32_t*>(smSMALL + sw128(r, 2 * ones_step)) = 0x3C003C00u;      // fp16 {1, 1}
@@ -181,9 +187,9 @@ tc_fchain_fwd_kernel(const __grid_constant__ FChainMaps maps, const __grid_const
                 const int32_t img = (int32_t)(((u * CG + rank) * CH_TILE_M) / P.rows_per_image);
                 const int32_t row = img * 256 + (int32_t)(rank * W_ROWS);
                 for (uint32_t i = 0; i < nL; i++) {
-                    const uint32_t n_main = P.layer[i].n_main;
-                    for (uint32_t k = 0; k <= n_main; k++) {            // the small chunk (column block n_main) first, then the main chunks
-                        const int32_t c0 = (int32_t)((k == 0 ? n_main : k - 1) * 64);
+                    const uint32_t n_main = P.layer[i].n_main, n_small = 1 + P.layer[i].split_x;
+                    for (uint32_t k = 0; k < n_small + n_main; k++) {   // the small chunk(s) (column blocks n_main, n_main + 1) first, then the main chunks
+                        const int32_t c0 = (int32_t)((k < n_small ? n_main + k : k - n_small) * 64);
                         mbar_wait(&S.w_empty[stage], phase ^ 1);
                         if (leader) mbar_arrive_expect_tx(&S.w_full[stage], CG * W_BYTES);
                         if (PAIR) tma_load_2d_2cta_hint(smRING + stage * W_BYTES, &maps.w[i], &S.w_full[stage], c0, row, keep);
@@ -221,6 +227,18 @@ tc_fchain_fwd_kernel(const __grid_constant__ FChainMaps maps, const __grid_const
                                 mma(tmem_d, smem_desc_sw128(a_small + s * 32, 16, 1024), smem_desc_sw128(b_addr + s * 32, 16, 1024), accumulate);
                                 accumulate = 1;
                             }
+                        if (P.layer[i].split_x) {                        // + W_hi x_lo (same chunk), then + W_lo x_hi (next chunk)
+                            const uint32_t a_lo = smem_u32(smSMALL2);
+                            for (uint32_t s = 0; s < P.x_nk; s++)
+                                mma(tmem_d, smem_desc_sw128(a_lo + s * 32, 16, 1024), smem_desc_sw128(b_addr + s * 32, 16, 1024), 1);
+                            commit(&S.w_empty[stage]);
+                            if (++stage == NW) { stage = 0; phase ^= 1; }
+                            mbar_wait(&S.w_full[stage], phase);
+                            tc_fence_after();
+                            const uint32_t b_lo = smem_u32(smRING + stage * W_BYTES);
+                            for (uint32_t s = 0; s < P.x_nk; s++)
+                                mma(tmem_d, smem_desc_sw128(a_small + s * 32, 16, 1024), smem_desc_sw128(b_lo + s * 32, 16, 1024), 1);
+                        }
                         if (P.layer[i].use_x) commit(&S.x_free);
                         if (P.layer[i].use_v) commit(&S.v_free);
                         commit(&S.w_empty[stage]);
@@ -249,7 +267,7 @@ tc_fchain_fwd_kernel(const __grid_constant__ FChainMaps maps, const __grid_const
         const bool x_fast = P.in_dim % 8 == 0 && (reinterpret_cast<uintptr_t>(P.x_in) & 15) == 0;
         const bool v_fast = vu && P.view_dim % 8 == 0 && (reinterpret_cast<uintptr_t>(P.view_feat) & 15) == 0;
         auto fill = [&](const float* src, uint32_t src_ld, uint32_t src_div, uint32_t n_valid, bool fast, uint32_t nu, uint32_t u_off,
-                        uint32_t row0, uint16_t* copy, uint64_t copy_ld, uint32_t copy_cols) {
+                        uint32_t row0, uint16_t* copy, uint64_t copy_ld, uint32_t copy_cols, bool lo) {
             const uint32_t total = CH_TILE_M * nu;
             for (uint32_t base = 0; base < total; base += 128) {
                 float v[4][8];
@@ -275,6 +293,17 @@ tc_fchain_fwd_kernel(const __grid_constant__ FChainMaps maps, const __grid_const
                         const uint32_t row = row0 + r;
                         const uint4 h = pack8(v[j], FMT_F16);
                         *reinterpret_cast<uint4*>(smSMALL + sw128(r, u_off + u)) = h;
+                        if (lo) {                                       // residual of the fp16 rounding, itself as fp16
+                            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+                            float d[8];
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                const float2 f = unpack_f16(hw[k]);
+                                d[2 * k] = v[j][2 * k] - f.x;
+                                d[2 * k + 1] = v[j][2 * k + 1] - f.y;
+                            }
+                            *reinterpret_cast<uint4*>(smSMALL2 + sw128(r, u_off + u)) = pack8(d, FMT_F16);
+                        }
                         if (SAVE && copy && row < P.M_total && u * 8 < copy_cols) *reinterpret_cast<uint4*>(copy + (uint64_t)row * copy_ld + u * 8) = h;
                     }
                 }
@@ -285,13 +314,13 @@ tc_fchain_fwd_kernel(const __grid_constant__ FChainMaps maps, const __grid_const
         for (uint32_t u = u_begin; u < u_end; u++, it++) {
             const uint32_t row0 = (u * CG + rank) * CH_TILE_M;
             mbar_wait(&S.x_free, (it & 1) ^ 1);
-            fill(P.x_in, P.in_dim, 1, P.in_dim, x_fast, xu, 0, row0, P.x16, P.kp_x, P.kp_x);
+            fill(P.x_in, P.in_dim, 1, P.in_dim, x_fast, xu, 0, row0, P.x16, P.kp_x, P.kp_x, P.split_x != 0);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) arrive_mma(&S.x_full);
             if (vu) {
                 mbar_wait(&S.v_free, (it & 1) ^ 1);
-                fill(P.view_feat, P.view_dim, P.rows_per_ray, P.view_dim, v_fast, vu, xu, row0, P.v16, (uint64_t)P.ld_v16, P.kp_v);
+                fill(P.view_feat, P.view_dim, P.rows_per_ray, P.view_dim, v_fast, vu, xu, row0, P.v16, (uint64_t)P.ld_v16, P.kp_v, false);
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) arrive_mma(&S.v_full);

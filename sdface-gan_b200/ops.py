@@ -317,13 +317,13 @@ def tc_wgrad_probe(dz, x, rows_per_image, x_fmt=0):
 # compositing
 
 def composite_forward(sdf, rgb, feat, z_vals, rays_d, pts, noise, sigmoid_beta, S, with_sdf, force_background, want_xyz):
-    """sdf [NR*S]; rgb [NR*S,3]; feat [NR*S,F]|None; z_vals [NR*S]; rays_d [NR,3]; pts [NR*S,3]|None.
-    Returns (rgb_map [NR,3], feat_map [NR,F]|None, xyz [NR,3]|None, mask [NR]|None)."""
+    """sdf [NR*S]; rgb [NR*S,3] (None: sdf-only query, no rgb map); feat [NR*S,F]|None; z_vals [NR*S]; rays_d [NR,3]; pts [NR*S,3]|None.
+    Returns (rgb_map [NR,3]|None, feat_map [NR,F]|None, xyz [NR,3]|None, mask [NR]|None)."""
     lib = _lib.load()
     NR = rays_d.shape[0]
     dev = sdf.device
     F = feat.shape[-1] if feat is not None else 0
-    rgb_map = torch.empty(NR, 3, device=dev)
+    rgb_map = torch.empty(NR, 3, device=dev) if rgb is not None else None
     feat_map = torch.empty(NR, F, device=dev) if feat is not None else None
     xyz = torch.empty(NR, 3, device=dev) if want_xyz else None
     mask = torch.empty(NR, device=dev) if want_xyz else None
@@ -363,6 +363,19 @@ def composite_backward(sdf, rgb, feat, z_vals, rays_d, pts, noise, sigmoid_beta,
                                                _ptr(_chk(d_xyz, "d_xyz")), _ptr(_chk(d_mask, "d_mask")), _ptr(d_sdf), _ptr(d_rgb),
                                                _ptr(d_feat), None, _ptr(d_beta), _stream()), "sdfg_composite_backward")
     return d_sdf, d_rgb, d_feat, d_beta
+
+
+def align_volume(volume, near=0.88, far=1.12):
+    """sdfg_align_volume: volume [B,H,W,D,C] (frustum-sampled sdf) -> the box-aligned volume marching cubes wants (ref sdf_utils.py:164-184)."""
+    lib = _lib.load()
+    _chk(volume, "volume")
+    if volume.dim() != 5:
+        raise RuntimeError("volume must be [B, H, W, D, C]")
+    B, H, W, D, C = volume.shape
+    out = torch.empty_like(volume)
+    with torch.cuda.device(volume.device):
+        _lib.check(lib.sdfg_align_volume(_ptr(volume), _ptr(out), B, H, W, D, C, float(near), float(far), _stream()), "sdfg_align_volume")
+    return out
 
 
 def log2_scale(per_level_scale):

@@ -488,14 +488,18 @@ class _composite(Function):
     @staticmethod
     def forward(ctx, sdf, rgb, feat, sigmoid_beta, z_vals, rays_d, pts, noise, S, with_sdf, force_background, want_xyz):
         ctx.set_materialize_grads(False)
-        sdf, rgb = sdf.contiguous(), rgb.contiguous()
+        sdf = sdf.contiguous()
+        rgb = rgb.contiguous() if rgb is not None else None
         feat = feat.contiguous() if feat is not None else None
         rgb_map, feat_map, xyz, mask = ops.composite_forward(sdf, rgb, feat, z_vals, rays_d, pts if want_xyz else None, noise,
                                                              sigmoid_beta, S, with_sdf, force_background, want_xyz)
         ctx.save_for_backward(sdf, rgb, feat, sigmoid_beta, z_vals, rays_d, pts if want_xyz else None, noise)
         ctx.cfg = (S, with_sdf, force_background, want_xyz)
         empty = sdf.new_empty(0)
-        outs = (rgb_map, feat_map if feat_map is not None else empty, xyz if xyz is not None else empty, mask if mask is not None else empty)
+        outs = (rgb_map if rgb_map is not None else empty, feat_map if feat_map is not None else empty, xyz if xyz is not None else empty,
+                mask if mask is not None else empty)
+        if rgb_map is None:
+            ctx.mark_non_differentiable(outs[0])
         if feat_map is None:
             ctx.mark_non_differentiable(outs[1])
         if not want_xyz:
@@ -538,6 +542,10 @@ class VolumeFeatureRenderer(nn.Module):
         self.force_background = opt.force_background
         self.with_sdf = not opt.no_sdf
         self.output_features = "no_features_output" not in opt.keys()     # by key presence, as the reference (:156-159)
+        # Not in the reference: sdf-only query for mesh extraction (sdf_mesh.py:138-182 keeps sdf / xyz / mask of a 128^3 frustum
+        # and throws rgb and the 256 features away).  When set, the view layer, both rgb outputs and the feature map are skipped:
+        # forward() returns None for them.  Inference only.
+        self.sdf_only = False
         if self.with_sdf:
             self.sigmoid_beta = nn.Parameter(0.1 * torch.ones(1))
 
@@ -612,8 +620,12 @@ class VolumeFeatureRenderer(nn.Module):
         R, S = self.out_im_res, self.N_samples
         smp, near, far = self._sample(c2w, focal, near, far, t_rand=t_rand)
         want_eik = bool(return_eikonal and self.with_sdf)
-        sdf, rgb, feat, dsdf = self.network.forward_rays(smp["npts"], smp["viewdirs"], styles, want_rgb=True,
-                                                         want_feat=self.output_features, want_dsdf=want_eik, feat_f16=True)
+        want_rgb = not self.sdf_only
+        if self.sdf_only and torch.is_grad_enabled():
+            raise RuntimeError("renderer.sdf_only is an inference path: build the Generator with ema=True (or call the renderer under "
+                               "torch.no_grad()) -- note that Generator.forward re-enables grad for a training-mode generator")
+        sdf, rgb, feat, dsdf = self.network.forward_rays(smp["npts"], smp["viewdirs"], styles, want_rgb=want_rgb,
+                                                         want_feat=self.output_features and want_rgb, want_dsdf=want_eik, feat_f16=True)
         noise = None
         if (not self.with_sdf) and self.raw_noise_std > 0.:
             noise = torch.randn_like(sdf) * self.raw_noise_std
@@ -621,8 +633,8 @@ class VolumeFeatureRenderer(nn.Module):
         rgb_map, feat_map, xyz, mask = _composite.apply(sdf, rgb, feat, sb, smp["z_vals"].reshape(-1), smp["rays_d"].reshape(-1, 3),
                                                         smp["pts"].reshape(-1, 3), noise, S, self.with_sdf, self.force_background,
                                                         bool(self.return_xyz))
-        rgb_map = rgb_map.view(B, R, R, 3)
-        feat_map = feat_map.view(B, R, R, -1) if self.output_features else None
+        rgb_map = rgb_map.view(B, R, R, 3) if want_rgb else None
+        feat_map = feat_map.view(B, R, R, -1) if (self.output_features and want_rgb) else None
         sdf_out = sdf.view(B, R, R, S, 1) if self.return_sdf else None
         if self.return_xyz:
             xyz, mask = xyz.view(B, R, R, 3), mask.view(B, R, R, 1)
@@ -646,8 +658,9 @@ class VolumeFeatureRenderer(nn.Module):
     def forward(self, cam_poses, focal, near, far, styles=None, return_eikonal=False, t_rand=None):
         rgb, features, sdf, mask, xyz, eikonal_term = self.render(focal, c2w=cam_poses, near=near, far=far, styles=styles,
                                                                   return_eikonal=return_eikonal, t_rand=t_rand)
-        rgb = rgb.permute(0, 3, 1, 2).contiguous()
-        if self.output_features:
+        if rgb is not None:
+            rgb = rgb.permute(0, 3, 1, 2).contiguous()
+        if features is not None:
             features = features.permute(0, 3, 1, 2).contiguous()
         if xyz is not None:
             xyz = xyz.permute(0, 3, 1, 2).contiguous()

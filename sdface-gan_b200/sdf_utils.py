@@ -72,3 +72,11 @@ def generate_camera_params(resolution, device, batch=1, locations=None, sweep=Fa
     R = torch.stack((x_axis, y_axis, z_axis), dim=1)
     extrinsics = torch.cat((R.transpose(1, 2), camera_loc[:, :, None]), -1)
     return extrinsics, focal, near, far, viewpoint
+
+
+def align_volume(volume, near=0.88, far=1.12):
+    """Frustum -> box resampling of the renderer's sdf volume [B,H,W,D,C] on the GPU (ref align_volume sdf_utils.py:164-184, same
+    signature; the reference runs torch.meshgrid + grid_sample on whatever device the volume is on -- sdf_mesh.py moves it to the
+    CPU first, :152).  CUDA tensors only."""
+    from . import ops
+    return ops.align_volume(volume.contiguous().float(), near, far)

@@ -174,12 +174,28 @@ def camera_goldens():
     print("camera", cam.shape)
 
 
+def align_volume_golden():
+    """The reference's own align_volume (sdf_utils.py:164-184) on a seeded, non-cubic volume (CPU torch; the reference function only accepts batch 1: its grid has batch 1)."""
+    rh.install()
+    from im2scene.sdf.models.sdf_utils import align_volume
+    rs = np.random.RandomState(5)
+    vol = torch.from_numpy(rs.standard_normal((1, 12, 10, 14, 1)).astype(np.float32))
+    out = align_volume(vol.clone())
+    out2 = align_volume(vol.clone(), near=0.7, far=1.3)
+    np.savez_compressed(os.path.join(HERE, "align_volume.npz"), volume=vol.numpy(), out=out.numpy(), out_near07_far13=out2.numpy())
+    print("align_volume", out.shape)
+
+
 def main():
     global run_case
     only = sys.argv[1:]
     if only:
         _rc = run_case
         run_case = lambda name, *a, **k: _rc(name, *a, **k) if name in only else None
+    if not only or "align_volume" in only:
+        align_volume_golden()
+    if only == ["align_volume"]:
+        return
     sh_from_reference_source()
     camera_goldens()
     # config-1 family: --sdf 1 --ngp 0 --fc 0 (SIREN 8x256), forward
@@ -194,6 +210,8 @@ def main():
              return_sdf=True, gen_kwargs=dict(return_sdf=True, return_eikonal=True))
     # full-feature backward (features consumed) -- gradients of thumb only via Generator, features via renderer fwd
     run_case("ngp_train_feat", "ngp", 2, 6, 24, table_std=1.0 / np.sqrt(3.0), perturb=1.0, grads=True)
+    # the same at a tensor-core-eligible size (8 x 8 x 24 = 1536 = 12 x 128 samples per image)
+    run_case("ngp_train_feat8", "ngp", 2, 8, 24, table_std=1.0 / np.sqrt(3.0), perturb=1.0, grads=True)
     run_case("siren_train", "sdf", 2, 6, 24, perturb=1.0, grads=True, no_features_output=True, return_sdf=True,
              gen_kwargs=dict(return_sdf=True, return_eikonal=True))
     # sdf_mesh.py surface generator (sdf_mesh.py:211-214,243-253): static dirs, forced background, xyz/sdf out, S = R

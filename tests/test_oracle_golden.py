@@ -43,7 +43,7 @@ def test_forward_matches_reference(name):
         assert H.max_abs(mask, z["out_mask"]) < 2e-5
 
 
-@pytest.mark.parametrize("name", ["ngp_train", "ngp_train_feat", "siren_train"])
+@pytest.mark.parametrize("name", ["ngp_train", "ngp_train_feat", "ngp_train_feat8", "siren_train"])
 def test_training_step_matches_reference(name):
     z = H.load_fixture(name)
     want_eik = "out_eikonal" in z.files
