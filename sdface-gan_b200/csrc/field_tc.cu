@@ -514,7 +514,20 @@ static int field_forward_fchain(const sdfg_field_params* p, const TcLayout& L, c
         nl++;
     }
     P.n_layers = nl;
-    for (uint32_t i = 0; i < nl; i++) P.layer[i].to_act = (i + 1 < nl || P.layer[i].store) ? 1 : 0;
+    for (uint32_t i = 0; i < nl; i++) {
+        tc::FLayer& Y = P.layer[i];
+        Y.to_act = (i + 1 < nl || Y.store) ? 1 : 0;
+        const bool fin = i + 1 == nl;
+        Y.kind = tc::FK_GENERIC;
+        if (Y.act && !Y.out_f32 && (!save || Y.sgn)) {
+            if (!fin && Y.to_act && Y.nh == 0) Y.kind = tc::FK_FILM;
+            else if (!fin && Y.to_act && Y.nh == 1) Y.kind = tc::FK_FILM_SDF;
+            else if (fin && Y.to_act && Y.nh == 3) Y.kind = tc::FK_VIEWS_FIN;
+            else if (fin && !Y.to_act && Y.nh == 1) Y.kind = tc::FK_SDF_FIN;
+        }
+        static const bool generic_env = getenv("SDFG_TC_GENERIC_EPI") != nullptr;      // A/B: every layer through the run-time-flag body
+        if (generic_env) Y.kind = tc::FK_GENERIC;
+    }
     fold_weights_kernel<<<dim3(256, B, nl), 192, 0, st>>>(F);
     if (int e = check_launch("fold_weights_kernel")) return e;
 

@@ -32,8 +32,26 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// SDFG_WAIT_HINT_NS > 0: try_wait carries a suspend-time hint -- ptxas then emits TRYWAIT; NANOSLEEP.SYNCS <hint>; PHASECHK, i.e. a
+// waiter that found the phase incomplete sleeps until the barrier completes (or the hint elapses) instead of re-polling every ~20
+// clk.  The role threads of the chain kernels sit at the highest warp ids (issue priority): their polling loops measured 15 % of
+// all issued instructions of the forward chain (ncu source page, profiles/r02a), taken from the epilogue warps of the same SMSP.
+#ifndef SDFG_WAIT_HINT_NS
+#define SDFG_WAIT_HINT_NS 20000
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+#if SDFG_WAIT_HINT_NS > 0
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)SDFG_WAIT_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -43,6 +61,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+#endif
     return ok != 0;
 }
 // wait until the phase with the given parity has completed (a fresh barrier passes parity 1 immediately)

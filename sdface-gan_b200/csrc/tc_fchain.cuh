@@ -29,13 +29,15 @@
 // CTA pairs (CG = 2): each CTA stages its own 128 rows of A and HALF of every weight chunk, halving the L2 -> SM weight stream
 // (0.6 MB per tile: at 2 ms per pass a single-CTA chain would need the chip's whole L2 bandwidth for it).
 #pragma once
+#include <type_traits>
+
 #include "tc_chain.cuh"
 
 namespace sdfg {
 namespace tc {
 
 #ifndef SDFG_POLY_PAIRS
-#define SDFG_POLY_PAIRS 3
+#define SDFG_POLY_PAIRS 2
 #endif
 constexpr int CH_POLY_PAIRS = SDFG_POLY_PAIRS;              // of the 8 element pairs per thread and piece: sine on the FMA pipe
 
@@ -44,7 +46,17 @@ __host__ __device__ constexpr uint32_t fc_w_bytes(int cg) { return 32768u / (uin
 __host__ __device__ constexpr uint32_t fc_w_stages(int cg) { return cg == 2 ? 7u : 3u; }
 constexpr uint32_t FC_MAX_W_STAGES = 7;
 
+// layer kinds: the epilogue body is compiled once per kind with the layer's properties as constants (FK_GENERIC reads them at run time)
+enum FKind : int {
+    FK_GENERIC = 0,
+    FK_FILM = 1,        // sin, no head, output feeds the next layer
+    FK_FILM_SDF = 2,    // sin + one head row (sdf), output feeds the next layer
+    FK_VIEWS_FIN = 3,   // sin + three head rows (rgb), last layer, output kept in ACT for the TMA store (features / saved activation)
+    FK_SDF_FIN = 4      // sin + one head row, last layer, output not kept (sdf-only query)
+};
+
 struct FLayer {
+    uint32_t kind;              // FKind
     uint32_t n_main;            // 4: K = 256 part (A = ACT, chunks 0..3 of the layer's matrix); 0: small chunk only
     uint32_t small_mask;        // K-steps (of 16 columns) of SMALL / of the small chunk this layer multiplies
     uint32_t use_x, use_v;      // the small chunk reads the x / view part (loader hand-shake)
@@ -375,121 +387,137 @@ tc_fchain_fwd_kernel(const __grid_constant__ FChainMaps maps, const __grid_const
             const bool valid = row < P.M_total;
             uint32_t hrow = 0;
             for (uint32_t i = 0; i < nL; i++, n++) {
-                // layer description -> registers (constant-bank reads with a dynamic index are slow inside the chunk loop)
-                const uint32_t L_act = P.layer[i].act, L_nh = P.layer[i].nh, L_to_act = P.layer[i].to_act;
-                float* const o32_row = (P.layer[i].out_f32 && valid) ? P.layer[i].out_f32 + row * P.layer[i].ld_out_f32 : nullptr;
-                const bool do_sgn = COS && P.layer[i].sgn != nullptr;
-                const bool fin = i + 1 == nL;
-                const uint32_t acc = n & 1, use = n >> 1;
-                const uint32_t heads_s = smem_u32(&S.heads[hrow][0]);
-                uint64_t hacc2[3] = {0ull, 0ull, 0ull};                 // packed (even, odd) partial head sums
-                mbar_wait(&S.acc_full[acc], use & 1);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((q * 32) << 16) + acc * 256 + sb * 16;
-                uint32_t raw[2][16];
-                tmem_ld16_issue(taddr, raw[0]);
+                // The layer body is instantiated per layer KIND (set by the host): what a layer does -- activation, head rows, final
+                // layer, fp32 copy -- is then a compile-time constant inside the piece loop.  With runtime flags the loop carried ~25
+                // branch / predicate / reconvergence instructions per 16-element piece and predicated-off stores (ncu source page,
+                // profiles/r02a: 13.5 issued instructions per element against ~5 of arithmetic).
+                auto body = [&](auto kind_c) {
+                    constexpr int KIND = decltype(kind_c)::value;
+                    constexpr bool GEN = KIND == FK_GENERIC;
+                    const uint32_t L_act = GEN ? P.layer[i].act : 1u;
+                    const uint32_t L_nh = GEN ? P.layer[i].nh : (KIND == FK_FILM ? 0u : (KIND == FK_FILM_SDF || KIND == FK_SDF_FIN) ? 1u : 3u);
+                    const uint32_t L_to_act = GEN ? P.layer[i].to_act : (KIND == FK_SDF_FIN ? 0u : 1u);
+                    const bool fin = GEN ? (i + 1 == nL) : (KIND == FK_VIEWS_FIN || KIND == FK_SDF_FIN);
+                    float* const o32_row = (GEN && P.layer[i].out_f32 && valid) ? P.layer[i].out_f32 + row * P.layer[i].ld_out_f32 : nullptr;
+                    const bool do_sgn = COS && (GEN ? P.layer[i].sgn != nullptr : true);
+                    const uint32_t acc = n & 1, use = n >> 1;
+                    const uint32_t heads_s = smem_u32(&S.heads[hrow][0]);
+                    uint64_t hacc2[3] = {0ull, 0ull, 0ull};                 // packed (even, odd) partial head sums
+                    mbar_wait(&S.acc_full[acc], use & 1);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((q * 32) << 16) + acc * 256 + sb * 16;
+                    uint32_t raw[2][16];
+                    tmem_ld16_issue(taddr, raw[0]);
 #pragma unroll
-                for (uint32_t c = 0; c < 4; c++) {
-                    const uint32_t col = c * 64 + sb * 16;
-                    tmem_ld_wait16(raw[c & 1]);
-                    if (c < 3) tmem_ld16_issue(taddr + (c + 1) * 64, raw[(c + 1) & 1]);
-                    float v[16];
+                    for (uint32_t c = 0; c < 4; c++) {
+                        const uint32_t col = c * 64 + sb * 16;
+                        tmem_ld_wait16(raw[c & 1]);
+                        if (c < 3) tmem_ld16_issue(taddr + (c + 1) * 64, raw[(c + 1) & 1]);
+                        float v[16];
 #pragma unroll
-                    for (int k = 0; k < 16; k++) v[k] = __uint_as_float(raw[c & 1][k]);
-                    if (L_act) {
-                        // t = u / pi + 1.5 * 2^23: the low mantissa bits hold k = rint(u / pi); parity(k) = sign of cos(u) = sign flip of the
-                        // range-reduced sine.  Needed for all pairs when the masks are recorded, else for the polynomial pairs only.
-                        uint64_t t2[8];
+                        for (int k = 0; k < 16; k++) v[k] = __uint_as_float(raw[c & 1][k]);
+                        if (L_act) {
+                            // t = u / pi + 1.5 * 2^23: the low mantissa bits hold k = rint(u / pi); parity(k) = sign of cos(u) = sign flip of the
+                            // range-reduced sine.  Needed for all pairs when the masks are recorded, else for the polynomial pairs only.
+                            uint64_t t2[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++)
-                            if (do_sgn || j >= 8 - CH_POLY_PAIRS) t2[j] = fma2(pk2(v[2 * j], v[2 * j + 1]), inv_pi2, magic2);
-                        if (do_sgn) {
-                            // A funnel shift per element moves the parity bit into the mask: even elements first, then odd ones, so that
-                            // bit j = element 2j and bit 8 + j = element 2j + 1 (the order the backward chain's packed-half sign flip wants).
-                            uint32_t m = 0;
+                            for (int j = 0; j < 8; j++)
+                                if (do_sgn || j >= 8 - CH_POLY_PAIRS) t2[j] = fma2(pk2(v[2 * j], v[2 * j + 1]), inv_pi2, magic2);
+                            if (do_sgn) {
+                                // A funnel shift per element moves the parity bit into the mask: even elements first, then odd ones, so that
+                                // bit j = element 2j and bit 8 + j = element 2j + 1 (the order the backward chain's packed-half sign flip wants).
+                                uint32_t m = 0;
 #pragma unroll
-                            for (int j = 0; j < 8; j++) m = __funnelshift_r(m, (uint32_t)t2[j], 1);
+                                for (int j = 0; j < 8; j++) m = __funnelshift_r(m, (uint32_t)t2[j], 1);
 #pragma unroll
-                            for (int j = 0; j < 8; j++) m = __funnelshift_r(m, (uint32_t)(t2[j] >> 32), 1);
-                            asm volatile("st.shared.u16 [%0], %1;" ::"r"(smem_u32(smSGN) + (((n & 1) * 16 + c * 4 + sb) * 128 + r) * 2), "h"((uint16_t)(m >> 16)) : "memory");
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            if (j >= 8 - CH_POLY_PAIRS) {
-                                const uint64_t x2 = pk2(v[2 * j], v[2 * j + 1]);
-                                const uint64_t rr = fma2(add2(t2[j], nmagic2), npi2, x2);          // r = u - k pi in [-pi/2, pi/2]
-                                const uint64_t r2 = mul2(rr, rr);
-                                uint64_t p = fma2(c7, r2, c5);
-                                p = fma2(p, r2, c3);
-                                const uint64_t y = fma2(rr, mul2(p, r2), rr);                      // r + r^3 (c3 + c5 r^2 + c7 r^4)
-                                float ylo, yhi;
-                                upk2(y, ylo, yhi);
-                                v[2 * j] = __uint_as_float(__float_as_uint(ylo) ^ ((uint32_t)t2[j] << 31));
-                                v[2 * j + 1] = __uint_as_float(__float_as_uint(yhi) ^ ((uint32_t)(t2[j] >> 32) << 31));
-                            } else {
-                                v[2 * j] = __sinf(v[2 * j]);
-                                v[2 * j + 1] = __sinf(v[2 * j + 1]);
+                                for (int j = 0; j < 8; j++) m = __funnelshift_r(m, (uint32_t)(t2[j] >> 32), 1);
+                                asm volatile("st.shared.u16 [%0], %1;" ::"r"(smem_u32(smSGN) + (((n & 1) * 16 + c * 4 + sb) * 128 + r) * 2), "h"((uint16_t)(m >> 16)) : "memory");
                             }
-                        }
-                    }
-                    if (L_nh) {
 #pragma unroll
-                        for (int hd = 0; hd < 3; hd++) {
-                            if ((uint32_t)hd < L_nh) {
-#pragma unroll
-                                for (int k = 0; k < 16; k += 4) {
-                                    const float4 w4 = lds128(heads_s + (hd * 256 + col + k) * 4);
-                                    hacc2[hd] = fma2(pk2(v[k], v[k + 1]), pk2(w4.x, w4.y), hacc2[hd]);
-                                    hacc2[hd] = fma2(pk2(v[k + 2], v[k + 3]), pk2(w4.z, w4.w), hacc2[hd]);
+                            for (int j = 0; j < 8; j++) {
+                                if (j >= 8 - CH_POLY_PAIRS) {
+                                    const uint64_t x2 = pk2(v[2 * j], v[2 * j + 1]);
+                                    const uint64_t rr = fma2(add2(t2[j], nmagic2), npi2, x2);          // r = u - k pi in [-pi/2, pi/2]
+                                    const uint64_t r2 = mul2(rr, rr);
+                                    uint64_t p = fma2(c7, r2, c5);
+                                    p = fma2(p, r2, c3);
+                                    const uint64_t y = fma2(rr, mul2(p, r2), rr);                      // r + r^3 (c3 + c5 r^2 + c7 r^4)
+                                    float ylo, yhi;
+                                    upk2(y, ylo, yhi);
+                                    v[2 * j] = __uint_as_float(__float_as_uint(ylo) ^ ((uint32_t)t2[j] << 31));
+                                    v[2 * j + 1] = __uint_as_float(__float_as_uint(yhi) ^ ((uint32_t)(t2[j] >> 32) << 31));
+                                } else {
+                                    v[2 * j] = __sinf(v[2 * j]);
+                                    v[2 * j + 1] = __sinf(v[2 * j + 1]);
                                 }
                             }
                         }
-                    }
-                    if (L_to_act) {
-                        const uint4 h0 = make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
-                        const uint4 h1 = make_uint4(pack_f16(v[8], v[9]), pack_f16(v[10], v[11]), pack_f16(v[12], v[13]), pack_f16(v[14], v[15]));
-                        if (SAVE) mbar_wait(&S.st_done[c], (stgen & 1) ^ 1);   // the previous contents of the chunk have been stored
-                        const uint32_t chunk = act_row + c * CH_CHUNK_BYTES;
-                        sts128(chunk + u0, h0);
-                        sts128(chunk + u1, h1);
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) {
-                            if (fin) mbar_arrive(&S.fin_ready[c]);
-                            else {
-                                arrive_mma(&S.act_ready[c]);
-                                if (SAVE) mbar_arrive(&S.act_ready_st[c]);
+                        if (L_nh) {
+#pragma unroll
+                            for (int hd = 0; hd < 3; hd++) {
+                                if ((uint32_t)hd < L_nh) {
+#pragma unroll
+                                    for (int k = 0; k < 16; k += 4) {
+                                        const float4 w4 = lds128(heads_s + (hd * 256 + col + k) * 4);
+                                        hacc2[hd] = fma2(pk2(v[k], v[k + 1]), pk2(w4.x, w4.y), hacc2[hd]);
+                                        hacc2[hd] = fma2(pk2(v[k + 2], v[k + 3]), pk2(w4.z, w4.w), hacc2[hd]);
+                                    }
+                                }
                             }
                         }
-                    }
-                    if (o32_row) {
-                        float4* dst = reinterpret_cast<float4*>(o32_row + col);
+                        if (L_to_act) {
+                            const uint4 h0 = make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
+                            const uint4 h1 = make_uint4(pack_f16(v[8], v[9]), pack_f16(v[10], v[11]), pack_f16(v[12], v[13]), pack_f16(v[14], v[15]));
+                            if (SAVE) mbar_wait(&S.st_done[c], (stgen & 1) ^ 1);   // the previous contents of the chunk have been stored
+                            const uint32_t chunk = act_row + c * CH_CHUNK_BYTES;
+                            sts128(chunk + u0, h0);
+                            sts128(chunk + u1, h1);
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) {
+                                if (fin) mbar_arrive(&S.fin_ready[c]);
+                                else {
+                                    arrive_mma(&S.act_ready[c]);
+                                    if (SAVE) mbar_arrive(&S.act_ready_st[c]);
+                                }
+                            }
+                        }
+                        if (GEN && o32_row) {
+                            float4* dst = reinterpret_cast<float4*>(o32_row + col);
 #pragma unroll
-                        for (int j = 0; j < 4; j++) dst[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+                            for (int j = 0; j < 4; j++) dst[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+                        }
                     }
-                }
-                if (L_to_act) stgen++;
-                // every TMEM read of this layer has completed (wait::ld): hand the accumulator back to the MMA thread
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) arrive_mma(&S.acc_empty[acc]);
-                if (L_nh) {                                             // combine the four sub-blocks' partial dot products
-                    float hacc[3];
+                    if (L_to_act) stgen++;
+                    // every TMEM read of this layer has completed (wait::ld): hand the accumulator back to the MMA thread
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) arrive_mma(&S.acc_empty[acc]);
+                    if (L_nh) {                                             // combine the four sub-blocks' partial dot products
+                        float hacc[3];
 #pragma unroll
-                    for (int hd = 0; hd < 3; hd++) { float lo, hi; upk2(hacc2[hd], lo, hi); hacc[hd] = lo + hi; }
-                    if (sb != 0) {
+                        for (int hd = 0; hd < 3; hd++) { float lo, hi; upk2(hacc2[hd], lo, hi); hacc[hd] = lo + hi; }
+                        if (sb != 0) {
 #pragma unroll
-                        for (int hd = 0; hd < 3; hd++) S.hx[sb - 1][r][hd] = hacc[hd];
+                            for (int hd = 0; hd < 3; hd++) S.hx[sb - 1][r][hd] = hacc[hd];
+                        }
+                        named_bar_sync(2 + q, 128);                       // only the four warps that share these rows (one per column sub-block)
+                        if (sb == 0 && valid) {
+                            float* oh = P.layer[i].out_head;
+#pragma unroll
+                            for (int hd = 0; hd < 3; hd++)
+                                if ((uint32_t)hd < L_nh) oh[row * L_nh + hd] = hacc[hd] + S.hx[0][r][hd] + S.hx[1][r][hd] + S.hx[2][r][hd] + S.hbias[hrow + hd];
+                        }
+                        named_bar_sync(2 + q, 128);                       // hx is free again before the next head layer writes it
+                        hrow += L_nh;
                     }
-                    named_bar_sync(2 + q, 128);                       // only the four warps that share these rows (one per column sub-block)
-                    if (sb == 0 && valid) {
-                        float* oh = P.layer[i].out_head;
-#pragma unroll
-                        for (int hd = 0; hd < 3; hd++)
-                            if ((uint32_t)hd < L_nh) oh[row * L_nh + hd] = hacc[hd] + S.hx[0][r][hd] + S.hx[1][r][hd] + S.hx[2][r][hd] + S.hbias[hrow + hd];
-                    }
-                    named_bar_sync(2 + q, 128);                       // hx is free again before the next head layer writes it
-                    hrow += L_nh;
+                };
+                switch (P.layer[i].kind) {
+                    case FK_FILM: body(std::integral_constant<int, FK_FILM>{}); break;
+                    case FK_FILM_SDF: body(std::integral_constant<int, FK_FILM_SDF>{}); break;
+                    case FK_VIEWS_FIN: body(std::integral_constant<int, FK_VIEWS_FIN>{}); break;
+                    case FK_SDF_FIN: body(std::integral_constant<int, FK_SDF_FIN>{}); break;
+                    default: body(std::integral_constant<int, FK_GENERIC>{}); break;
                 }
             }
         }
