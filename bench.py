@@ -264,6 +264,55 @@ def run_ours(args):
                          "field_chain_ms": ik_ms / max(ik_n, 1),
                          "field_chain_tflops": B * SAMPLES_PER_IMAGE * FIELD_FLOP_FWD / (ik_ms / max(ik_n, 1) * 1e-3) / 1e12 if ik_n else None}
 
+    # --- configs[2]: the 256^2 generator forward (renderer 64^2 x 24 -> StyleGAN2 decoder -> 256^2), eval, B = 64 split over the GPUs
+    #     (strong scaling: 64 / world images per GPU and pass); end to end from resident latents / cameras to the image tensor
+    inf256 = None
+    if args.precision == "tc16" and 64 % world == 0:
+        Bi = 64 // world
+        mo_d, ro_d = sg.default_options("ngp", size=256, renderer_res=R, n_samples=S, perturb=0.)
+        g_full = sg.Generator(mo_d, ro_d, full_pipeline=True, ema=True).to(dev).eval()
+        g_full.renderer.network.precision = args.precision
+        cam_i, focal_i, near_i, far_i, _ = sg.generate_camera_params(R, dev, batch=Bi)
+        z_i = torch.randn(Bi, STYLE, device=dev)
+        with torch.no_grad():
+            for _ in range(3):
+                g_full([z_i], cam_i, focal_i, near_i, far_i)
+            barrier()
+            sg._lib.prof_enable(True, "gemm")
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(args.steps):
+                img, _thumb = g_full([z_i], cam_i, focal_i, near_i, far_i)
+            f1.record()
+            barrier()
+            sg._lib.prof_enable(False, "")
+            gk_ms, gk_n = sg._lib.prof_collect()
+            # renderer alone (same batch), to split the pass
+            style_i = g_full.style(z_i)
+            for _ in range(2):
+                g_full.renderer(cam_i, focal_i, near_i, far_i, styles=style_i)
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for _ in range(args.steps):
+                g_full.renderer(cam_i, focal_i, near_i, far_i, styles=style_i)
+            r1.record()
+            barrier()
+        t = torch.tensor([f0.elapsed_time(f1) / args.steps, r0.elapsed_time(r1) / args.steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        full_ms, rend_ms = float(t[0]), float(t[1])
+        # decoder MACs per image: 3x3 modulated convolutions 256->512@64^2, 512->256 (x2 up), 256->256@128^2, 256->128 (x2 up), 128->128@256^2
+        dec_flop = 2 * 9 * (64 * 64 * 256 * 512 + 64 * 64 * 512 * 256 + 128 * 128 * 256 * 256 + 128 * 128 * 256 * 128 + 256 * 256 * 128 * 128)
+        inf256 = {"workload": "configs[2]: ffhq_256_sdf_ngp generator forward (renderer + decoder), eval, B = 64 over %d GPU(s)" % world,
+                  "batch_per_gpu": Bi, "ms_per_pass": full_ms, "images_per_s": 64 / (full_ms * 1e-3), "renderer_ms": rend_ms,
+                  "decoder_ms": full_ms - rend_ms, "scaling": "strong",
+                  "gemm_kernel_ms_per_pass": gk_ms / args.steps, "gemm_kernel_launches_per_pass": gk_n / args.steps,
+                  "generator_tflops_algorithmic": Bi * (SAMPLES_PER_IMAGE * FIELD_FLOP_FWD + dec_flop) / (full_ms * 1e-3) / 1e12,
+                  "image_shape": list(img.shape)}
+        del g_full
+        torch.cuda.empty_cache()
+
     if rank == 0:
         peaks = {}
         try:
@@ -281,17 +330,25 @@ def run_ours(args):
                          + (trunk + first)                      # eikonal pass: trunk dgrads + input-linear dgrad
                          + (2 * trunk + 2 * first + views + 2 * 256 * 256 + 2 * 16 * 256))   # backward: dgrad + wgrad
         achieved = flop_step / (k_ms / args.steps * 1e-3) / 1e12 if k_n else None
+        # what the kernels EXECUTE is less: input_linear is folded into the first FiLM layer (its x part as hi + lo pairs), every layer
+        # carries one K = 16 step for the folded FiLM offset.  MMA K per layer: 112 | 272 | 272 | 288 (forward); 2 trunk dgrads + the
+        # N = 32 input stage (eikonal); 3 dgrads + input stage + weight gradients with K = 288 | 272 | 272 | 48 (backward).
+        flop_exec = N * 2 * 256 * ((112 + 272 + 272 + 288) + (2 * 256 + 32) + (3 * 256 + 32) + (288 + 272 + 272 + 48))
         traffic, traffic_note = None, None
-        try:        # dram bytes per launch of the largest GEMM-class kernel, from the committed ncu --set full capture (B = 32)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        try:        # dram bytes of the same launches per step, from the committed ncu --set full capture (B = 32)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
             if B == tj.get("batch") and args.precision == "tc16":
-                traffic, traffic_note = tj["dram_bytes_per_launch"], tj["note"]
+                traffic, traffic_note = tj["dram_bytes_per_step"], tj["note"]
         except Exception:
             pass
         roof = {"bound": "tensor", "kernel": "field GEMMs (%s)" % ("gemm_f32_kernel, fp32 SIMT" if args.precision == "fp32" else "tcgen05"),
                 "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": (achieved / tensor_peak) if achieved else None,
                 "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src, "kernel_ms_per_step": k_ms / args.steps, "kernel_launches_per_step": k_n / args.steps,
-                "kernel_share_of_step": (k_ms / args.steps) / ms}
+                "kernel_share_of_step": (k_ms / args.steps) / ms,
+                "algorithmic_flop_per_step": flop_step, "executed_flop_per_step": flop_exec if args.precision == "tc16" else flop_step,
+                "achieved_executed": (flop_exec / (k_ms / args.steps * 1e-3) / 1e12) if (k_n and args.precision == "tc16") else achieved,
+                "note": "achieved = algorithmic GEMM flop of the reference network for this step (SURVEY 8d: forward 550 912 flop/sample incl. heads' "
+                        "GEMM part, eikonal dgrads, backward dgrad + wgrad) / summed CUDA-event time of the tcgen05 launches of the step"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
@@ -314,7 +371,7 @@ def run_ours(args):
                            "l2": "per-step saved activations + gradient tiles (%.1f GB) exceed the 126 MB L2; no flush needed" % (N * 5.3e3 / 1e9)},
                 "clocks": clk.summary(),
                 "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-                "gpu_launches": launches, "roofline": roof, "inference": inf, "cpu_baseline": cpu}
+                "gpu_launches": launches, "roofline": roof, "inference": inf, "inference_256": inf256, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

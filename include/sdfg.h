@@ -267,6 +267,40 @@ int sdfg_composite_backward(const float* sdf, const float* rgb, const float* fea
 int sdfg_align_volume(const float* volume, float* out, uint32_t B, uint32_t H, uint32_t W, uint32_t D, uint32_t C, float near_, float far_,
                       void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * StyleGAN2 decoder, forward (ref Decoder sdf_model.py:883-1056, ModulatedConv2d :614-704, StyledConv :793-818,
+ * ToRGB :821-843, Upsample / Blur :480-538, fused_leaky_relu + upfirdn2d sdf_op.py).  Activations are channels-last fp16
+ * [B, H, W, C]; the caller allocates everything.
+ */
+/* fp32 -> fp16, same element order (the renderer's feature map [B, H*W, C] is channels-last already) */
+int sdfg_nhwc16(const float* in, uint16_t* out, uint64_t n_elems, void* stream);
+
+/* per-sample weights of a ModulatedConv2d (:655-669): out[b][tap][o][i] = fp16(scale * weight[o][i][tap] * style[b][i] * demod[b][o]),
+ * demod[b][o] = rsqrt(sum_{i,tap} (scale * weight * style)^2 + 1e-8) when `demodulate`, else 1.  weight [Cout, Cin, taps] (the
+ * reference parameter [1, Cout, Cin, k, k]), style [B, Cin] (output of the layer's `modulation` EqualLinear), demod_scratch [B, Cout]. */
+int sdfg_modconv_fold(const float* weight, const float* style, float scale, uint32_t B, uint32_t Cin, uint32_t Cout, uint32_t taps,
+                      int demodulate, float* demod_scratch, uint16_t* out, void* stream);
+
+/* gemm_mode 0: 3 x 3 (taps = 9) / 1 x 1 (taps = 1) convolution, stride 1, zero padding, on per-sample weights wf (sdfg_modconv_fold),
+ *   fused with out = leaky_relu(conv + noise_w[0] * noise[b,y,x] + bias[o], 0.2) * sqrt(2) (NoiseInjection + FusedLeakyReLU);
+ *   out [B, H, W, Cout].  noise [B, H, W] / noise_w (device scalar) / bias [Cout] may be NULL.
+ * gemm_mode 1: the tap matrices side by side, out[b, pixel, tap * Cout + o] = sum_i x[b, pixel, i] * wf[b][tap][o][i]  (raw fp16):
+ *   the transposed convolution of an up-sampling StyledConv before sdfg_upconv_gather.  out [B, H, W, taps * Cout].
+ * Cin % 64 == 0, Cout % 128 == 0, W a power of two >= 8. */
+int sdfg_conv_forward(const uint16_t* x, const uint16_t* wf, uint32_t B, uint32_t H, uint32_t W, uint32_t Cin, uint32_t Cout, uint32_t taps,
+                      int gemm_mode, const float* bias, const float* noise, const float* noise_w, uint16_t* out, void* stream);
+
+/* y [B, H, W, 9 * C] (gemm_mode output) -> out [B, 2H, 2W, C]: conv_transpose2d(stride 2) tap sum, Blur(outer([1,3,3,1]) / 16, pad (1,1)),
+ * + noise_w[0] * noise[b, Y, X] + bias[o], leaky_relu(0.2) * sqrt(2).  ref ModulatedConv2d.forward :671-684 + StyledConv.forward :812-816. */
+int sdfg_upconv_gather(const uint16_t* y, uint32_t B, uint32_t H, uint32_t W, uint32_t C, const float* bias, const float* noise,
+                       const float* noise_w, uint16_t* out, void* stream);
+
+/* ToRGB (:821-843): 1 x 1 modulated convolution without demodulation to 3 channels + bias [3] + (skip != NULL) the previous level's
+ * rgb [B, H/2, W/2, 3] up-sampled by Upsample (upfirdn2d up = 2, outer([1,3,3,1]) / 16, pad (2, 1)).  weight [3, C], style [B, C],
+ * wrgb_scratch [B, 3, C].  Outputs (either may be NULL): out_nhwc [B, H, W, 3] (skip of the next level), out_nchw [B, 3, H, W]. */
+int sdfg_to_rgb(const uint16_t* x, const float* weight, const float* style, float scale, const float* bias, const float* skip, uint32_t B,
+                uint32_t H, uint32_t W, uint32_t C, float* wrgb_scratch, float* out_nhwc, float* out_nchw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,278 @@
+// StyleGAN2 decoder (ref sdf_model.py:614-1056 + sdf_op.py) -- forward kernels behind the C ABI (include/sdfg.h):
+//   sdfg_nhwc16                 fp32 [B, H*W, C] (the renderer's feature map, channels last) -> fp16 [B, H, W, C]
+//   sdfg_modconv_fold           per-sample weights of a ModulatedConv2d: scale * W * style, demodulated           (:655-669)
+//   sdfg_conv_forward           3 x 3 convolution / plain GEMM on tcgen05 (tc_conv.cuh) + noise + bias + leaky ReLU (:790-818)
+//   sdfg_upconv_gather          transposed-convolution taps -> blur -> noise + bias + leaky ReLU                 (:671-684, Blur :522-538)
+//   sdfg_to_rgb                 1 x 1 modulated convolution to 3 channels + bias + up-sampled skip               (:821-843, Upsample :480-499)
+// Activations are channels-last fp16; every kernel takes a stream; nothing allocates.
+#include <algorithm>
+#include <memory>
+#include <vector>
+
+#include "tc_conv.cuh"
+
+namespace sdfg {
+
+int make_tensor_map_16_4d(CUtensorMap* out, const void* base, uint32_t B, uint32_t H, uint32_t W, uint32_t C, uint32_t box_w, uint32_t box_h);
+
+static int optin_smem_conv(const void* fn, uint32_t smem) {
+    struct Done { int dev; uint32_t smem; };
+    static thread_local std::vector<Done> done;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "conv: cudaGetDevice failed");
+    for (const Done& d : done)
+        if (d.dev == dev && d.smem >= smem) return SDFG_OK;
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return set_error(SDFG_ERR_CUDA, "conv: cannot opt in to %u bytes of shared memory", smem);
+    done.push_back({dev, smem});
+    return SDFG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nhwc16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, uint64_t n4) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = ldg_stream4(reinterpret_cast<const float4*>(in) + i);
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(tc::pack_f16_sat(v.x, v.y), tc::pack_f16_sat(v.z, v.w));
+}
+
+// demod[b, o] = rsqrt(sum_{i, tap} (scale * W[o, i, tap] * s[b, i])^2 + 1e-8)                      block = (o, b), threads over i * taps
+__global__ void __launch_bounds__(256) demod_kernel(const float* __restrict__ W, const float* __restrict__ style, float scale, uint32_t Cin,
+                                                     uint32_t Cout, uint32_t taps, float* __restrict__ demod) {
+    __shared__ float red[8];
+    const uint32_t o = blockIdx.x, b = blockIdx.y;
+    const float* Wo = W + (size_t)o * Cin * taps;
+    float acc = 0.f;
+    for (uint32_t k = threadIdx.x; k < Cin * taps; k += blockDim.x) {
+        const float w = scale * __ldg(Wo + k) * __ldg(style + (size_t)b * Cin + k / taps);
+        acc = fmaf(w, w, acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; i++) t += red[i];
+        demod[(size_t)b * Cout + o] = rsqrtf(t + 1e-8f);
+    }
+}
+
+// Wf[b][tap][o][i] = fp16(scale * W[o, i, tap] * s[b, i] * demod[b, o])          (W is [Cout, Cin, taps] row-major: the reference's
+// weight[0, o, i, a, b'] with tap = a * k + b')            grid (Cout, B), threads over i; one 16-bit store per (tap, i)
+__global__ void __launch_bounds__(256) modconv_fold_kernel(const float* __restrict__ W, const float* __restrict__ style, const float* __restrict__ demod,
+                                                            float scale, uint32_t Cin, uint32_t Cout, uint32_t taps, uint16_t* __restrict__ out) {
+    const uint32_t o = blockIdx.x, b = blockIdx.y;
+    const float d = demod ? __ldg(demod + (size_t)b * Cout + o) : 1.f;
+    for (uint32_t i = threadIdx.x; i < Cin; i += blockDim.x) {
+        const float s = scale * d * __ldg(style + (size_t)b * Cin + i);
+        for (uint32_t t = 0; t < taps; t++)
+            out[(((size_t)b * taps + t) * Cout + o) * Cin + i] = __half_as_ushort(__float2half_rn(s * __ldg(W + ((size_t)o * Cin + i) * taps + t)));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Up-sampling StyledConv, second half.  Y[b, (y, x), tap * C + o] holds the nine tap products of the transposed convolution
+// (conv_transpose2d, stride 2: T[2y + a, 2x + b'] += Y[(y, x), (a, b')], T is (2H + 1)^2).  out = lrelu(blur(T) + noise + bias) * sqrt(2)
+// with blur = upfirdn2d(T, outer([1,3,3,1]) / 16, pad (1, 1)):  out[Y, X] = sum_{p, q < 4} k[p] k[q] T[Y + p - 1, X + q - 1].
+// Block: 8 x 8 output pixels x 64 channels; the 11 x 11 patch of T is assembled in shared memory (<= 4 reads of Y per element).
+constexpr int UG_T = 8;
+__global__ void __launch_bounds__(256) upconv_gather_kernel(const uint16_t* __restrict__ Y, uint32_t B, uint32_t H, uint32_t W, uint32_t C,
+                                                             const float* __restrict__ bias, const float* __restrict__ noise,
+                                                             const float* __restrict__ noise_w, uint16_t* __restrict__ out) {
+    __shared__ float T[UG_T + 3][UG_T + 3][64];
+    const uint32_t ch = threadIdx.x & 63, sub = threadIdx.x >> 6;       // 4 pixel slots x 64 channels
+    const uint32_t Ho = 2 * H, Wo = 2 * W;
+    const uint32_t c0 = blockIdx.y * 64;
+    const uint32_t tiles_x = (Wo + UG_T - 1) / UG_T, tiles_y = (Ho + UG_T - 1) / UG_T;
+    const uint32_t b = blockIdx.x / (tiles_x * tiles_y), t = blockIdx.x % (tiles_x * tiles_y);
+    const int Y0 = (int)(t / tiles_x) * UG_T, X0 = (int)(t % tiles_x) * UG_T;
+    const size_t ldy = (size_t)9 * C;
+    const uint16_t* Yb = Y + (size_t)b * H * W * ldy + c0 + ch;
+    for (int e = sub; e < (UG_T + 3) * (UG_T + 3); e += 4) {
+        const int tr = e / (UG_T + 3), tcn = e % (UG_T + 3);
+        const int r = Y0 + tr - 1, c = X0 + tcn - 1;                    // position in T
+        float acc = 0.f;
+        if (r >= 0 && c >= 0 && r <= (int)Ho && c <= (int)Wo) {
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                if (((r - a) & 1) || r - a < 0) continue;
+                const int y = (r - a) >> 1;
+                if (y >= (int)H) continue;
+#pragma unroll
+                for (int bb = 0; bb < 3; bb++) {
+                    if (((c - bb) & 1) || c - bb < 0) continue;
+                    const int x = (c - bb) >> 1;
+                    if (x >= (int)W) continue;
+                    acc += __half2float(__ushort_as_half(__ldg(Yb + ((size_t)y * W + x) * ldy + (size_t)(a * 3 + bb) * C)));
+                }
+            }
+        }
+        T[tr][tcn][ch] = acc;
+    }
+    __syncthreads();
+    const float nw = (noise && noise_w) ? __ldg(noise_w) : 0.f;
+    const float bs = bias ? __ldg(bias + c0 + ch) : 0.f;
+    const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};                  // [1,3,3,1] / 4 per axis: make_kernel (outer / 64) * upsample_factor^2 (Blur :522-531)
+    for (int e = sub; e < UG_T * UG_T; e += 4) {
+        const int oy = e / UG_T, ox = e % UG_T;
+        const int Yo = Y0 + oy, Xo = X0 + ox;
+        if (Yo >= (int)Ho || Xo >= (int)Wo) continue;
+        float acc = 0.f;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            float rowacc = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; q++) rowacc = fmaf(k4[q], T[oy + p][ox + q][ch], rowacc);
+            acc = fmaf(k4[p], rowacc, acc);
+        }
+        const size_t pix = ((size_t)b * Ho + Yo) * Wo + Xo;
+        float v = acc + bs + (nw != 0.f ? nw * __ldg(noise + pix) : 0.f);
+        v = (v > 0.f ? v : 0.2f * v) * 1.4142135623730951f;
+        out[pix * C + c0 + ch] = __half_as_ushort(__float2half_rn(v));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ToRGB: rgb[b, y, x, c] = sum_i x[b, y, x, i] * wrgb[b, c, i] + bias[c] (+ upsample(skip)[y, x, c]); wrgb = scale * W * style (no
+// demodulation).  skip [B, H/2, W/2, 3] fp32 is up-sampled by upfirdn2d(up = 2, kernel outer([1,3,3,1]) / 16, pad (2, 1)) on the fly:
+// out[Y, X] = sum_{p, q} k[p] k[q] U[Y + p - 2, X + q - 2], U[2y, 2x] = skip[y, x], zero elsewhere.   warp per pixel.
+// out_nchw (fp32 [B, 3, H, W], the image) and / or out_nhwc (fp32 [B, H, W, 3], the next level's skip)
+__global__ void __launch_bounds__(256) to_rgb_kernel(const uint16_t* __restrict__ x, const float* __restrict__ wrgb, const float* __restrict__ bias,
+                                                      const float* __restrict__ skip, uint32_t B, uint32_t H, uint32_t W, uint32_t C,
+                                                      float* __restrict__ out_nhwc, float* __restrict__ out_nchw) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t pix = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pix >= (uint64_t)B * H * W) return;
+    const uint32_t b = (uint32_t)(pix / ((uint64_t)H * W));
+    const uint32_t yx = (uint32_t)(pix % ((uint64_t)H * W)), Yo = yx / W, Xo = yx % W;
+    const uint16_t* xr = x + pix * C;
+    const float* w = wrgb + (size_t)b * 3 * C;
+    float acc[3] = {0.f, 0.f, 0.f};
+    for (uint32_t i = lane * 8; i < C; i += 256) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + i));
+        const uint32_t hw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float2 f = tc::unpack_f16(hw[k]);
+#pragma unroll
+            for (int c = 0; c < 3; c++) acc[c] = fmaf(f.x, __ldg(w + c * C + i + 2 * k), fmaf(f.y, __ldg(w + c * C + i + 2 * k + 1), acc[c]));
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) acc[c] = warp_sum(acc[c]);
+    if (lane < 3) {
+        float v = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : acc[2]) + __ldg(bias + lane);
+        if (skip) {
+            const uint32_t Hs = H / 2, Ws = W / 2;
+            const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};          // [1,3,3,1] / 8 * 2 per axis (kernel * factor^2 over both axes)
+            float s = 0.f;
+            for (int p = 0; p < 4; p++) {
+                const int r = (int)Yo + p - 2;
+                if (r < 0 || (r & 1) || (r >> 1) >= (int)Hs) continue;
+                for (int q = 0; q < 4; q++) {
+                    const int c = (int)Xo + q - 2;
+                    if (c < 0 || (c & 1) || (c >> 1) >= (int)Ws) continue;
+                    s = fmaf(k4[p] * k4[q], __ldg(skip + (((size_t)b * Hs + (r >> 1)) * Ws + (c >> 1)) * 3 + lane), s);
+                }
+            }
+            v += s;
+        }
+        if (out_nhwc) out_nhwc[pix * 3 + lane] = v;
+        if (out_nchw) out_nchw[(((size_t)b * 3 + lane) * H + Yo) * W + Xo] = v;
+    }
+}
+
+// wrgb[b, c, i] = scale * W[c, i] * style[b, i]
+__global__ void __launch_bounds__(256) rgb_weight_kernel(const float* __restrict__ W, const float* __restrict__ style, float scale, uint32_t C,
+                                                          uint32_t B, float* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 3 * C) return;
+    const uint32_t b = i / (3 * C), k = i % (3 * C);
+    out[i] = scale * __ldg(W + k) * __ldg(style + (size_t)b * C + k % C);
+}
+
+}  // namespace sdfg
+
+using namespace sdfg;
+
+extern "C" int sdfg_nhwc16(const float* in, uint16_t* out, uint64_t n_elems, void* stream) {
+    if (n_elems == 0) return SDFG_OK;
+    SDFG_REQUIRE(in && out && n_elems % 4 == 0, SDFG_ERR_INVALID, "nhwc16: null pointer or element count not a multiple of 4");
+    nhwc16_kernel<<<(unsigned)ceil_div<uint64_t>(n_elems / 4, 256), 256, 0, (cudaStream_t)stream>>>(in, out, n_elems / 4);
+    return check_launch("nhwc16_kernel");
+}
+
+extern "C" int sdfg_modconv_fold(const float* weight, const float* style, float scale, uint32_t B, uint32_t Cin, uint32_t Cout, uint32_t taps,
+                                 int demodulate, float* demod_scratch, uint16_t* out, void* stream) {
+    if (B == 0) return SDFG_OK;
+    SDFG_REQUIRE(weight && style && out && (!demodulate || demod_scratch), SDFG_ERR_INVALID, "modconv_fold: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (demodulate) {
+        demod_kernel<<<dim3(Cout, B), 256, 0, st>>>(weight, style, scale, Cin, Cout, taps, demod_scratch);
+        if (int e = check_launch("demod_kernel")) return e;
+    }
+    modconv_fold_kernel<<<dim3(Cout, B), 256, 0, st>>>(weight, style, demodulate ? demod_scratch : nullptr, scale, Cin, Cout, taps, out);
+    return check_launch("modconv_fold_kernel");
+}
+
+extern "C" int sdfg_conv_forward(const uint16_t* x, const uint16_t* wf, uint32_t B, uint32_t H, uint32_t W, uint32_t Cin, uint32_t Cout, uint32_t taps,
+                                 int gemm_mode, const float* bias, const float* noise, const float* noise_w, uint16_t* out, void* stream) {
+    if (B == 0) return SDFG_OK;
+    SDFG_REQUIRE(x && wf && out, SDFG_ERR_INVALID, "conv_forward: null pointer");
+    SDFG_REQUIRE(Cin % 64 == 0 && Cout % 128 == 0, SDFG_ERR_UNSUPPORTED, "conv_forward: Cin must be a multiple of 64 and Cout of 128 (got %u, %u)", Cin, Cout);
+    SDFG_REQUIRE(taps == 9 || taps == 1, SDFG_ERR_UNSUPPORTED, "conv_forward: 3 x 3 (taps = 9) or 1 x 1 (taps = 1) only");
+    SDFG_REQUIRE(W >= 8 && (W & (W - 1)) == 0, SDFG_ERR_UNSUPPORTED, "conv_forward: width must be a power of two >= 8 (got %u)", W);
+    tc::ConvParams P = {};
+    P.B = B; P.H = H; P.W = W; P.Cin = Cin;
+    // gemm_mode: the nine tap matrices are NOT summed over shifted inputs but laid side by side as 9 * Cout output columns
+    P.taps = gemm_mode ? 1 : taps;
+    P.ncols = gemm_mode ? taps * Cout : Cout;
+    P.wrows_per_sample = taps * Cout;
+    P.NT = (P.ncols % 256 == 0) ? 256 : 128;
+    P.bw = std::min(W, 128u); P.bh = 128 / P.bw;
+    P.tiles_x = W / P.bw; P.tiles_y = ceil_div<uint32_t>(H, P.bh);
+    P.pairs_per_sample = ceil_div<uint32_t>(P.tiles_x * P.tiles_y, 2);
+    P.n_nt = P.ncols / P.NT;
+    P.n_units = B * P.pairs_per_sample * P.n_nt;
+    const uint32_t pairs = std::max(1u, std::min<uint32_t>((uint32_t)sm_count() / 2, P.n_units));
+    P.units_per_pair = ceil_div<uint32_t>(P.n_units, pairs);
+    const uint32_t grid = 2 * ceil_div<uint32_t>(P.n_units, P.units_per_pair);
+    P.epi = gemm_mode ? tc::EPI_RAW : tc::EPI_ACT;
+    P.bias = bias; P.noise = noise; P.noise_w = noise_w; P.out = out; P.ld_out = P.ncols;
+    SDFG_REQUIRE(gemm_mode || P.ncols <= 2304, SDFG_ERR_UNSUPPORTED, "conv_forward: too many output channels");      // bias table in shared memory
+    CUtensorMap tmA, tmB;
+    if (int e = make_tensor_map_16_4d(&tmA, x, B, H, W, Cin, P.bw, P.bh)) return e;
+    if (int e = make_tensor_map_16(&tmB, wf, (uint64_t)B * taps * Cout, Cin, Cin, P.NT / 2, 64, tc::FMT_F16)) return e;
+    const uint32_t smem = tc::conv_smem_bytes(P.NT);
+    if (int e = optin_smem_conv((const void*)tc::tc_conv_kernel, smem)) return e;
+    ProfScope prof("tc_conv_kernel<gemm>", (cudaStream_t)stream);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::CV_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, tc::tc_conv_kernel, tmA, tmB, P) != cudaSuccess) { (void)check_launch("tc_conv_kernel<gemm>"); return SDFG_ERR_CUDA; }
+    return check_launch("tc_conv_kernel<gemm>");
+}
+
+extern "C" int sdfg_upconv_gather(const uint16_t* y, uint32_t B, uint32_t H, uint32_t W, uint32_t C, const float* bias, const float* noise,
+                                  const float* noise_w, uint16_t* out, void* stream) {
+    if (B == 0) return SDFG_OK;
+    SDFG_REQUIRE(y && out && C % 64 == 0, SDFG_ERR_INVALID, "upconv_gather: null pointer or channels not a multiple of 64");
+    const uint32_t tiles = ceil_div<uint32_t>(2 * W, UG_T) * ceil_div<uint32_t>(2 * H, UG_T);
+    upconv_gather_kernel<<<dim3(B * tiles, C / 64), 256, 0, (cudaStream_t)stream>>>(y, B, H, W, C, bias, noise, noise_w, out);
+    return check_launch("upconv_gather_kernel");
+}
+
+extern "C" int sdfg_to_rgb(const uint16_t* x, const float* weight, const float* style, float scale, const float* bias, const float* skip,
+                           uint32_t B, uint32_t H, uint32_t W, uint32_t C, float* wrgb_scratch, float* out_nhwc, float* out_nchw, void* stream) {
+    if (B == 0) return SDFG_OK;
+    SDFG_REQUIRE(x && weight && style && bias && wrgb_scratch && (out_nhwc || out_nchw) && C % 8 == 0, SDFG_ERR_INVALID, "to_rgb: null pointer / bad channel count");
+    cudaStream_t st = (cudaStream_t)stream;
+    rgb_weight_kernel<<<ceil_div<uint32_t>(B * 3 * C, 256), 256, 0, st>>>(weight, style, scale, C, B, wrgb_scratch);
+    if (int e = check_launch("rgb_weight_kernel")) return e;
+    const uint64_t npix = (uint64_t)B * H * W;
+    to_rgb_kernel<<<(unsigned)ceil_div<uint64_t>(npix, 8), 256, 0, st>>>(x, wrgb_scratch, bias, skip, B, H, W, C, out_nhwc, out_nchw);
+    return check_launch("to_rgb_kernel");
+}

@@ -34,4 +34,22 @@ int make_tensor_map_16(CUtensorMap* out, const void* base, uint64_t rows, uint64
     return SDFG_OK;
 }
 
+// channels-last fp16 activation [B, H, W, C] as a 4-D tensor (C, W, H, B); box = 64 channels x box_w x box_h pixels of one sample,
+// 128B swizzle: a loaded box is a K-major [box_w * box_h pixels x 64 channels] operand tile; coordinates outside the image
+// (negative or past the edge) are zero-filled -- the zero padding of a convolution
+int make_tensor_map_16_4d(CUtensorMap* out, const void* base, uint32_t B, uint32_t H, uint32_t W, uint32_t C, uint32_t box_w, uint32_t box_h) {
+    PFN_cuTensorMapEncodeTiled_v12000 fn = encode_fn();
+    SDFG_REQUIRE(fn, SDFG_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    SDFG_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && C % 8 == 0, SDFG_ERR_INVALID, "tensor map (4d): base must be 16-byte aligned, channels a multiple of 8");
+    SDFG_REQUIRE(box_w <= 256 && box_h <= 256 && C >= 64, SDFG_ERR_INVALID, "tensor map (4d): box too large or fewer than 64 channels");
+    cuuint64_t dims[4] = {C, W, H, B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64, box_w, box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SDFG_REQUIRE(r == CUDA_SUCCESS, SDFG_ERR_CUDA, "cuTensorMapEncodeTiled (4d) failed (%d) B=%u H=%u W=%u C=%u box %ux%u", (int)r, B, H, W, C, box_w, box_h);
+    return SDFG_OK;
+}
+
 }  // namespace sdfg

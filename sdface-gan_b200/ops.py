@@ -381,3 +381,74 @@ def align_volume(volume, near=0.88, far=1.12):
 def log2_scale(per_level_scale):
     """S = log2(per_level_scale), rounded to float32 as the reference's pybind call does (gridencoder/grid.py:38)."""
     return float(np.float32(np.log2(per_level_scale)))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# StyleGAN2 decoder (forward): channels-last fp16 activations
+
+def nhwc16(x):
+    """fp32 [..., C] (channels last, contiguous) -> fp16, same shape (sdfg_nhwc16)."""
+    lib = _lib.load()
+    _chk(x, "x")
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sdfg_nhwc16(_ptr(x), _ptr(out), x.numel(), _stream()), "sdfg_nhwc16")
+    return out
+
+
+def modconv_fold(weight, style, scale, demodulate=True):
+    """weight [1, Cout, Cin, k, k] (reference ModulatedConv2d parameter), style [B, Cin] -> per-sample fp16 weights [B, k*k, Cout, Cin]."""
+    lib = _lib.load()
+    _, Cout, Cin, k, _ = weight.shape
+    w = _chk(weight.reshape(Cout, Cin, k * k).contiguous(), "weight")
+    style = _chk(style.contiguous().float(), "style")
+    B = style.shape[0]
+    out = torch.empty(B, k * k, Cout, Cin, device=w.device, dtype=torch.float16)
+    demod = torch.empty(B, Cout, device=w.device) if demodulate else None
+    with torch.cuda.device(w.device):
+        _lib.check(lib.sdfg_modconv_fold(_ptr(w), _ptr(style), float(scale), B, Cin, Cout, k * k, int(bool(demodulate)), _ptr(demod), _ptr(out),
+                                         _stream()), "sdfg_modconv_fold")
+    return out
+
+
+def conv_forward(x, wf, bias=None, noise=None, noise_w=None, gemm_mode=False):
+    """x [B,H,W,Cin] fp16; wf [B,taps,Cout,Cin] fp16 -> fp16 [B,H,W,Cout] (3x3 / 1x1 convolution + noise + bias + leaky ReLU * sqrt 2), or
+    with gemm_mode the raw tap products [B,H,W,taps*Cout] of a transposed convolution (see upconv_gather)."""
+    lib = _lib.load()
+    _chk(x, "x", torch.float16); _chk(wf, "wf", torch.float16)
+    B, H, W, Cin = x.shape
+    _, taps, Cout, _ = wf.shape
+    out = torch.empty(B, H, W, taps * Cout if gemm_mode else Cout, device=x.device, dtype=torch.float16)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sdfg_conv_forward(_ptr(x), _ptr(wf), B, H, W, Cin, Cout, taps, int(bool(gemm_mode)), _ptr(_chk(bias, "bias")),
+                                         _ptr(_chk(noise, "noise")), _ptr(_chk(noise_w, "noise_w")), _ptr(out), _stream()), "sdfg_conv_forward")
+    return out
+
+
+def upconv_gather(y, C, bias=None, noise=None, noise_w=None):
+    """y [B,H,W,9*C] fp16 (conv_forward(..., gemm_mode=True)) -> fp16 [B,2H,2W,C]: transposed-convolution tap sum + blur + noise + bias + act."""
+    lib = _lib.load()
+    _chk(y, "y", torch.float16)
+    B, H, W, _ = y.shape
+    out = torch.empty(B, 2 * H, 2 * W, C, device=y.device, dtype=torch.float16)
+    with torch.cuda.device(y.device):
+        _lib.check(lib.sdfg_upconv_gather(_ptr(y), B, H, W, C, _ptr(_chk(bias, "bias")), _ptr(_chk(noise, "noise")), _ptr(_chk(noise_w, "noise_w")),
+                                          _ptr(out), _stream()), "sdfg_upconv_gather")
+    return out
+
+
+def to_rgb(x, weight, style, scale, bias, skip=None, want_nhwc=True, want_nchw=False):
+    """x [B,H,W,C] fp16; weight [1,3,C,1,1]; style [B,C]; bias [1,3,1,1]; skip [B,H/2,W/2,3] fp32|None -> (nhwc [B,H,W,3]|None, nchw [B,3,H,W]|None) fp32."""
+    lib = _lib.load()
+    _chk(x, "x", torch.float16)
+    B, H, W, C = x.shape
+    w = _chk(weight.reshape(3, C).contiguous(), "weight")
+    style = _chk(style.contiguous().float(), "style")
+    b = _chk(bias.reshape(3).contiguous(), "bias")
+    scratch = torch.empty(B, 3, C, device=x.device)
+    o1 = torch.empty(B, H, W, 3, device=x.device) if want_nhwc else None
+    o2 = torch.empty(B, 3, H, W, device=x.device) if want_nchw else None
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sdfg_to_rgb(_ptr(x), _ptr(w), _ptr(style), float(scale), _ptr(b), _ptr(_chk(skip, "skip")), B, H, W, C, _ptr(scratch),
+                                   _ptr(o1), _ptr(o2), _stream()), "sdfg_to_rgb")
+    return o1, o2

@@ -242,10 +242,21 @@ class _FieldNetwork(nn.Module):
         return _lib.PRECISION_FP32
 
     def _modulation(self, styles):
+        """gamma = 15 Lin(w) + 30, beta = 0.25 Lin(w) of every FiLM layer (ref :58-59) as ONE [B, style] x [style, 2 (n+1) W] product
+        instead of 2 (n+1) skinny GEMMs with their scale / shift launches (forward and backward: ~100 launches of a training step)."""
         layers = list(self.pts_linears) + [self.views_linears]
-        gamma = torch.stack([l.gamma(styles) for l in layers], 1)       # [B, n+1, W]
-        beta = torch.stack([l.beta(styles) for l in layers], 1)
-        return gamma, beta
+        n, W = len(layers), layers[0].out_channel
+        heads = [l.gamma for l in layers] + [l.beta for l in layers]
+        weight = torch.cat([h.weight for h in heads], 0)
+        bias = torch.cat([h.bias for h in heads], 0)
+        key = (styles.device, styles.dtype)
+        consts = self.__dict__.setdefault("_mod_consts", {})
+        if key not in consts:                                             # per-column scale / shift, built once per device (no per-call H2D copy)
+            consts[key] = (styles.new_tensor([h.std_init for h in heads]).repeat_interleave(W),
+                           styles.new_tensor([h.bias_init for h in heads]).repeat_interleave(W))
+        mul, add = consts[key]
+        out = torch.addcmul(add, F.linear(styles, weight, bias), mul).view(styles.shape[0], 2, n, W)
+        return out[:, 0], out[:, 1]                                      # gamma, beta: [B, n+1, W] (made contiguous by the field node)
 
     def _run_field(self, x_in, view_feat, styles, samples_per_image, samples_per_ray, want_rgb=True, want_feat=True, want_dsdf=False,
                    feat_f16=False, emb=None, grid=None):
@@ -661,7 +672,9 @@ class VolumeFeatureRenderer(nn.Module):
         if rgb is not None:
             rgb = rgb.permute(0, 3, 1, 2).contiguous()
         if features is not None:
-            features = features.permute(0, 3, 1, 2).contiguous()
+            # logically [B, W, R, R] like the reference (:415-421); the memory stays channels-last (what the compositing kernel wrote and
+            # what the decoder kernels read): no transposing copy in either direction
+            features = features.permute(0, 3, 1, 2)
         if xyz is not None:
             xyz = xyz.permute(0, 3, 1, 2).contiguous()
             mask = mask.permute(0, 3, 1, 2).contiguous()
@@ -692,8 +705,9 @@ _DECODER_FACTORY = None
 
 
 def register_decoder(factory):
-    """Plug the (out-of-scope) StyleGAN2 decoder class of the host project: factory(model_opt) -> nn.Module with the
-    reference Decoder's forward/mean_latent signature (ref :883-1056)."""
+    """Use another decoder class than this package's (decoder.Decoder, forward-only kernels) -- e.g. the host project's own
+    torch StyleGAN2 Decoder for stage-2 training: factory(model_opt) -> nn.Module with the reference Decoder's
+    forward / mean_latent signature (ref :883-1056).  None restores the default."""
     global _DECODER_FACTORY
     _DECODER_FACTORY = factory
 
@@ -713,10 +727,11 @@ class Generator(nn.Module):
         self.style = nn.Sequential(*[MappingLinear(self.style_dim, self.style_dim, activation="fused_lrelu") for _ in range(3)])
         self.renderer = VolumeFeatureRenderer(renderer_opt, style_dim=self.style_dim, out_im_res=model_opt.renderer_spatial_output_dim)
         if self.full_pipeline:
-            if _DECODER_FACTORY is None:
-                raise NotImplementedError("full_pipeline=True needs the host project's StyleGAN2 Decoder: call "
-                                          "sdf_model.register_decoder(Decoder) first (see INTEGRATION.md)")
-            self.decoder = _DECODER_FACTORY(model_opt)
+            if _DECODER_FACTORY is not None:
+                self.decoder = _DECODER_FACTORY(model_opt)
+            else:
+                from .decoder import Decoder
+                self.decoder = Decoder(model_opt)
 
     def mean_latent(self, n_latent, device, z=None):
         if z is None:

@@ -186,6 +186,44 @@ def align_volume_golden():
     print("align_volume", out.shape)
 
 
+def decoder_table(dec):
+    """(name, shape, std, mean) like pf.param_table, with the zero-initialised tensors (noise weights, activation / rgb biases)
+    made non-zero so that every term of the decoder is exercised."""
+    tab = []
+    for name, shape, std, mean in pf.param_table(dec):
+        if name.endswith("noise.weight"):
+            mean = 0.3
+        elif std == 0.0 and int(np.prod(shape)) > 1:
+            std = 0.1
+        tab.append((name, shape, std, mean))
+    return tab
+
+
+def decoder_golden():
+    """The reference's own Decoder (sdf_model.py:883-1056; CPU branches of sdf_op.py) at 8^2 -> 32^2: 5 styled convolutions (2 of them
+    up-sampling), 3 ToRGB with skip up-sampling, fixed noise buffers."""
+    sm = rh.install()
+    torch.manual_seed(SEED)
+    mo, _ = rh.default_opts("ngp", res=8, size=32)
+    mo["feature_encoder_in_channels"] = 256
+    dec = sm.Decoder(mo)
+    tab = decoder_table(dec)
+    pf.fill_state(dec, tab, SEED)
+    g = torch.Generator().manual_seed(11)
+    feats = torch.randn(2, 256, 8, 8, generator=g)
+    z = torch.randn(2, 256, generator=g)
+    noise = [torch.randn(1, 1, 2 ** ((i + 2 * 3 + 1) // 2), 2 ** ((i + 2 * 3 + 1) // 2), generator=g) for i in range(dec.num_layers)]
+    with torch.no_grad():
+        img, latent = dec(feats, [z], noise=noise, return_latents=True)
+        img_b, _ = dec(feats, [z], randomize_noise=False)               # the registered noise buffers, broadcast over the batch
+    out = dict(pf.table_to_npz(tab))
+    out.update(features=feats.numpy(), z=z.numpy(), image=img.numpy(), latent=latent.numpy(), image_buffers=img_b.numpy(),
+               **{f"noise_{i}": n.numpy() for i, n in enumerate(noise)},
+               **{f"buf_noise_{i}": getattr(dec.noises, f"noise_{i}").numpy() for i in range(dec.num_layers)})
+    np.savez_compressed(os.path.join(HERE, "decoder.npz"), **out)
+    print("decoder", img.shape, float(img.abs().mean()))
+
+
 def main():
     global run_case
     only = sys.argv[1:]
@@ -194,7 +232,9 @@ def main():
         run_case = lambda name, *a, **k: _rc(name, *a, **k) if name in only else None
     if not only or "align_volume" in only:
         align_volume_golden()
-    if only == ["align_volume"]:
+    if not only or "decoder" in only:
+        decoder_golden()
+    if only and all(o in ("align_volume", "decoder") for o in only):
         return
     sh_from_reference_source()
     camera_goldens()

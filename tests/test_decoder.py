@@ -1,0 +1,108 @@
+"""the StyleGAN2 decoder forward.
+
+CPU: the oracle (oracle/decoder_oracle.py) against the golden produced by the reference's own Decoder (tests/golden/make_golden.py).
+GPU: the sm_100a decoder (decoder.py on csrc/tc_conv.cuh + conv.cu) against that golden and, at the BASELINE size (64^2 features ->
+256^2 image), against the oracle.  Tolerance: fp16 operands / activations with fp32 accumulation through 5 convolutions --
+max-abs 2e-2 of the image's value range (the image is O(1): mean |value| 0.86 in the golden)."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+import param_fill as pf
+from oracle import decoder_oracle as do
+
+
+def _golden():
+    z = H.load_fixture("decoder")
+    tab = pf.table_from_npz(z)
+    params = {name: torch.from_numpy(pf.values_for(name, shape, std, 0, mean)) for name, shape, std, mean in tab}
+    noise = [torch.from_numpy(z[f"noise_{i}"]) for i in range(5)]
+    return z, tab, params, noise
+
+
+def test_decoder_oracle_matches_reference_golden():
+    z, tab, params, noise = _golden()
+    with torch.no_grad():
+        img = do.decoder_forward(params, torch.from_numpy(z["features"]), torch.from_numpy(z["z"]), noise)
+        assert H.max_abs(do.mapping(params, torch.from_numpy(z["z"])), z["latent"][:, 0]) < 1e-5
+        assert H.max_abs(img, z["image"]) < 2e-4 * float(np.abs(z["image"]).max())
+        bufs = [torch.from_numpy(z[f"buf_noise_{i}"]) for i in range(5)]
+        img_b = do.decoder_forward(params, torch.from_numpy(z["features"]), torch.from_numpy(z["z"]), bufs)
+        assert H.max_abs(img_b, z["image_buffers"]) < 2e-4 * float(np.abs(z["image_buffers"]).max())
+
+
+def _product_decoder(size, res, tab=None, seed=0):
+    import sdface_gan_b200 as sg
+    mo, _ = sg.default_options("ngp", size=size, renderer_res=res)
+    mo.feature_encoder_in_channels = 256
+    dec = sg.Decoder(mo)
+    if tab is not None:
+        pf.fill_state(dec, tab, seed)
+    return dec.cuda().eval()
+
+
+@pytest.mark.gpu
+def test_decoder_matches_reference_golden():
+    z, tab, params, noise = _golden()
+    dec = _product_decoder(32, 8, tab)
+    assert set(k for k in dec.state_dict()) >= set(params)                      # the reference's parameter names, all of them
+    with torch.no_grad():
+        img, latent = dec(torch.from_numpy(z["features"]).cuda(), [torch.from_numpy(z["z"]).cuda()], noise=[n.cuda() for n in noise],
+                          return_latents=True)
+        assert H.max_abs(latent, z["latent"]) < 1e-4
+        scale = float(np.abs(z["image"]).max())
+        assert img.shape == (2, 3, 32, 32) and H.max_abs(img, z["image"]) < 2e-2 * scale
+        assert H.rel_err(img, z["image"]) < 1e-2
+        # registered noise buffers, broadcast over the batch (randomize_noise = False)
+        for i in range(5):
+            getattr(dec.noises, f"noise_{i}").copy_(torch.from_numpy(z[f"buf_noise_{i}"]))
+        img_b, none = dec(torch.from_numpy(z["features"]).cuda(), [torch.from_numpy(z["z"]).cuda()], randomize_noise=False)
+        assert none is None and H.rel_err(img_b, z["image_buffers"]) < 1e-2
+    with pytest.raises(NotImplementedError):                                     # forward-only kernels: loud, not silent
+        dec(torch.from_numpy(z["features"]).cuda().requires_grad_(True), [torch.from_numpy(z["z"]).cuda()])
+
+
+@pytest.mark.gpu
+def test_decoder_full_size_matches_oracle():
+    """BASELINE configs[2] decoder shape: [B, 256, 64, 64] features -> [B, 3, 256, 256], seeded weights with live noise / biases."""
+    import sdface_gan_b200 as sg
+    torch.manual_seed(1)
+    dec = _product_decoder(256, 64)
+    with torch.no_grad():
+        for n, p in dec.named_parameters():
+            if n.endswith("noise.weight"):
+                p.fill_(0.2)
+            elif p.abs().max() == 0:
+                p.normal_(0, 0.1)
+    Bn = 2
+    feats = torch.randn(Bn, 256, 64, 64)
+    zl = torch.randn(Bn, 256)
+    noise = [torch.randn(Bn, 1, r, r) for r in (64, 128, 128, 256, 256)]
+    params = {k: v.detach().cpu() for k, v in dec.state_dict().items()}
+    with torch.no_grad():
+        ref = do.decoder_forward(params, feats, zl, noise)
+        img, _ = dec(feats.cuda(), [zl.cuda()], noise=[n.cuda() for n in noise])
+    assert img.shape == (Bn, 3, 256, 256)
+    assert H.rel_err(img, ref) < 1e-2 and H.max_abs(img, ref) < 2e-2 * float(ref.abs().max())
+
+
+@pytest.mark.gpu
+def test_generator_full_pipeline_runs_and_matches_parts():
+    """Generator(full_pipeline=True): renderer -> (channels-last view) -> decoder; the image equals the decoder applied to the renderer's
+    features, and the thumbnail equals the renderer-only generator's."""
+    import sdface_gan_b200 as sg
+    torch.manual_seed(2)
+    mo, ro = sg.default_options("ngp", size=32, renderer_res=8, n_samples=16, perturb=0.)
+    g = sg.Generator(mo, ro, full_pipeline=True, ema=True).cuda().eval()
+    g.renderer.network.encoder.embeddings.data.uniform_(-0.5, 0.5)
+    cam, focal, near, far, _ = sg.generate_camera_params(8, "cuda", batch=2)
+    zl = torch.randn(2, 256, device="cuda")
+    with torch.no_grad():
+        img, thumb = g([zl], cam, focal, near, far, randomize_noise=False)
+        style = g.style(zl)
+        t2, feats, _, _, _, _ = g.renderer(cam, focal, near, far, styles=style)
+        img2, _ = g.decoder(feats, [style], randomize_noise=False)
+    assert img.shape == (2, 3, 32, 32) and thumb.shape == (2, 3, 8, 8)
+    assert feats.shape == (2, 256, 8, 8) and feats.permute(0, 2, 3, 1).is_contiguous()       # logically NCHW, channels-last memory
+    assert torch.equal(thumb, t2) and torch.equal(img, img2) and torch.isfinite(img).all()
