@@ -1,7 +1,7 @@
 /*
  * oracle/hashgrid_oracle.c  --  TEST INFRASTRUCTURE ONLY (never linked into / imported by the product).
  *
- * Plain-C, single-threaded-per-call (optionally OpenMP) CPU restatement of the reference's multi-resolution
+ * Plain-C CPU restatement (pthreads over independent samples / levels: this image's gcc has no libgomp) of the reference's multi-resolution
  * hash-grid encoder, which the reference only ships as CUDA (no CPU path exists in
  * im2scene/sdf/models/gridencoder/grid.py).  Every function cites the reference file:line it follows;
  * paths are relative to /root/reference/im2scene/sdf/models/gridencoder/.
@@ -23,8 +23,38 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <pthread.h>
+#include <unistd.h>
+
 #define ORACLE_MAX_D 3
 #define ORACLE_MAX_C 8
+
+/* Minimal parallel-for: [0, n) in contiguous chunks over min(threads, n / grain) pthreads.  ORACLE_THREADS overrides the count
+ * (default: online cores, at most 64).  The work functions write disjoint outputs, so results do not depend on the thread count. */
+typedef void (*range_fn)(int64_t begin, int64_t end, void* ctx);
+typedef struct { range_fn fn; void* ctx; int64_t begin, end; } pf_task;
+static void* pf_run(void* p) { pf_task* t = (pf_task*)p; t->fn(t->begin, t->end, t->ctx); return NULL; }
+int oracle_num_threads(void) {
+    const char* e = getenv("ORACLE_THREADS");
+    long n = e ? atol(e) : sysconf(_SC_NPROCESSORS_ONLN);
+    return (int)(n < 1 ? 1 : (n > 64 ? 64 : n));
+}
+static void parallel_for(int64_t n, int64_t grain, range_fn fn, void* ctx) {
+    int64_t T = oracle_num_threads();
+    if (grain < 1) grain = 1;
+    if (T > (n + grain - 1) / grain) T = (n + grain - 1) / grain;
+    if (T <= 1) { fn(0, n, ctx); return; }
+    pthread_t th[64]; pf_task task[64];
+    const int64_t per = (n + T - 1) / T;
+    int64_t started = 0;
+    for (int64_t t = 0; t < T; t++) {
+        task[t].fn = fn; task[t].ctx = ctx; task[t].begin = t * per; task[t].end = (t + 1) * per < n ? (t + 1) * per : n;
+        if (task[t].begin >= task[t].end) break;
+        if (pthread_create(&th[t], NULL, pf_run, &task[t]) != 0) { fn(task[t].begin, n, ctx); break; }   /* fall back to this thread */
+        started++;
+    }
+    for (int64_t t = 0; t < started; t++) pthread_join(th[t], NULL);
+}
 
 /* src/gridencoder.cu:50-63 : coherent prime hash, uint32 wraparound */
 static uint32_t fast_hash(uint32_t D, const uint32_t* pos_grid) {
@@ -86,12 +116,13 @@ static int locate(uint32_t D, const float* x, float scale, int align_corners, ui
  *   corner_idx  optional [B, L, 2^D] uint32 : table ROW index (without the *C) of each corner, 0xFFFFFFFF if OOB
  *   corner_w    optional [B, L, 2^D] float  : D-linear weight of each corner
  */
-void oracle_grid_encode_forward(const float* inputs, const float* embeddings, const int* offsets, float* outputs,
-                                uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
-                                float* dy_dx, uint32_t gridtype, int align_corners, uint32_t interp,
-                                const float* level_scales, uint32_t* corner_idx, float* corner_w) {
+static void grid_encode_forward_range(int64_t b_begin, int64_t b_end, const float* inputs, const float* embeddings, const int* offsets,
+                                      float* outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                                      float* dy_dx, uint32_t gridtype, int align_corners, uint32_t interp,
+                                      const float* level_scales, uint32_t* corner_idx, float* corner_w) {
     const uint32_t NC = 1u << D;
-    for (int64_t bb = 0; bb < (int64_t)B; bb++) {
+    /* samples are independent: split over the host threads by the caller (fwd_range / parallel_for); results do not depend on the count */
+    for (int64_t bb = b_begin; bb < b_end; bb++) {
         const uint32_t b = (uint32_t)bb;
         const float* x = inputs + (size_t)b * D;
         for (uint32_t level = 0; level < L; level++) {
@@ -146,6 +177,23 @@ void oracle_grid_encode_forward(const float* inputs, const float* embeddings, co
     }
 }
 
+typedef struct {
+    const float* inputs; const float* embeddings; const int* offsets; float* outputs; uint32_t B, D, C, L; float S; uint32_t H;
+    float* dy_dx; uint32_t gridtype; int align_corners; uint32_t interp; const float* level_scales; uint32_t* corner_idx; float* corner_w;
+} fwd_args;
+static void fwd_range(int64_t a, int64_t b, void* p) {
+    fwd_args* q = (fwd_args*)p;
+    grid_encode_forward_range(a, b, q->inputs, q->embeddings, q->offsets, q->outputs, q->B, q->D, q->C, q->L, q->S, q->H, q->dy_dx, q->gridtype,
+                              q->align_corners, q->interp, q->level_scales, q->corner_idx, q->corner_w);
+}
+void oracle_grid_encode_forward(const float* inputs, const float* embeddings, const int* offsets, float* outputs,
+                                uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                                float* dy_dx, uint32_t gridtype, int align_corners, uint32_t interp,
+                                const float* level_scales, uint32_t* corner_idx, float* corner_w) {
+    fwd_args a = {inputs, embeddings, offsets, outputs, B, D, C, L, S, H, dy_dx, gridtype, align_corners, interp, level_scales, corner_idx, corner_w};
+    parallel_for((int64_t)B, 4096, fwd_range, &a);
+}
+
 /*
  * Backward: src/gridencoder.cu:248-340 (kernel_grid_backward) + :343-369 (kernel_input_backward).
  *   grad            [L, B, C]
@@ -154,47 +202,64 @@ void oracle_grid_encode_forward(const float* inputs, const float* embeddings, co
  * The GPU reference uses float atomics whose order is non-deterministic; this restatement accumulates in double and
  * rounds once, i.e. it is the exact sum the atomics approximate (tolerance-compared, never bit-compared).
  */
-void oracle_grid_encode_backward(const float* grad, const float* inputs, const float* embeddings, const int* offsets,
-                                 float* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
-                                 const float* dy_dx, float* grad_inputs, uint32_t gridtype, int align_corners, uint32_t interp,
-                                 const float* level_scales) {
-    (void)embeddings;
-    const uint32_t NC = 1u << D;
-    const size_t total = (size_t)(uint32_t)offsets[L] * C;
-    double* acc = (double*)calloc(total, sizeof(double));
-    for (uint32_t level = 0; level < L; level++) {
-        double* gg = acc + (size_t)(uint32_t)offsets[level] * C;
-        const uint32_t hashmap_size = (uint32_t)(offsets[level + 1] - offsets[level]);
+typedef struct {
+    const float* grad; const float* inputs; const int* offsets; double* acc; uint32_t B, D, C, L; float S; uint32_t H;
+    uint32_t gridtype; int align_corners; uint32_t interp; const float* level_scales; const float* dy_dx; float* grad_inputs;
+} bwd_args;
+
+/* one table level = one disjoint region of the accumulator: the serial accumulation order inside a level is kept */
+static void bwd_levels(int64_t l_begin, int64_t l_end, void* p) {
+    const bwd_args* q = (const bwd_args*)p;
+    const uint32_t B = q->B, D = q->D, C = q->C, NC = 1u << q->D;
+    for (int64_t lv = l_begin; lv < l_end; lv++) {
+        const uint32_t level = (uint32_t)lv;
+        double* gg = q->acc + (size_t)(uint32_t)q->offsets[level] * C;
+        const uint32_t hashmap_size = (uint32_t)(q->offsets[level + 1] - q->offsets[level]);
         float scale; uint32_t resolution;
-        level_geometry(level, S, H, level_scales, &scale, &resolution);
+        level_geometry(level, q->S, q->H, q->level_scales, &scale, &resolution);
         for (uint32_t b = 0; b < B; b++) {
-            const float* x = inputs + (size_t)b * D;
-            const float* g = grad + ((size_t)level * B + b) * C;
+            const float* x = q->inputs + (size_t)b * D;
+            const float* g = q->grad + ((size_t)level * B + b) * C;
             float pos[ORACLE_MAX_D], pos_deriv[ORACLE_MAX_D]; uint32_t pos_grid[ORACLE_MAX_D];
-            if (locate(D, x, scale, align_corners, interp, pos, pos_deriv, pos_grid)) continue;   /* :276-281 */
+            if (locate(D, x, scale, q->align_corners, q->interp, pos, pos_deriv, pos_grid)) continue;   /* :276-281 */
             for (uint32_t idx = 0; idx < NC; idx++) {                                             /* :305-339 */
                 float w = 1; uint32_t pgl[ORACLE_MAX_D];
                 for (uint32_t d = 0; d < D; d++) {
                     if ((idx & (1u << d)) == 0) { w *= 1 - pos[d]; pgl[d] = pos_grid[d]; }
                     else { w *= pos[d]; pgl[d] = pos_grid[d] + 1; }
                 }
-                uint32_t index = grid_index(D, C, gridtype, align_corners, 0, hashmap_size, resolution, pgl);
+                uint32_t index = grid_index(D, C, q->gridtype, q->align_corners, 0, hashmap_size, resolution, pgl);
                 for (uint32_t ch = 0; ch < C; ch++) gg[index + ch] += (double)(w * g[ch]);
             }
         }
     }
+}
+
+static void bwd_inputs(int64_t b_begin, int64_t b_end, void* p) {                               /* :343-369 */
+    const bwd_args* q = (const bwd_args*)p;
+    const uint32_t B = q->B, D = q->D, C = q->C, L = q->L;
+    for (int64_t b = b_begin; b < b_end; b++)
+        for (uint32_t d = 0; d < D; d++) {
+            float r = 0;
+            for (uint32_t l = 0; l < L; l++)
+                for (uint32_t ch = 0; ch < C; ch++)
+                    r = fmaf(q->grad[((size_t)l * B + (size_t)b) * C + ch], q->dy_dx[(((size_t)b * L + l) * D + d) * C + ch], r);
+            q->grad_inputs[(size_t)b * D + d] = r;
+        }
+}
+
+void oracle_grid_encode_backward(const float* grad, const float* inputs, const float* embeddings, const int* offsets,
+                                 float* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                                 const float* dy_dx, float* grad_inputs, uint32_t gridtype, int align_corners, uint32_t interp,
+                                 const float* level_scales) {
+    (void)embeddings;
+    const size_t total = (size_t)(uint32_t)offsets[L] * C;
+    double* acc = (double*)calloc(total, sizeof(double));
+    bwd_args a = {grad, inputs, offsets, acc, B, D, C, L, S, H, gridtype, align_corners, interp, level_scales, dy_dx, grad_inputs};
+    parallel_for((int64_t)L, 1, bwd_levels, &a);
     for (size_t i = 0; i < total; i++) grad_embeddings[i] += (float)acc[i];
     free(acc);
-    if (dy_dx && grad_inputs) {                                                                   /* :343-369 */
-        for (uint32_t b = 0; b < B; b++)
-            for (uint32_t d = 0; d < D; d++) {
-                float r = 0;
-                for (uint32_t l = 0; l < L; l++)
-                    for (uint32_t ch = 0; ch < C; ch++)
-                        r = fmaf(grad[((size_t)l * B + b) * C + ch], dy_dx[(((size_t)b * L + l) * D + d) * C + ch], r);
-                grad_inputs[(size_t)b * D + d] = r;
-            }
-    }
+    if (dy_dx && grad_inputs) parallel_for((int64_t)B, 4096, bwd_inputs, &a);
 }
 
 /*

@@ -74,111 +74,153 @@ __global__ void __launch_bounds__(256) modconv_fold_kernel(const float* __restri
 // Up-sampling StyledConv, second half.  Y[b, (y, x), tap * C + o] holds the nine tap products of the transposed convolution
 // (conv_transpose2d, stride 2: T[2y + a, 2x + b'] += Y[(y, x), (a, b')], T is (2H + 1)^2).  out = lrelu(blur(T) + noise + bias) * sqrt(2)
 // with blur = upfirdn2d(T, outer([1,3,3,1]) / 16, pad (1, 1)):  out[Y, X] = sum_{p, q < 4} k[p] k[q] T[Y + p - 1, X + q - 1].
-// Block: 8 x 8 output pixels x 64 channels; the 11 x 11 patch of T is assembled in shared memory (<= 4 reads of Y per element).
-constexpr int UG_T = 8;
+// Block: 16 x 16 output pixels x 64 channels.  The 19 x 19 patch of T is assembled in shared memory as fp16 (<= 4 reads of Y per
+// element, 16-byte loads: a thread owns 8 channels), then every thread blurs its pixels from shared memory and writes 16 bytes.
+// HBM: Y is read ~1.4x (patch halo), the output written once.
+constexpr int UG_T = 16, UG_P = UG_T + 3;
 __global__ void __launch_bounds__(256) upconv_gather_kernel(const uint16_t* __restrict__ Y, uint32_t B, uint32_t H, uint32_t W, uint32_t C,
                                                              const float* __restrict__ bias, const float* __restrict__ noise,
                                                              const float* __restrict__ noise_w, uint16_t* __restrict__ out) {
-    __shared__ float T[UG_T + 3][UG_T + 3][64];
-    const uint32_t ch = threadIdx.x & 63, sub = threadIdx.x >> 6;       // 4 pixel slots x 64 channels
+    __shared__ uint4 T[UG_P * UG_P][8];                                // [position][8 channel groups of 8 fp16]
+    const uint32_t cg = threadIdx.x & 7, slot = threadIdx.x >> 3;       // 8 threads per position / pixel, 32 positions per pass
     const uint32_t Ho = 2 * H, Wo = 2 * W;
-    const uint32_t c0 = blockIdx.y * 64;
+    const uint32_t c0 = blockIdx.y * 64 + cg * 8;
     const uint32_t tiles_x = (Wo + UG_T - 1) / UG_T, tiles_y = (Ho + UG_T - 1) / UG_T;
     const uint32_t b = blockIdx.x / (tiles_x * tiles_y), t = blockIdx.x % (tiles_x * tiles_y);
     const int Y0 = (int)(t / tiles_x) * UG_T, X0 = (int)(t % tiles_x) * UG_T;
     const size_t ldy = (size_t)9 * C;
-    const uint16_t* Yb = Y + (size_t)b * H * W * ldy + c0 + ch;
-    for (int e = sub; e < (UG_T + 3) * (UG_T + 3); e += 4) {
-        const int tr = e / (UG_T + 3), tcn = e % (UG_T + 3);
-        const int r = Y0 + tr - 1, c = X0 + tcn - 1;                    // position in T
-        float acc = 0.f;
+    const uint16_t* Yb = Y + (size_t)b * H * W * ldy + c0;
+    for (int e = slot; e < UG_P * UG_P; e += 32) {
+        const int r = Y0 + e / UG_P - 1, c = X0 + e % UG_P - 1;        // position in T
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (r >= 0 && c >= 0 && r <= (int)Ho && c <= (int)Wo) {
+            // a = r mod 2 (+ 2 when r is even): the taps whose stride-2 placement lands on this row / column
 #pragma unroll
-            for (int a = 0; a < 3; a++) {
-                if (((r - a) & 1) || r - a < 0) continue;
+            for (int ai = 0; ai < 2; ai++) {
+                const int a = (r & 1) ? 1 : 2 * ai;
+                if ((r & 1) && ai) break;
                 const int y = (r - a) >> 1;
-                if (y >= (int)H) continue;
+                if (r - a < 0 || y >= (int)H) continue;
 #pragma unroll
-                for (int bb = 0; bb < 3; bb++) {
-                    if (((c - bb) & 1) || c - bb < 0) continue;
+                for (int bi = 0; bi < 2; bi++) {
+                    const int bb = (c & 1) ? 1 : 2 * bi;
+                    if ((c & 1) && bi) break;
                     const int x = (c - bb) >> 1;
-                    if (x >= (int)W) continue;
-                    acc += __half2float(__ushort_as_half(__ldg(Yb + ((size_t)y * W + x) * ldy + (size_t)(a * 3 + bb) * C)));
+                    if (c - bb < 0 || x >= (int)W) continue;
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(Yb + ((size_t)y * W + x) * ldy + (size_t)(a * 3 + bb) * C));
+                    const uint32_t hw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float2 f = tc::unpack_f16(hw[k]);
+                        acc[2 * k] += f.x; acc[2 * k + 1] += f.y;
+                    }
                 }
             }
         }
-        T[tr][tcn][ch] = acc;
+        T[e][cg] = make_uint4(tc::pack_f16_sat(acc[0], acc[1]), tc::pack_f16_sat(acc[2], acc[3]), tc::pack_f16_sat(acc[4], acc[5]), tc::pack_f16_sat(acc[6], acc[7]));
     }
     __syncthreads();
     const float nw = (noise && noise_w) ? __ldg(noise_w) : 0.f;
-    const float bs = bias ? __ldg(bias + c0 + ch) : 0.f;
+    float bs[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) bs[k] = bias ? __ldg(bias + c0 + k) : 0.f;
     const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};                  // [1,3,3,1] / 4 per axis: make_kernel (outer / 64) * upsample_factor^2 (Blur :522-531)
-    for (int e = sub; e < UG_T * UG_T; e += 4) {
+    for (int e = slot; e < UG_T * UG_T; e += 32) {
         const int oy = e / UG_T, ox = e % UG_T;
         const int Yo = Y0 + oy, Xo = X0 + ox;
         if (Yo >= (int)Ho || Xo >= (int)Wo) continue;
-        float acc = 0.f;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int p = 0; p < 4; p++) {
-            float rowacc = 0.f;
 #pragma unroll
-            for (int q = 0; q < 4; q++) rowacc = fmaf(k4[q], T[oy + p][ox + q][ch], rowacc);
-            acc = fmaf(k4[p], rowacc, acc);
+            for (int q = 0; q < 4; q++) {
+                const uint4 v = T[(oy + p) * UG_P + ox + q][cg];
+                const uint32_t hw[4] = {v.x, v.y, v.z, v.w};
+                const float kk = k4[p] * k4[q];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float2 f = tc::unpack_f16(hw[k]);
+                    acc[2 * k] = fmaf(kk, f.x, acc[2 * k]); acc[2 * k + 1] = fmaf(kk, f.y, acc[2 * k + 1]);
+                }
+            }
         }
         const size_t pix = ((size_t)b * Ho + Yo) * Wo + Xo;
-        float v = acc + bs + (nw != 0.f ? nw * __ldg(noise + pix) : 0.f);
-        v = (v > 0.f ? v : 0.2f * v) * 1.4142135623730951f;
-        out[pix * C + c0 + ch] = __half_as_ushort(__float2half_rn(v));
+        const float nz = nw != 0.f ? nw * __ldg(noise + pix) : 0.f;
+        uint32_t h[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float v0 = acc[2 * k] + bs[2 * k] + nz, v1 = acc[2 * k + 1] + bs[2 * k + 1] + nz;
+            v0 = (v0 > 0.f ? v0 : 0.2f * v0) * 1.4142135623730951f;
+            v1 = (v1 > 0.f ? v1 : 0.2f * v1) * 1.4142135623730951f;
+            h[k] = tc::pack_f16_sat(v0, v1);
+        }
+        *reinterpret_cast<uint4*>(out + pix * C + c0) = make_uint4(h[0], h[1], h[2], h[3]);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // ToRGB: rgb[b, y, x, c] = sum_i x[b, y, x, i] * wrgb[b, c, i] + bias[c] (+ upsample(skip)[y, x, c]); wrgb = scale * W * style (no
 // demodulation).  skip [B, H/2, W/2, 3] fp32 is up-sampled by upfirdn2d(up = 2, kernel outer([1,3,3,1]) / 16, pad (2, 1)) on the fly:
-// out[Y, X] = sum_{p, q} k[p] k[q] U[Y + p - 2, X + q - 2], U[2y, 2x] = skip[y, x], zero elsewhere.   warp per pixel.
-// out_nchw (fp32 [B, 3, H, W], the image) and / or out_nhwc (fp32 [B, H, W, 3], the next level's skip)
+// out[Y, X] = sum_{p, q} k[p] k[q] U[Y + p - 2, X + q - 2], U[2y, 2x] = skip[y, x], zero elsewhere.
+// 8 threads per pixel (each a contiguous eighth of the channels, 16-byte loads), the sample's 3 x C weights in shared memory;
+// a block's 32 pixels belong to one sample.   out_nchw (fp32 [B, 3, H, W], the image) and / or out_nhwc (fp32 [B, H, W, 3], the next skip)
 __global__ void __launch_bounds__(256) to_rgb_kernel(const uint16_t* __restrict__ x, const float* __restrict__ wrgb, const float* __restrict__ bias,
                                                       const float* __restrict__ skip, uint32_t B, uint32_t H, uint32_t W, uint32_t C,
                                                       float* __restrict__ out_nhwc, float* __restrict__ out_nchw) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t pix = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (pix >= (uint64_t)B * H * W) return;
-    const uint32_t b = (uint32_t)(pix / ((uint64_t)H * W));
-    const uint32_t yx = (uint32_t)(pix % ((uint64_t)H * W)), Yo = yx / W, Xo = yx % W;
-    const uint16_t* xr = x + pix * C;
-    const float* w = wrgb + (size_t)b * 3 * C;
+    __shared__ float4 ws[512];                                          // the three weights of input channel i in one 16-byte word
+    const uint32_t blocks_per_sample = (H * W + 31) / 32;
+    const uint32_t b = blockIdx.x / blocks_per_sample;
+    const uint32_t yx = (blockIdx.x % blocks_per_sample) * 32 + (threadIdx.x >> 3);
+    const uint32_t part = threadIdx.x & 7;
+    for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) {
+        const float* wb = wrgb + (size_t)b * 3 * C + i;
+        ws[i] = make_float4(__ldg(wb), __ldg(wb + C), __ldg(wb + 2 * C), 0.f);
+    }
+    __syncthreads();
+    const bool valid = yx < H * W;
+    const uint64_t pix = (uint64_t)b * H * W + (valid ? yx : 0);
+    const uint32_t per = C / 8;                                         // channels per thread (a multiple of 8)
+    const uint16_t* xr = x + pix * C + part * per;
+    const float4* w = ws + part * per;
     float acc[3] = {0.f, 0.f, 0.f};
-    for (uint32_t i = lane * 8; i < C; i += 256) {
+    for (uint32_t i = 0; i < per; i += 8) {
         const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + i));
         const uint32_t hw[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const float2 f = tc::unpack_f16(hw[k]);
-#pragma unroll
-            for (int c = 0; c < 3; c++) acc[c] = fmaf(f.x, __ldg(w + c * C + i + 2 * k), fmaf(f.y, __ldg(w + c * C + i + 2 * k + 1), acc[c]));
+            const float4 w0 = w[i + 2 * k], w1 = w[i + 2 * k + 1];
+            acc[0] = fmaf(f.x, w0.x, fmaf(f.y, w1.x, acc[0]));
+            acc[1] = fmaf(f.x, w0.y, fmaf(f.y, w1.y, acc[1]));
+            acc[2] = fmaf(f.x, w0.z, fmaf(f.y, w1.z, acc[2]));
         }
     }
 #pragma unroll
-    for (int c = 0; c < 3; c++) acc[c] = warp_sum(acc[c]);
-    if (lane < 3) {
-        float v = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : acc[2]) + __ldg(bias + lane);
+    for (int c = 0; c < 3; c++) {
+        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 4);
+    }
+    if (valid && part < 3) {
+        const uint32_t Yo = yx / W, Xo = yx % W;
+        float v = (part == 0 ? acc[0] : part == 1 ? acc[1] : acc[2]) + __ldg(bias + part);
         if (skip) {
             const uint32_t Hs = H / 2, Ws = W / 2;
             const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};          // [1,3,3,1] / 8 * 2 per axis (kernel * factor^2 over both axes)
-            float s = 0.f;
+            float sacc = 0.f;
             for (int p = 0; p < 4; p++) {
                 const int r = (int)Yo + p - 2;
                 if (r < 0 || (r & 1) || (r >> 1) >= (int)Hs) continue;
                 for (int q = 0; q < 4; q++) {
                     const int c = (int)Xo + q - 2;
                     if (c < 0 || (c & 1) || (c >> 1) >= (int)Ws) continue;
-                    s = fmaf(k4[p] * k4[q], __ldg(skip + (((size_t)b * Hs + (r >> 1)) * Ws + (c >> 1)) * 3 + lane), s);
+                    sacc = fmaf(k4[p] * k4[q], __ldg(skip + (((size_t)b * Hs + (r >> 1)) * Ws + (c >> 1)) * 3 + part), sacc);
                 }
             }
-            v += s;
+            v += sacc;
         }
-        if (out_nhwc) out_nhwc[pix * 3 + lane] = v;
-        if (out_nchw) out_nchw[(((size_t)b * 3 + lane) * H + Yo) * W + Xo] = v;
+        if (out_nhwc) out_nhwc[pix * 3 + part] = v;
+        if (out_nchw) out_nchw[(((size_t)b * 3 + part) * H + Yo) * W + Xo] = v;
     }
 }
 
@@ -268,11 +310,11 @@ extern "C" int sdfg_upconv_gather(const uint16_t* y, uint32_t B, uint32_t H, uin
 extern "C" int sdfg_to_rgb(const uint16_t* x, const float* weight, const float* style, float scale, const float* bias, const float* skip,
                            uint32_t B, uint32_t H, uint32_t W, uint32_t C, float* wrgb_scratch, float* out_nhwc, float* out_nchw, void* stream) {
     if (B == 0) return SDFG_OK;
-    SDFG_REQUIRE(x && weight && style && bias && wrgb_scratch && (out_nhwc || out_nchw) && C % 8 == 0, SDFG_ERR_INVALID, "to_rgb: null pointer / bad channel count");
+    SDFG_REQUIRE(x && weight && style && bias && wrgb_scratch && (out_nhwc || out_nchw), SDFG_ERR_INVALID, "to_rgb: null pointer");
+    SDFG_REQUIRE(C % 64 == 0 && C <= 512, SDFG_ERR_UNSUPPORTED, "to_rgb: channels must be a multiple of 64, at most 512 (got %u)", C);
     cudaStream_t st = (cudaStream_t)stream;
     rgb_weight_kernel<<<ceil_div<uint32_t>(B * 3 * C, 256), 256, 0, st>>>(weight, style, scale, C, B, wrgb_scratch);
     if (int e = check_launch("rgb_weight_kernel")) return e;
-    const uint64_t npix = (uint64_t)B * H * W;
-    to_rgb_kernel<<<(unsigned)ceil_div<uint64_t>(npix, 8), 256, 0, st>>>(x, wrgb_scratch, bias, skip, B, H, W, C, out_nhwc, out_nchw);
+    to_rgb_kernel<<<B * ceil_div<uint32_t>(H * W, 32), 256, 0, st>>>(x, wrgb_scratch, bias, skip, B, H, W, C, out_nhwc, out_nchw);
     return check_launch("to_rgb_kernel");
 }

@@ -174,130 +174,11 @@ static bool bchain_eligible(const sdfg_field_params* p, const float* d_x_in) {
     return true;
 }
 
-static int field_forward_chain(const sdfg_field_params* p, const TcLayout& L, const float* x_in, const float* view_feat, uint64_t N,
-                               float* out_sdf, float* out_rgb, float* out_feat, uint16_t* out_feat16, uint8_t* ws, int save, cudaStream_t st) {
-    const bool want_views = out_rgb || out_feat || out_feat16;
-    const uint32_t W = L.W, nf = L.n_film;
-    auto Wb = [&](uint32_t i) { return (h16*)(ws + L.off_w[i]); };
-    auto A = [&](uint32_t l) { return (h16*)(ws + L.off_a[l]); };
-    SDFG_REQUIRE(!want_views || view_feat, SDFG_ERR_INVALID, "field_forward: view_feat is required for the rgb / feature outputs");
-    SDFG_REQUIRE(!out_rgb || (p->rgb_w && p->rgb_b), SDFG_ERR_INVALID, "field_forward: rgb head missing");
-
-    tc::ChainMaps maps;
-    tc::ChainStoreMaps stores;
-    tc::ChainParams P = {};
-    P.M_total = (uint32_t)N; P.rows_per_image = p->samples_per_image; P.rows_per_ray = p->samples_per_ray;
-    P.in_dim = p->in_dim; P.view_dim = p->view_dim;
-    P.x_nk = ceil_div<uint32_t>(p->in_dim, 16);
-    P.v_nk = want_views ? ceil_div<uint32_t>(p->view_dim, 16) : 0;   // the view part is loaded only when a layer consumes it
-    P.x_in = x_in; P.view_feat = view_feat;
-    P.w_x = p->has_input_linear ? p->input_w : p->film_w[0]; P.ld_wx = p->in_dim;
-    P.w_v = p->film_w[nf] ? p->film_w[nf] + W : nullptr; P.ld_wv = W + p->view_dim;
-    if (!P.w_v) P.v_nk = 0;
-    P.gamma = p->gamma; P.beta = p->beta; P.gstride = (int64_t)(nf + 1) * W;
-    P.kp_x = L.Kp_in; P.kp_v = L.Kp_v - W;
-    if (save) {
-        P.x16 = (h16*)(ws + L.off_x0);
-        if (P.v_nk) { P.v16 = A(nf) + W; P.ld_v16 = L.Kp_v; }
-    }
-    uint32_t nl = 0, nm = 0;
-    auto add_main_map = [&](uint32_t wi, uint32_t ldw) -> int {          // fp16 weights [W, ldw]: every 64-column chunk incl. a partial tail (OOB = 0)
-        return make_tensor_map_16(&maps.m[nm], Wb(wi), W, ldw, ldw, 256, 64, tc::FMT_F16);
-    };
-    // SAVE: sign(cos(gamma u + c)) masks of FiLM layer l for the backward chain
-    auto cos_to = [&](uint32_t layer, uint32_t l) -> int {
-        P.layer[layer].sgn = ws + L.off_c[l];
-        return SDFG_OK;
-    };
-    // SAVE: the layer's output tile is TMA-stored chunk by chunk to dst [N, 256] (pitch ld)
-    auto store_to = [&](uint32_t layer, h16* dst, uint64_t ld) -> int {
-        P.layer[layer].store = 1;
-        return make_tensor_map_16(&stores.m[layer], dst, N, W, ld, tc::CH_TILE_M, 64, tc::FMT_F16);
-    };
-    auto trunk_outputs = [&](uint32_t layer, uint32_t l) -> int {     // output of trunk layer l = A(l+1)
-        const bool last = l + 1 == nf;
-        if (last && out_sdf) { tc::ChainLayer& Y = P.layer[layer]; Y.nh = 1; Y.head_w = p->sigma_w; Y.head_b = p->sigma_b; Y.out_head = out_sdf; }
-        return save ? store_to(layer, A(l + 1), last ? L.Kp_v : W) : SDFG_OK;
-    };
-    // layer 0: input_linear (ngp) or the first FiLM layer on the raw x part (siren)
-    {
-        tc::ChainLayer& Y = P.layer[nl];
-        Y.small_k0 = 0; Y.small_nk = P.x_nk;
-        Y.tm_small = tc::CH_MAX_MAPS; Y.c0_small = 0;                   // layer 0's weights: one chunk of the last map slot
-        if (int e = make_tensor_map_16(&maps.m[tc::CH_MAX_MAPS], Wb(p->has_input_linear ? 0 : 1), W, L.Kp_in, L.Kp_in, 256, 64, tc::FMT_F16)) return e;
-        if (p->has_input_linear) {
-            Y.act = 0; Y.bias = p->input_b;
-            if (save) if (int e = store_to(nl, A(0), W)) return e;
-        } else {
-            Y.act = 1; Y.film = 0; Y.bias = p->film_b[0];
-            if (save) if (int e = cos_to(nl, 0)) return e;
-            if (int e = trunk_outputs(nl, 0)) return e;
-        }
-        nl++;
-    }
-    for (uint32_t l = p->has_input_linear ? 0u : 1u; l < nf; l++) {
-        tc::ChainLayer& Y = P.layer[nl];
-        Y.has_main = 1; Y.tm = nm; Y.act = 1; Y.film = l; Y.bias = p->film_b[l];
-        if (save) if (int e = cos_to(nl, l)) return e;
-        if (int e = add_main_map(1 + l, W)) return e;
-        nm++;
-        if (int e = trunk_outputs(nl, l)) return e;
-        nl++;
-    }
-    if (want_views) {
-        tc::ChainLayer& Y = P.layer[nl];
-        Y.has_main = 1; Y.tm = nm; Y.act = 1; Y.film = nf; Y.bias = p->film_b[nf];
-        if (save) if (int e = cos_to(nl, nf)) return e;
-        Y.small_k0 = P.x_nk; Y.small_nk = P.v_nk;
-        Y.tm_small = nm; Y.c0_small = W;                                // the view columns: the 5th chunk of the same matrix
-        if (int e = add_main_map(1 + nf, L.Kp_v)) return e;
-        nm++;
-        if (save) if (int e = store_to(nl, (h16*)(ws + L.off_hv), W)) return e;
-        if (out_feat16) if (int e = store_to(nl, out_feat16, W)) return e;      // features leave the chip as fp16, by TMA
-        if (out_feat) { Y.out_f32 = out_feat; Y.ld_out_f32 = W; }
-        if (out_rgb) { Y.nh = 3; Y.head_w = p->rgb_w; Y.head_b = p->rgb_b; Y.out_head = out_rgb; }
-        nl++;
-    }
-    P.n_layers = nl;
-    for (uint32_t i = 0; i < nl; i++) P.layer[i].to_act = (i + 1 < nl || P.layer[i].store) ? 1 : 0;
-    P.n_tiles = (uint32_t)ceil_div<uint64_t>(N, tc::CH_TILE_M);
-    const uint32_t ctas = std::min<uint32_t>((uint32_t)sm_count(), P.n_tiles);
-    P.tiles_per_cta = ceil_div<uint32_t>(P.n_tiles, ctas);
-    const uint32_t grid = ceil_div<uint32_t>(P.n_tiles, P.tiles_per_cta);
-    const uint32_t smem = tc::chain_smem_bytes();
-    const bool storing = save || out_feat16;
-    auto kern = save ? tc::tc_chain_fwd_kernel<true, true> : (storing ? tc::tc_chain_fwd_kernel<true, false> : tc::tc_chain_fwd_kernel<false, false>);
-    if (int e = optin_smem((const void*)kern, smem, "tc_chain_fwd_kernel")) return e;
-    static const bool dbg_on = getenv("SDFG_CHAIN_DBG") != nullptr;     // debugging aid: event log of CTA 0 to stderr
-    if (dbg_on) {
-        static unsigned long long* dbuf = nullptr;
-        if (!dbuf) cudaMalloc(&dbuf, 20 * 2048 * 8);
-        cudaMemsetAsync(dbuf, 0, 20 * 2048 * 8, st);
-        P.dbg = dbuf;
-        kern<<<grid, tc::CH_THREADS, smem, st>>>(maps, stores, P);
-        cudaStreamSynchronize(st);
-        static unsigned long long host[20 * 2048];
-        cudaMemcpy(host, dbuf, sizeof(host), cudaMemcpyDeviceToHost);
-        static int dumps = 0;
-        if (dumps++ == 2)
-            for (int role = 0; role < 20; role++)
-                for (int k = 0; k < 1024 && host[role * 2048 + 2 * k + 1]; k++)
-                    fprintf(stderr, "CHDBG %d %llu %llu\n", role, host[role * 2048 + 2 * k], host[role * 2048 + 2 * k + 1]);
-        return check_launch("tc_chain_fwd_kernel<gemm>");
-    }
-    ProfScope prof("tc_chain_fwd_kernel<gemm>", st);
-    kern<<<grid, tc::CH_THREADS, smem, st>>>(maps, stores, P);
-    return check_launch("tc_chain_fwd_kernel<gemm>");
-}
-
 static bool split_enabled() {
     static const bool on = []() { const char* e = getenv("SDFG_TC_SPLIT"); return !(e && e[0] == '0'); }();      // SDFG_TC_SPLIT=0: plain fp16 x part
     return on;
 }
-static bool fchain_enabled() {
-    static const bool on = []() { const char* e = getenv("SDFG_TC_FWD"); return !(e && e[0] == 'o'); }();      // SDFG_TC_FWD=old: tc_chain.cuh
-    return on;
-}
+static bool fchain_enabled() { return true; }
 // input_linear collapsed into the first FiLM layer (the forward chain and the backward must agree on it):
 //   u_0 = gamma o (W_0 (W_in x + b_in) + b_0) + beta = (gamma o W10) x + (gamma o c0 + beta),  W10 = W_0 W_in [256, in_dim], c0 = W_0 b_in + b_0
 // The product W10 is formed in fp32 and rounded to fp16 once, so the fp16 rounding of h_0 = W_in x + b_in and of W_0 (|W_0| ~ 1/3, then
@@ -565,8 +446,9 @@ int field_forward_tc(const sdfg_field_params* p, const float* x_in, const float*
     const uint32_t W = L.W, nf = L.n_film;
     const int64_t gstride = (int64_t)(nf + 1) * W;
     const bool want_views = out_rgb || out_feat || out_feat16;
-    if (chain_enabled() && fchain_enabled() && chain_eligible(p, want_views))
+    if (chain_enabled() && chain_eligible(p, want_views))
         return field_forward_fchain(p, L, x_in, view_feat, N, out_sdf, out_rgb, out_feat, out_feat16, ws, save, st);
+    // ---- per-layer kernels (tc_layer.cuh): shapes the fused chain does not take (in_dim > 32, view_dim > 16), or SDFG_TC_CHAIN=0
     // 1. weights -> fp16 (padded K)
     if (p->has_input_linear)
         if (int e = cast_pad(p->input_w, p->in_dim, 1, Wb(0), L.Kp_in, W, p->in_dim, L.Kp_in, st)) return e;
@@ -575,8 +457,6 @@ int field_forward_tc(const sdfg_field_params* p, const float* x_in, const float*
         const uint32_t K = l == nf ? W + p->view_dim : ((l == 0 && !p->has_input_linear) ? p->in_dim : W);
         if (int e = cast_pad(p->film_w[l], K, 1, Wb(1 + l), round_up(K, 8), W, K, round_up(K, 8), st)) return e;
     }
-    if (chain_enabled() && chain_eligible(p, want_views))
-        return field_forward_chain(p, L, x_in, view_feat, N, out_sdf, out_rgb, out_feat, out_feat16, ws, save, st);
     // 2. encoder features -> fp16
     h16* X0 = (h16*)(ws + L.off_x0);
     if (int e = cast_pad(x_in, p->in_dim, 1, X0, L.Kp_in, N, p->in_dim, L.Kp_in, st)) return e;
