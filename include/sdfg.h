@@ -297,7 +297,7 @@ int sdfg_upconv_gather(const uint16_t* y, uint32_t B, uint32_t H, uint32_t W, ui
 
 /* ToRGB (:821-843): 1 x 1 modulated convolution without demodulation to 3 channels + bias [3] + (skip != NULL) the previous level's
  * rgb [B, H/2, W/2, 3] up-sampled by Upsample (upfirdn2d up = 2, outer([1,3,3,1]) / 16, pad (2, 1)).  weight [3, C], style [B, C],
- * wrgb_scratch [B, 3, C].  Outputs (either may be NULL): out_nhwc [B, H, W, 3] (skip of the next level), out_nchw [B, 3, H, W]. */
+ * wrgb_scratch [B, C, 4] floats (16-byte aligned).  Outputs (either may be NULL): out_nhwc [B, H, W, 3] (skip of the next level), out_nchw [B, 3, H, W]. */
 int sdfg_to_rgb(const uint16_t* x, const float* weight, const float* style, float scale, const float* bias, const float* skip, uint32_t B,
                 uint32_t H, uint32_t W, uint32_t C, float* wrgb_scratch, float* out_nhwc, float* out_nchw, void* stream);
 

@@ -42,7 +42,7 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 if rank == 0:
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     evs.sort(key=lambda e: e.time_range.start)
-    last_fwd = [e for e in evs if "tc_chain_fwd" in e.name][-1].time_range.start
+    last_fwd = [e for e in evs if "tc_fchain_fwd" in e.name][-1].time_range.start
     for e in evs:
         d = e.time_range.end - e.time_range.start
         if e.time_range.start >= last_fwd and (d > 80 or "nccl" in e.name.lower()):

@@ -90,34 +90,63 @@ __global__ void __launch_bounds__(256) upconv_gather_kernel(const uint16_t* __re
     const int Y0 = (int)(t / tiles_x) * UG_T, X0 = (int)(t % tiles_x) * UG_T;
     const size_t ldy = (size_t)9 * C;
     const uint16_t* Yb = Y + (size_t)b * H * W * ldy + c0;
-    for (int e = slot; e < UG_P * UG_P; e += 32) {
-        const int r = Y0 + e / UG_P - 1, c = X0 + e % UG_P - 1;        // position in T
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (r >= 0 && c >= 0 && r <= (int)Ho && c <= (int)Wo) {
-            // a = r mod 2 (+ 2 when r is even): the taps whose stride-2 placement lands on this row / column
+    // Positions of the patch by parity class: tile origins are multiples of 16, so patch row tr is T row Y0 + tr - 1 -- ODD for even tr.
+    // An odd T row receives tap a = 1 only, an even one taps a = 0 and 2 (likewise for columns): 1, 2, 2 or 4 reads of Y per position.
+    // One loop per class keeps the bodies branch-free, so the loads of several positions are in flight together.
+    auto ld8 = [&](int y, int x, int tap, float (&acc)[8]) {
+        const bool ok = y >= 0 && x >= 0 && y < (int)H && x < (int)W;
+        const uint4 v = ok ? __ldg(reinterpret_cast<const uint4*>(Yb + ((size_t)y * W + x) * ldy + (size_t)tap * C)) : make_uint4(0, 0, 0, 0);
+        const uint32_t hw[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int ai = 0; ai < 2; ai++) {
-                const int a = (r & 1) ? 1 : 2 * ai;
-                if ((r & 1) && ai) break;
-                const int y = (r - a) >> 1;
-                if (r - a < 0 || y >= (int)H) continue;
-#pragma unroll
-                for (int bi = 0; bi < 2; bi++) {
-                    const int bb = (c & 1) ? 1 : 2 * bi;
-                    if ((c & 1) && bi) break;
-                    const int x = (c - bb) >> 1;
-                    if (c - bb < 0 || x >= (int)W) continue;
-                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(Yb + ((size_t)y * W + x) * ldy + (size_t)(a * 3 + bb) * C));
-                    const uint32_t hw[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const float2 f = tc::unpack_f16(hw[k]);
-                        acc[2 * k] += f.x; acc[2 * k + 1] += f.y;
-                    }
-                }
-            }
+        for (int k = 0; k < 4; k++) {
+            const float2 f = tc::unpack_f16(hw[k]);
+            acc[2 * k] += f.x; acc[2 * k + 1] += f.y;
         }
-        T[e][cg] = make_uint4(tc::pack_f16_sat(acc[0], acc[1]), tc::pack_f16_sat(acc[2], acc[3]), tc::pack_f16_sat(acc[4], acc[5]), tc::pack_f16_sat(acc[6], acc[7]));
+    };
+    auto put = [&](int tr, int tcn, const float (&acc)[8]) {
+        T[tr * UG_P + tcn][cg] = make_uint4(tc::pack_f16_sat(acc[0], acc[1]), tc::pack_f16_sat(acc[2], acc[3]), tc::pack_f16_sat(acc[4], acc[5]), tc::pack_f16_sat(acc[6], acc[7]));
+    };
+    constexpr int NE = (UG_P + 1) / 2, NO = UG_P / 2;                  // even / odd patch indices: 10 / 9
+    // (even tr, even tc): T row and column odd -> tap (1, 1)
+#pragma unroll 2
+    for (int e = slot; e < NE * NE; e += 32) {
+        const int tr = 2 * (e / NE), tcn = 2 * (e % NE);
+        const int r = Y0 + tr - 1, c = X0 + tcn - 1;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        ld8((r - 1) >> 1, (c - 1) >> 1, 4, acc);
+        put(tr, tcn, acc);
+    }
+    // (even tr, odd tc): row odd (a = 1), column even (b' = 0, 2)
+#pragma unroll 2
+    for (int e = slot; e < NE * NO; e += 32) {
+        const int tr = 2 * (e / NO), tcn = 2 * (e % NO) + 1;
+        const int r = Y0 + tr - 1, c = X0 + tcn - 1;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        ld8((r - 1) >> 1, c >> 1, 3, acc);
+        ld8((r - 1) >> 1, (c >> 1) - 1, 5, acc);
+        put(tr, tcn, acc);
+    }
+    // (odd tr, even tc): row even (a = 0, 2), column odd (b' = 1)
+#pragma unroll 2
+    for (int e = slot; e < NO * NE; e += 32) {
+        const int tr = 2 * (e / NE) + 1, tcn = 2 * (e % NE);
+        const int r = Y0 + tr - 1, c = X0 + tcn - 1;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        ld8(r >> 1, (c - 1) >> 1, 1, acc);
+        ld8((r >> 1) - 1, (c - 1) >> 1, 7, acc);
+        put(tr, tcn, acc);
+    }
+    // (odd tr, odd tc): both even -> four taps
+#pragma unroll 2
+    for (int e = slot; e < NO * NO; e += 32) {
+        const int tr = 2 * (e / NO) + 1, tcn = 2 * (e % NO) + 1;
+        const int r = Y0 + tr - 1, c = X0 + tcn - 1;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        ld8(r >> 1, c >> 1, 0, acc);
+        ld8(r >> 1, (c >> 1) - 1, 2, acc);
+        ld8((r >> 1) - 1, c >> 1, 6, acc);
+        ld8((r >> 1) - 1, (c >> 1) - 1, 8, acc);
+        put(tr, tcn, acc);
     }
     __syncthreads();
     const float nw = (noise && noise_w) ? __ldg(noise_w) : 0.f;
@@ -164,73 +193,79 @@ __global__ void __launch_bounds__(256) upconv_gather_kernel(const uint16_t* __re
 // out[Y, X] = sum_{p, q} k[p] k[q] U[Y + p - 2, X + q - 2], U[2y, 2x] = skip[y, x], zero elsewhere.
 // 8 threads per pixel (each a contiguous eighth of the channels, 16-byte loads), the sample's 3 x C weights in shared memory;
 // a block's 32 pixels belong to one sample.   out_nchw (fp32 [B, 3, H, W], the image) and / or out_nhwc (fp32 [B, H, W, 3], the next skip)
-__global__ void __launch_bounds__(256) to_rgb_kernel(const uint16_t* __restrict__ x, const float* __restrict__ wrgb, const float* __restrict__ bias,
+// A thread owns 16 consecutive input channels (its 48 weights live in registers) and walks RGB_PIX / lanes pixels of one sample;
+// C / 16 adjacent threads (8 .. 32: a shuffle group) share a pixel.  Weights through L1 per pixel cost 8 tag look-ups per load.
+constexpr uint32_t RGB_PIX = 256;      // pixels per block, all of one sample
+__global__ void __launch_bounds__(256) to_rgb_kernel(const uint16_t* __restrict__ x, const float4* __restrict__ wrgb4, const float* __restrict__ bias,
                                                       const float* __restrict__ skip, uint32_t B, uint32_t H, uint32_t W, uint32_t C,
                                                       float* __restrict__ out_nhwc, float* __restrict__ out_nchw) {
-    __shared__ float4 ws[512];                                          // the three weights of input channel i in one 16-byte word
-    const uint32_t blocks_per_sample = (H * W + 31) / 32;
-    const uint32_t b = blockIdx.x / blocks_per_sample;
-    const uint32_t yx = (blockIdx.x % blocks_per_sample) * 32 + (threadIdx.x >> 3);
-    const uint32_t part = threadIdx.x & 7;
-    for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) {
-        const float* wb = wrgb + (size_t)b * 3 * C + i;
-        ws[i] = make_float4(__ldg(wb), __ldg(wb + C), __ldg(wb + 2 * C), 0.f);
-    }
-    __syncthreads();
-    const bool valid = yx < H * W;
-    const uint64_t pix = (uint64_t)b * H * W + (valid ? yx : 0);
-    const uint32_t per = C / 8;                                         // channels per thread (a multiple of 8)
-    const uint16_t* xr = x + pix * C + part * per;
-    const float4* w = ws + part * per;
-    float acc[3] = {0.f, 0.f, 0.f};
-    for (uint32_t i = 0; i < per; i += 8) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + i));
-        const uint32_t hw[4] = {u.x, u.y, u.z, u.w};
+    const uint32_t tpp = C / 16;                                        // threads per pixel: 8, 16 or 32
+    const uint32_t part = threadIdx.x % tpp, lane_px = threadIdx.x / tpp, px_per_iter = 256 / tpp;
+    const uint32_t blocks_per_sample = (H * W + RGB_PIX - 1) / RGB_PIX;
+    const uint32_t b = blockIdx.x / blocks_per_sample, yx0 = (blockIdx.x % blocks_per_sample) * RGB_PIX;
+    float wr[16], wg[16], wb[16];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 16; k++) {
+        const float4 w4 = __ldg(wrgb4 + (size_t)b * C + part * 16 + k);
+        wr[k] = w4.x; wg[k] = w4.y; wb[k] = w4.z;
+    }
+    const float bs = part < 3 ? __ldg(bias + part) : 0.f;
+    const uint16_t* xb = x + (size_t)b * H * W * C + part * 16;
+#pragma unroll 2
+    for (uint32_t it = 0; it < RGB_PIX; it += px_per_iter) {
+        const uint32_t yx = yx0 + it + lane_px;
+        const bool valid = yx < H * W;
+        const uint4* xr = reinterpret_cast<const uint4*>(xb + (size_t)(valid ? yx : 0) * C);
+        const uint4 u0 = __ldg(xr), u1 = __ldg(xr + 1);
+        const uint32_t hw[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+        float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
             const float2 f = tc::unpack_f16(hw[k]);
-            const float4 w0 = w[i + 2 * k], w1 = w[i + 2 * k + 1];
-            acc[0] = fmaf(f.x, w0.x, fmaf(f.y, w1.x, acc[0]));
-            acc[1] = fmaf(f.x, w0.y, fmaf(f.y, w1.y, acc[1]));
-            acc[2] = fmaf(f.x, w0.z, fmaf(f.y, w1.z, acc[2]));
+            acc[0] = fmaf(f.x, wr[2 * k], fmaf(f.y, wr[2 * k + 1], acc[0]));
+            acc[1] = fmaf(f.x, wg[2 * k], fmaf(f.y, wg[2 * k + 1], acc[1]));
+            acc[2] = fmaf(f.x, wb[2 * k], fmaf(f.y, wb[2 * k + 1], acc[2]));
         }
-    }
+        for (uint32_t o = 1; o < tpp; o <<= 1) {
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
-        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
-        acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 4);
-    }
-    if (valid && part < 3) {
-        const uint32_t Yo = yx / W, Xo = yx % W;
-        float v = (part == 0 ? acc[0] : part == 1 ? acc[1] : acc[2]) + __ldg(bias + part);
-        if (skip) {
-            const uint32_t Hs = H / 2, Ws = W / 2;
-            const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};          // [1,3,3,1] / 8 * 2 per axis (kernel * factor^2 over both axes)
-            float sacc = 0.f;
-            for (int p = 0; p < 4; p++) {
-                const int r = (int)Yo + p - 2;
-                if (r < 0 || (r & 1) || (r >> 1) >= (int)Hs) continue;
-                for (int q = 0; q < 4; q++) {
-                    const int c = (int)Xo + q - 2;
-                    if (c < 0 || (c & 1) || (c >> 1) >= (int)Ws) continue;
-                    sacc = fmaf(k4[p] * k4[q], __ldg(skip + (((size_t)b * Hs + (r >> 1)) * Ws + (c >> 1)) * 3 + part), sacc);
-                }
-            }
-            v += sacc;
+            for (int c = 0; c < 3; c++) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
         }
-        if (out_nhwc) out_nhwc[pix * 3 + part] = v;
-        if (out_nchw) out_nchw[(((size_t)b * 3 + part) * H + Yo) * W + Xo] = v;
+        if (valid && part < 3) {
+            const uint32_t Yo = yx / W, Xo = yx % W;
+            const uint64_t pix = (uint64_t)b * H * W + yx;
+            float v = (part == 0 ? acc[0] : part == 1 ? acc[1] : acc[2]) + bs;
+            if (skip) {
+                const uint32_t Hs = H / 2, Ws = W / 2;
+                const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};      // [1,3,3,1] / 8 * 2 per axis (kernel * factor^2 over both axes)
+                // U[2y, 2x] = skip[y, x]: of the 4 x 4 taps the two per axis with Y + p even contribute
+                float sacc = 0.f;
+#pragma unroll
+                for (int pi = 0; pi < 2; pi++) {
+                    const int p = (Yo & 1) + 2 * pi, r = ((int)Yo + p - 2) >> 1;
+                    if (r < 0 || r >= (int)Hs) continue;
+#pragma unroll
+                    for (int qi = 0; qi < 2; qi++) {
+                        const int q = (Xo & 1) + 2 * qi, c = ((int)Xo + q - 2) >> 1;
+                        if (c < 0 || c >= (int)Ws) continue;
+                        sacc = fmaf(k4[p] * k4[q], __ldg(skip + (((size_t)b * Hs + r) * Ws + c) * 3 + part), sacc);
+                    }
+                }
+                v += sacc;
+            }
+            if (out_nhwc) out_nhwc[pix * 3 + part] = v;
+            if (out_nchw) out_nchw[(((size_t)b * 3 + part) * H + Yo) * W + Xo] = v;
+        }
     }
 }
 
-// wrgb[b, c, i] = scale * W[c, i] * style[b, i]
+// wrgb4[b, i] = scale * style[b, i] * (W[0, i], W[1, i], W[2, i], 0)
 __global__ void __launch_bounds__(256) rgb_weight_kernel(const float* __restrict__ W, const float* __restrict__ style, float scale, uint32_t C,
-                                                          uint32_t B, float* __restrict__ out) {
+                                                          uint32_t B, float4* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * 3 * C) return;
-    const uint32_t b = i / (3 * C), k = i % (3 * C);
-    out[i] = scale * __ldg(W + k) * __ldg(style + (size_t)b * C + k % C);
+    if (i >= B * C) return;
+    const uint32_t k = i % C;
+    const float sc = scale * __ldg(style + i);
+    out[i] = make_float4(sc * __ldg(W + k), sc * __ldg(W + C + k), sc * __ldg(W + 2 * C + k), 0.f);
 }
 
 }  // namespace sdfg
@@ -311,10 +346,11 @@ extern "C" int sdfg_to_rgb(const uint16_t* x, const float* weight, const float* 
                            uint32_t B, uint32_t H, uint32_t W, uint32_t C, float* wrgb_scratch, float* out_nhwc, float* out_nchw, void* stream) {
     if (B == 0) return SDFG_OK;
     SDFG_REQUIRE(x && weight && style && bias && wrgb_scratch && (out_nhwc || out_nchw), SDFG_ERR_INVALID, "to_rgb: null pointer");
-    SDFG_REQUIRE(C % 64 == 0 && C <= 512, SDFG_ERR_UNSUPPORTED, "to_rgb: channels must be a multiple of 64, at most 512 (got %u)", C);
+    SDFG_REQUIRE(C == 128 || C == 256 || C == 512, SDFG_ERR_UNSUPPORTED, "to_rgb: 128, 256 or 512 channels (got %u)", C);
     cudaStream_t st = (cudaStream_t)stream;
-    rgb_weight_kernel<<<ceil_div<uint32_t>(B * 3 * C, 256), 256, 0, st>>>(weight, style, scale, C, B, wrgb_scratch);
+    rgb_weight_kernel<<<ceil_div<uint32_t>(B * C, 256), 256, 0, st>>>(weight, style, scale, C, B, reinterpret_cast<float4*>(wrgb_scratch));
     if (int e = check_launch("rgb_weight_kernel")) return e;
-    to_rgb_kernel<<<B * ceil_div<uint32_t>(H * W, 32), 256, 0, st>>>(x, wrgb_scratch, bias, skip, B, H, W, C, out_nhwc, out_nchw);
+    to_rgb_kernel<<<B * ceil_div<uint32_t>(H * W, RGB_PIX), 256, 0, st>>>(x, reinterpret_cast<const float4*>(wrgb_scratch), bias, skip, B, H, W, C, out_nhwc,
+                                                                           out_nchw);
     return check_launch("to_rgb_kernel");
 }

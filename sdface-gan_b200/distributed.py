@@ -6,6 +6,8 @@ im2scene/training_utils.py:186-187, but nothing is wrapped); this module is the 
 unchanged on the package's modules (their custom autograd nodes deposit gradients on ordinary parameters); `average_gradients`
 is the explicit, bucketed alternative used when the caller accumulates several micro-batches before exchanging.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -85,8 +87,11 @@ def data_parallel(module, device_ids=None, early_table_exchange=True, process_gr
                 owner = n[:-len("encoder.embeddings")].rstrip(".")
                 mods[owner]._table_exchange = {"group": process_group}                       # the field network (sdf_model._field)
                 mods[(owner + "." if owner else "") + "encoder"]._table_exchange = {"group": process_group}   # GridEncoder's own node (query_sdf)
-    ddp_kwargs.setdefault("bucket_cap_mb", 64)
+    # (with the table handled above, 4 MB of MLP / mapping gradients remain) small buckets: all but the last leave while backward
+    # still runs; buffers are constants (level offsets, pixel grids): no per-forward broadcast
+    ddp_kwargs.setdefault("bucket_cap_mb", int(os.environ.get("SDFG_DDP_BUCKET_MB", "2")) if names else 64)
     ddp_kwargs.setdefault("gradient_as_bucket_view", True)
+    ddp_kwargs.setdefault("broadcast_buffers", False)
     if process_group is not None:
         ddp_kwargs.setdefault("process_group", process_group)
     return ddp(module, device_ids=device_ids, **ddp_kwargs)

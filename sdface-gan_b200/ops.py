@@ -445,7 +445,7 @@ def to_rgb(x, weight, style, scale, bias, skip=None, want_nhwc=True, want_nchw=F
     w = _chk(weight.reshape(3, C).contiguous(), "weight")
     style = _chk(style.contiguous().float(), "style")
     b = _chk(bias.reshape(3).contiguous(), "bias")
-    scratch = torch.empty(B, 3, C, device=x.device)
+    scratch = torch.empty(B, C, 4, device=x.device)
     o1 = torch.empty(B, H, W, 3, device=x.device) if want_nhwc else None
     o2 = torch.empty(B, 3, H, W, device=x.device) if want_nchw else None
     with torch.cuda.device(x.device):
