@@ -4,7 +4,7 @@
 //             16-byte unit u of row r stored at u ^ (r & 7) -- what TMA SWIZZLE_128B writes and the UMMA descriptors expect
 //   threads   640 = 16 epilogue warps (4 per TMEM lane quarter = 4 per SM sub-partition, 16 columns of every 64-column chunk each)
 //             + 4 role warps (TMA producer, MMA issuer, loader, storer) at the highest warp ids (issue priority)
-//   sign plane  sign(cos u) of one tile and layer as 1 bit per element: [4 chunks][4 sub-blocks][128 rows] x u16 = 4 KB
+//   derivative plane  sign(cos u) + rounding bit of the saved sine, 2 bits per element: [4 chunks][4 sub-blocks][128 rows] x u32 = 8 KB
 #pragma once
 #include "tc_common.cuh"
 
@@ -14,7 +14,11 @@ namespace tc {
 constexpr uint32_t CH_TILE_M = 128;
 constexpr uint32_t CH_CHUNK_BYTES = CH_TILE_M * 128;        // [128 samples x 64 fp16] = 16 KB
 constexpr uint32_t CH_ACT_BYTES = 4 * CH_CHUNK_BYTES;       // K = 256
-constexpr uint32_t CH_SGN_TILE_BYTES = 4096;                // sign(cos) bits of one tile and layer: [4 chunks][4 sub-blocks][128 rows] x 16 bit
+// derivative planes of one tile and layer: [4 chunks][4 sub-blocks][128 rows] x 32 bit.  Per thread and 16-column piece: low half =
+// sign(cos u) of its 16 elements, high half = the ROUNDING bit of the saved fp16 sine (1: round-to-nearest went away from zero,
+// |stored| > |sin u|) -- it halves the interval the backward's cos = sqrt(1 - sin^2) has to guess in where |sin| -> 1.
+// Bit j = element 2j, bit 8 + j = element 2j + 1 in both halves.
+constexpr uint32_t CH_SGN_TILE_BYTES = 8192;
 constexpr uint32_t CH_AUX_BYTES = 32768;                    // inference: resident small weights; training: 2 sign-mask tiles
 constexpr uint32_t CH_W_STAGE_BYTES = 256 * 128;            // one streamed weight chunk
 constexpr uint32_t CH_W_STAGES = 3;

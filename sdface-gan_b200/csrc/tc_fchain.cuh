@@ -43,7 +43,7 @@ constexpr int CH_POLY_PAIRS = SDFG_POLY_PAIRS;              // of the 8 element 
 
 constexpr uint32_t FC_MAX_LAYERS = SDFG_MAX_FILM + 1;
 __host__ __device__ constexpr uint32_t fc_w_bytes(int cg) { return 32768u / (uint32_t)cg; }
-__host__ __device__ constexpr uint32_t fc_w_stages(int cg) { return cg == 2 ? 7u : 3u; }
+__host__ __device__ constexpr uint32_t fc_w_stages(int cg) { return cg == 2 ? 6u : 3u; }
 constexpr uint32_t FC_MAX_W_STAGES = 7;
 
 // layer kinds: the epilogue body is compiled once per kind with the layer's properties as constants (FK_GENERIC reads them at run time)
@@ -414,6 +414,7 @@ tc_fchain_fwd_kernel(const __grid_constant__ FChainMaps maps, const __grid_const
                         tmem_ld_wait16(raw[c & 1]);
                         if (c < 3) tmem_ld16_issue(taddr + (c + 1) * 64, raw[(c + 1) & 1]);
                         float v[16];
+                        uint32_t sgn_m = 0;                                 // sign(cos) mask of this piece, in bits 16..31 once all 16 are in
 #pragma unroll
                         for (int k = 0; k < 16; k++) v[k] = __uint_as_float(raw[c & 1][k]);
                         if (L_act) {
@@ -426,12 +427,10 @@ tc_fchain_fwd_kernel(const __grid_constant__ FChainMaps maps, const __grid_const
                             if (do_sgn) {
                                 // A funnel shift per element moves the parity bit into the mask: even elements first, then odd ones, so that
                                 // bit j = element 2j and bit 8 + j = element 2j + 1 (the order the backward chain's packed-half sign flip wants).
-                                uint32_t m = 0;
 #pragma unroll
-                                for (int j = 0; j < 8; j++) m = __funnelshift_r(m, (uint32_t)t2[j], 1);
+                                for (int j = 0; j < 8; j++) sgn_m = __funnelshift_r(sgn_m, (uint32_t)t2[j], 1);
 #pragma unroll
-                                for (int j = 0; j < 8; j++) m = __funnelshift_r(m, (uint32_t)(t2[j] >> 32), 1);
-                                asm volatile("st.shared.u16 [%0], %1;" ::"r"(smem_u32(smSGN) + (((n & 1) * 16 + c * 4 + sb) * 128 + r) * 2), "h"((uint16_t)(m >> 16)) : "memory");
+                                for (int j = 0; j < 8; j++) sgn_m = __funnelshift_r(sgn_m, (uint32_t)(t2[j] >> 32), 1);
                             }
 #pragma unroll
                             for (int j = 0; j < 8; j++) {
@@ -466,8 +465,28 @@ tc_fchain_fwd_kernel(const __grid_constant__ FChainMaps maps, const __grid_const
                             }
                         }
                         if (L_to_act) {
-                            const uint4 h0 = make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
-                            const uint4 h1 = make_uint4(pack_f16(v[8], v[9]), pack_f16(v[10], v[11]), pack_f16(v[12], v[13]), pack_f16(v[14], v[15]));
+                            uint32_t hp[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) hp[j] = pack_f16(v[2 * j], v[2 * j + 1]);
+                            const uint4 h0 = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                            const uint4 h1 = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+                            if (do_sgn) {
+                                // rounding bits: round-to-nearest and round-toward-zero differ (by one ulp: the LSB flips) exactly where
+                                // the stored sine's magnitude was rounded UP; pair j contributes bit j (low half) and bit 16 + j (high half)
+                                uint32_t rm = 0;
+#pragma unroll
+                                for (int j = 0; j < 8; j++) {
+#if SDFG_RBIT == 1
+                                    rm += ((hp[j] ^ pack_f16_rz(v[2 * j], v[2 * j + 1])) & 0x00010001u) << j;
+#elif SDFG_RBIT == 2
+                                    // RN != RZ <=> the first dropped mantissa bit (bit 12 of the fp32 word) is set (ties and fp16 subnormals aside)
+                                    const uint32_t t = __byte_perm(__float_as_uint(v[2 * j]), __float_as_uint(v[2 * j + 1]), 0x5511);
+                                    rm |= (j >= 4 ? t << (j - 4) : t >> (4 - j)) & (0x00010001u << j);
+#endif
+                                }
+                                const uint32_t plane = (sgn_m >> 16) | __byte_perm(rm, 0, 0x2044);      // [sign16 | rounding16]
+                                asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_u32(smSGN) + (((n & 1) * 16 + c * 4 + sb) * 128 + r) * 4), "r"(plane) : "memory");
+                            }
                             if (SAVE) mbar_wait(&S.st_done[c], (stgen & 1) ^ 1);   // the previous contents of the chunk have been stored
                             const uint32_t chunk = act_row + c * CH_CHUNK_BYTES;
                             sts128(chunk + u0, h0);

@@ -7,8 +7,7 @@ benchmarked tensor-core path -- are compared with the oracle on the same seeded 
 and every parameter gradient.
 
 Tolerances (north star): fp32 path max-abs 1e-3 on rendered maps; tensor-core path 2e-2 relative (rgb map: 2e-2 of its [-1, 1]
-range); gradients 1e-2 relative L2 per parameter tensor for both (one stated exception: 2e-2 for at most 3 tensors of the
-tensor-core path with the degenerate 1e-4 table).  The oracle needs ~2 s per image forward + backward.
+range); gradients 1e-2 relative L2 per parameter tensor for both.  The oracle needs ~2 s per image forward + backward.
 """
 import numpy as np
 import pytest
@@ -120,13 +119,11 @@ def test_full_size_forward_backward_matches_oracle(table_amp, features, precisio
     worst = max(errs.items(), key=lambda kv: kv[1])
     print("%s table %g features %d: worst gradient rel err %.3e (%s) over %d tensors" % (precision, table_amp, features, worst[1], worst[0], len(errs)))
     assert len(errs) >= 30
-    # 1e-2 (north star) for both CUDA paths.  One exception, stated: tensor-core path x reference init.  With a 1e-4 table every
-    # sample of an image sees the same activations, so the backward's per-element rounding (cos rebuilt as sqrt(1 - fp16(sin)^2):
-    # coarse where |sin| -> 1) no longer averages out over the 98 304 samples of an image but hits whole rows coherently:
-    # 36 of 38 tensors stay below 1e-2 (median 6e-3), the gamma head of FiLM layer 1 reaches 1.6e-2 -> 2e-2 there.
-    tol = 2e-2 if (precision == "tc16" and table_amp < 1e-3) else 1e-2
-    if tol > 1e-2:
-        assert float(np.median(list(errs.values()))) < 1e-2 and sum(e >= 1e-2 for e in errs.values()) <= 3
+    # 1e-2 (north star) for both CUDA paths.  The hard case is tensor-core path x reference init: with a 1e-4 table every sample of
+    # an image sees the same activations, so the backward's per-element rounding (cos rebuilt from the saved fp16 sine: coarse
+    # where |sin| -> 1) no longer averages out over the 98 304 samples of an image but hits whole rows coherently.  Measured worst
+    # 6.1e-3 (gamma head of FiLM layer 1); 1.6e-2 before the saved sines carried their rounding bit.
+    tol = 1e-2
     assert worst[1] < tol, [(n, e, float(ref["grads"][n].double().norm())) for n, e in sorted(errs.items(), key=lambda kv: -kv[1])[:5]]
 
 

@@ -120,14 +120,14 @@ def test_tc_wgrad_probe_matches_matmul(N, Kx, rpi, fmt):
 def test_tc_training_step_matches_reference_fixture(name):
     """The BENCHMARKED path (tc16) against the reference's own gradient digests at the north star's 1e-2 -- not against the repo's
     fp32 kernels.  8 x 8 rays x 24 samples = 1536 = 12 x 128 samples per image: tensor-core eligible.
-    Per tensor the L2 norm and a seeded random projection of the gradient are held to 1e-2 of the reference norm.  The 16 sampled
-    single ENTRIES per tensor are held to 1.5e-2 of max(|entry|, rms): one entry of a 3 072-sample sum does not average the
-    backward's per-element rounding (cos rebuilt as sqrt(1 - fp16(sin)^2), fp16 gradient tiles) the way a norm does; measured
-    worst 1.2e-2 (pts_linears.0.weight), fp32 kernels: 1e-2 (test_gpu_render.py).  Tensors whose reference gradient norm is below 1e-3
-    of the largest one (sigma_linear.bias under a loss without an sdf term: 3e-4 vs 3.5, a residue of cancelling per-sample terms) are
-    held to 1e-2 of that floor instead of their own norm."""
+    Per tensor the L2 norm, a seeded random projection of the gradient and 16 sampled single entries (against max(|entry|, rms))
+    are held to 1e-2 of the reference -- the same bar as the fp32 kernels in test_gpu_render.py.  Measured worst: norm 5.3e-3
+    (sigmoid_beta), sampled entry 4.8e-3 (pts_linears.0.weight); before the saved sines carried their rounding bit the
+    sampled entries reached 1.2e-2.  Tensors whose reference gradient norm is below 1e-3 of the largest one (sigma_linear.bias under
+    a loss without an sdf term: 3e-4 vs 3.5, a residue of cancelling per-sample terms) are held to 1e-2 of that floor instead of
+    their own norm."""
     from test_gpu_render import check_training_fixture
-    worst, worst_val = check_training_fixture(name, "tc16", 2e-2, 2e-2, val_tol=float(os.environ.get("SDFG_TEST_VAL_TOL", "1.5e-2")),
+    worst, worst_val = check_training_fixture(name, "tc16", 2e-2, 2e-2, val_tol=1e-2,
                                               norm_floor_frac=1e-3)
     print("worst |grad norm| deviation vs reference: %.3e (%s); worst sampled-entry deviation: %.3e (%s)" % (worst + worst_val))
 
