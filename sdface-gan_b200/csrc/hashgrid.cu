@@ -15,8 +15,6 @@
 // (grid.py:57) -- the affine map (x+bound)/(2*bound) of GridEncoder.forward (grid.py:149) is folded in, gradients are
 // scattered with vectorised no-return reductions (red.global.add.v2/v4.f32) straight into the caller's buffer, and every
 // launch goes to the caller's stream.
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace sdfg {
@@ -33,7 +31,6 @@ struct LevelInfo {
     uint32_t ndims;     // how many dims the dense walk consumed before stride > hashmap
     uint32_t use_hash;  // gridtype == hash && final stride > hashmap
     uint32_t pow2mask;  // hashmap - 1 if hashmap is a power of two, else 0
-    uint32_t pair_ok;   // level starts on an even row and has an even row count: rows 2k, 2k+1 form one aligned 2*C-float group
 };
 
 // exp2f() of the CUDA math library and an explicit fma: what nvcc makes of the reference's
@@ -61,7 +58,6 @@ __device__ __forceinline__ void fill_level_info(LevelInfo& li, uint32_t level, c
     li.ndims = nd;
     li.use_hash = (gridtype == 0 && stride > li.hashmap) ? 1u : 0u;
     li.pow2mask = (li.hashmap & (li.hashmap - 1)) == 0 ? li.hashmap - 1 : 0u;
-    li.pair_ok = ((li.offset | li.hashmap) & 1u) == 0 ? 1u : 0u;
 }
 
 template <uint32_t D>
@@ -153,57 +149,18 @@ __device__ __forceinline__ void red_feat_keep(float* p, const float (&v)[C], uin
 // One level of one sample: blend (and optional dy_dx).  Returns false (and zeros) when the sample is outside [0,1]^D.
 template <uint32_t D, uint32_t C, bool DYDX>
 __device__ __forceinline__ void encode_level(const float (&u)[D], const LevelInfo& li, const float* __restrict__ table,
-                                             int align_corners, uint32_t interp, bool pair16, float (&out)[C], float (&dd)[D * C]) {
+                                             int align_corners, uint32_t interp, float (&out)[C], float (&dd)[D * C]) {
     float f[D], fd[D];
     uint32_t g[D];
     locate<D>(u, li, align_corners, interp, f, fd, g);
     const float* __restrict__ grid = table + (size_t)li.offset * C;
     Feat<C> corner[1u << D];
-    bool paired = false;
-    if constexpr (C == 2) {
-        // The two corners along x of a pair are rows r and r + 1 of the level (dense: stride 1 in x; hashed: x enters the hash with
-        // prime 1, so an even x and x + 1 differ in bit 0 of the row only): when r is even both live in one aligned 16-byte group.
-        // The L1 processes a gather one 128-byte line per lane, so the cost is the number of lane-loads, not their width: fetch the
-        // aligned group of the left corner, and the right corner's group only in the lanes where it is a different one (a predicated
-        // load -- about half of the lanes at fine levels): 6 lane-loads per level instead of 8.
-        if (pair16 && li.pair_ok) {
-            paired = true;
-            uint32_t r0[1u << (D - 1)], r1[1u << (D - 1)];
-            float4 A[1u << (D - 1)], B[1u << (D - 1)];
 #pragma unroll
-            for (uint32_t h = 0; h < (1u << (D - 1)); h++) {
-                uint32_t gl[D];
-                gl[0] = g[0];
+    for (uint32_t idx = 0; idx < (1u << D); idx++) {          // issue all 2^D gathers before any use
+        uint32_t gl[D];
 #pragma unroll
-                for (uint32_t d = 1; d < D; d++) gl[d] = g[d] + ((h >> (d - 1)) & 1u);
-                r0[h] = corner_row<D>(li, gl);
-                gl[0] = g[0] + 1;
-                r1[h] = corner_row<D>(li, gl);
-                A[h] = __ldg(reinterpret_cast<const float4*>(grid) + (r0[h] >> 1));
-            }
-#pragma unroll
-            for (uint32_t h = 0; h < (1u << (D - 1)); h++) {
-                B[h] = A[h];
-                if ((r1[h] >> 1) != (r0[h] >> 1)) B[h] = __ldg(reinterpret_cast<const float4*>(grid) + (r1[h] >> 1));
-            }
-#pragma unroll
-            for (uint32_t h = 0; h < (1u << (D - 1)); h++) {
-                const bool o0 = r0[h] & 1u, o1 = r1[h] & 1u;
-                corner[2 * h].v[0] = o0 ? A[h].z : A[h].x;
-                corner[2 * h].v[C - 1] = o0 ? A[h].w : A[h].y;
-                corner[2 * h + 1].v[0] = o1 ? B[h].z : B[h].x;
-                corner[2 * h + 1].v[C - 1] = o1 ? B[h].w : B[h].y;
-            }
-        }
-    }
-    if (!paired) {
-#pragma unroll
-        for (uint32_t idx = 0; idx < (1u << D); idx++) {          // issue all 2^D gathers before any use
-            uint32_t gl[D];
-#pragma unroll
-            for (uint32_t d = 0; d < D; d++) gl[d] = g[d] + ((idx >> d) & 1u);
-            corner[idx] = load_feat<C>(grid + (size_t)corner_row<D>(li, gl) * C);
-        }
+        for (uint32_t d = 0; d < D; d++) gl[d] = g[d] + ((idx >> d) & 1u);
+        corner[idx] = load_feat<C>(grid + (size_t)corner_row<D>(li, gl) * C);
     }
 #pragma unroll
     for (uint32_t c = 0; c < C; c++) out[c] = 0.f;
@@ -262,7 +219,7 @@ __global__ void __launch_bounds__(256) grid_forward_kernel(const float* __restri
                                                            const int* __restrict__ offsets, float* __restrict__ outputs,
                                                            uint32_t N, uint32_t L, float S, uint32_t H, float bound,
                                                            float* __restrict__ dy_dx, uint32_t gridtype, int align_corners,
-                                                           uint32_t interp, int out_layout, bool pair16) {
+                                                           uint32_t interp, int out_layout) {
     __shared__ LevelInfo info[kMaxLevels];
     if (threadIdx.x < L) fill_level_info<D>(info[threadIdx.x], threadIdx.x, offsets, S, H, gridtype, align_corners);
     __syncthreads();
@@ -276,7 +233,7 @@ __global__ void __launch_bounds__(256) grid_forward_kernel(const float* __restri
     for (uint32_t level = 0; level < L; level++) {
         float out[C], dd[D * C];
         if (inside) {
-            encode_level<D, C, DYDX>(u, info[level], table, align_corners, interp, pair16, out, dd);
+            encode_level<D, C, DYDX>(u, info[level], table, align_corners, interp, out, dd);
         } else {
 #pragma unroll
             for (uint32_t c = 0; c < C; c++) out[c] = 0.f;
@@ -520,14 +477,12 @@ static int launch_forward(const float* inputs, const float* table, const int* of
                           float S, uint32_t H, float bound, float* dy_dx, uint32_t gridtype, int align_corners, uint32_t interp,
                           int out_layout, cudaStream_t st) {
     const dim3 grid(ceil_div<uint32_t>(N, 256));
-    static const bool pair_env = !(getenv("SDFG_GRID_PAIR") && atoi(getenv("SDFG_GRID_PAIR")) == 0);
-    const bool pair16 = pair_env && C == 2 && (reinterpret_cast<uintptr_t>(table) & 15) == 0;   // 16-byte corner-pair loads
     if (dy_dx)
         grid_forward_kernel<D, C, true><<<grid, 256, 0, st>>>(inputs, table, offsets, outputs, N, L, S, H, bound, dy_dx, gridtype,
-                                                              align_corners, interp, out_layout, pair16);
+                                                              align_corners, interp, out_layout);
     else
         grid_forward_kernel<D, C, false><<<grid, 256, 0, st>>>(inputs, table, offsets, outputs, N, L, S, H, bound, nullptr,
-                                                               gridtype, align_corners, interp, out_layout, pair16);
+                                                               gridtype, align_corners, interp, out_layout);
     return check_launch("grid_forward_kernel");
 }
 
