@@ -187,85 +187,15 @@ __global__ void __launch_bounds__(256) upconv_gather_kernel(const uint16_t* __re
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// ToRGB: rgb[b, y, x, c] = sum_i x[b, y, x, i] * wrgb[b, c, i] + bias[c] (+ upsample(skip)[y, x, c]); wrgb = scale * W * style (no
-// demodulation).  skip [B, H/2, W/2, 3] fp32 is up-sampled by upfirdn2d(up = 2, kernel outer([1,3,3,1]) / 16, pad (2, 1)) on the fly:
-// out[Y, X] = sum_{p, q} k[p] k[q] U[Y + p - 2, X + q - 2], U[2y, 2x] = skip[y, x], zero elsewhere.
-// 8 threads per pixel (each a contiguous eighth of the channels, 16-byte loads), the sample's 3 x C weights in shared memory;
-// a block's 32 pixels belong to one sample.   out_nchw (fp32 [B, 3, H, W], the image) and / or out_nhwc (fp32 [B, H, W, 3], the next skip)
-// A thread owns 16 consecutive input channels (its 48 weights live in registers) and walks RGB_PIX / lanes pixels of one sample;
-// C / 16 adjacent threads (8 .. 32: a shuffle group) share a pixel.  Weights through L1 per pixel cost 8 tag look-ups per load.
-constexpr uint32_t RGB_PIX = 256;      // pixels per block, all of one sample
-__global__ void __launch_bounds__(256) to_rgb_kernel(const uint16_t* __restrict__ x, const float4* __restrict__ wrgb4, const float* __restrict__ bias,
-                                                      const float* __restrict__ skip, uint32_t B, uint32_t H, uint32_t W, uint32_t C,
-                                                      float* __restrict__ out_nhwc, float* __restrict__ out_nchw) {
-    const uint32_t tpp = C / 16;                                        // threads per pixel: 8, 16 or 32
-    const uint32_t part = threadIdx.x % tpp, lane_px = threadIdx.x / tpp, px_per_iter = 256 / tpp;
-    const uint32_t blocks_per_sample = (H * W + RGB_PIX - 1) / RGB_PIX;
-    const uint32_t b = blockIdx.x / blocks_per_sample, yx0 = (blockIdx.x % blocks_per_sample) * RGB_PIX;
-    float wr[16], wg[16], wb[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        const float4 w4 = __ldg(wrgb4 + (size_t)b * C + part * 16 + k);
-        wr[k] = w4.x; wg[k] = w4.y; wb[k] = w4.z;
-    }
-    const float bs = part < 3 ? __ldg(bias + part) : 0.f;
-    const uint16_t* xb = x + (size_t)b * H * W * C + part * 16;
-#pragma unroll 2
-    for (uint32_t it = 0; it < RGB_PIX; it += px_per_iter) {
-        const uint32_t yx = yx0 + it + lane_px;
-        const bool valid = yx < H * W;
-        const uint4* xr = reinterpret_cast<const uint4*>(xb + (size_t)(valid ? yx : 0) * C);
-        const uint4 u0 = __ldg(xr), u1 = __ldg(xr + 1);
-        const uint32_t hw[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-        float acc[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const float2 f = tc::unpack_f16(hw[k]);
-            acc[0] = fmaf(f.x, wr[2 * k], fmaf(f.y, wr[2 * k + 1], acc[0]));
-            acc[1] = fmaf(f.x, wg[2 * k], fmaf(f.y, wg[2 * k + 1], acc[1]));
-            acc[2] = fmaf(f.x, wb[2 * k], fmaf(f.y, wb[2 * k + 1], acc[2]));
-        }
-        for (uint32_t o = 1; o < tpp; o <<= 1) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-        }
-        if (valid && part < 3) {
-            const uint32_t Yo = yx / W, Xo = yx % W;
-            const uint64_t pix = (uint64_t)b * H * W + yx;
-            float v = (part == 0 ? acc[0] : part == 1 ? acc[1] : acc[2]) + bs;
-            if (skip) {
-                const uint32_t Hs = H / 2, Ws = W / 2;
-                const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};      // [1,3,3,1] / 8 * 2 per axis (kernel * factor^2 over both axes)
-                // U[2y, 2x] = skip[y, x]: of the 4 x 4 taps the two per axis with Y + p even contribute
-                float sacc = 0.f;
-#pragma unroll
-                for (int pi = 0; pi < 2; pi++) {
-                    const int p = (Yo & 1) + 2 * pi, r = ((int)Yo + p - 2) >> 1;
-                    if (r < 0 || r >= (int)Hs) continue;
-#pragma unroll
-                    for (int qi = 0; qi < 2; qi++) {
-                        const int q = (Xo & 1) + 2 * qi, c = ((int)Xo + q - 2) >> 1;
-                        if (c < 0 || c >= (int)Ws) continue;
-                        sacc = fmaf(k4[p] * k4[q], __ldg(skip + (((size_t)b * Hs + r) * Ws + c) * 3 + part), sacc);
-                    }
-                }
-                v += sacc;
-            }
-            if (out_nhwc) out_nhwc[pix * 3 + part] = v;
-            if (out_nchw) out_nchw[(((size_t)b * 3 + part) * H + Yo) * W + Xo] = v;
-        }
-    }
-}
-
-// wrgb4[b, i] = scale * style[b, i] * (W[0, i], W[1, i], W[2, i], 0)
-__global__ void __launch_bounds__(256) rgb_weight_kernel(const float* __restrict__ W, const float* __restrict__ style, float scale, uint32_t C,
-                                                          uint32_t B, float4* __restrict__ out) {
+// wrgb16[b * 8 + o, i] = fp16(scale * style[b, i] * W[o, i]) for o < 3, zero rows 3..7: the B operand of the ToRGB GEMM (8 rows per CTA)
+__global__ void __launch_bounds__(256) rgb_weight16_kernel(const float* __restrict__ W, const float* __restrict__ style, float scale, uint32_t C,
+                                                            uint32_t B, __half* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * C) return;
-    const uint32_t k = i % C;
+    const uint32_t b = i / C, k = i % C;
     const float sc = scale * __ldg(style + i);
-    out[i] = make_float4(sc * __ldg(W + k), sc * __ldg(W + C + k), sc * __ldg(W + 2 * C + k), 0.f);
+#pragma unroll
+    for (uint32_t o = 0; o < 8; o++) out[((size_t)b * 8 + o) * C + k] = __float2half_rn(o < 3 ? sc * __ldg(W + o * C + k) : 0.f);
 }
 
 }  // namespace sdfg
@@ -292,6 +222,32 @@ extern "C" int sdfg_modconv_fold(const float* weight, const float* style, float 
     return check_launch("modconv_fold_kernel");
 }
 
+// pixel tiling, unit split over the CTA pairs, tensor maps and launch of tc_conv_kernel; P carries B, H, W, Cin, taps, ncols, NT, epi and the epilogue pointers
+static int launch_conv(tc::ConvParams& P, const uint16_t* x, const uint16_t* wf, uint64_t w_rows, const char* name, cudaStream_t stream) {
+    P.bw = std::min(P.W, 128u); P.bh = 128 / P.bw;
+    P.tiles_x = P.W / P.bw; P.tiles_y = ceil_div<uint32_t>(P.H, P.bh);
+    P.pairs_per_sample = ceil_div<uint32_t>(P.tiles_x * P.tiles_y, 2);
+    P.n_nt = P.ncols / P.NT;
+    P.n_units = P.B * P.pairs_per_sample * P.n_nt;
+    const uint32_t pairs = std::max(1u, std::min<uint32_t>((uint32_t)sm_count() / 2, P.n_units));
+    P.units_per_pair = ceil_div<uint32_t>(P.n_units, pairs);
+    const uint32_t grid = 2 * ceil_div<uint32_t>(P.n_units, P.units_per_pair);
+    CUtensorMap tmA, tmB;
+    if (int e = make_tensor_map_16_4d(&tmA, x, P.B, P.H, P.W, P.Cin, P.bw, P.bh)) return e;
+    if (int e = make_tensor_map_16(&tmB, wf, w_rows, P.Cin, P.Cin, P.NT / 2, 64, tc::FMT_F16)) return e;
+    const uint32_t smem = tc::conv_smem_bytes(P.NT);
+    if (int e = optin_smem_conv((const void*)tc::tc_conv_kernel, smem)) return e;
+    ProfScope prof(name, stream);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::CV_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, tc::tc_conv_kernel, tmA, tmB, P) != cudaSuccess) { (void)check_launch(name); return SDFG_ERR_CUDA; }
+    return check_launch(name);
+}
+
 extern "C" int sdfg_conv_forward(const uint16_t* x, const uint16_t* wf, uint32_t B, uint32_t H, uint32_t W, uint32_t Cin, uint32_t Cout, uint32_t taps,
                                  int gemm_mode, const float* bias, const float* noise, const float* noise_w, uint16_t* out, void* stream) {
     if (B == 0) return SDFG_OK;
@@ -306,31 +262,10 @@ extern "C" int sdfg_conv_forward(const uint16_t* x, const uint16_t* wf, uint32_t
     P.ncols = gemm_mode ? taps * Cout : Cout;
     P.wrows_per_sample = taps * Cout;
     P.NT = (P.ncols % 256 == 0) ? 256 : 128;
-    P.bw = std::min(W, 128u); P.bh = 128 / P.bw;
-    P.tiles_x = W / P.bw; P.tiles_y = ceil_div<uint32_t>(H, P.bh);
-    P.pairs_per_sample = ceil_div<uint32_t>(P.tiles_x * P.tiles_y, 2);
-    P.n_nt = P.ncols / P.NT;
-    P.n_units = B * P.pairs_per_sample * P.n_nt;
-    const uint32_t pairs = std::max(1u, std::min<uint32_t>((uint32_t)sm_count() / 2, P.n_units));
-    P.units_per_pair = ceil_div<uint32_t>(P.n_units, pairs);
-    const uint32_t grid = 2 * ceil_div<uint32_t>(P.n_units, P.units_per_pair);
     P.epi = gemm_mode ? tc::EPI_RAW : tc::EPI_ACT;
     P.bias = bias; P.noise = noise; P.noise_w = noise_w; P.out = out; P.ld_out = P.ncols;
     SDFG_REQUIRE(gemm_mode || P.ncols <= 2304, SDFG_ERR_UNSUPPORTED, "conv_forward: too many output channels");      // bias table in shared memory
-    CUtensorMap tmA, tmB;
-    if (int e = make_tensor_map_16_4d(&tmA, x, B, H, W, Cin, P.bw, P.bh)) return e;
-    if (int e = make_tensor_map_16(&tmB, wf, (uint64_t)B * taps * Cout, Cin, Cin, P.NT / 2, 64, tc::FMT_F16)) return e;
-    const uint32_t smem = tc::conv_smem_bytes(P.NT);
-    if (int e = optin_smem_conv((const void*)tc::tc_conv_kernel, smem)) return e;
-    ProfScope prof("tc_conv_kernel<gemm>", (cudaStream_t)stream);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::CV_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, tc::tc_conv_kernel, tmA, tmB, P) != cudaSuccess) { (void)check_launch("tc_conv_kernel<gemm>"); return SDFG_ERR_CUDA; }
-    return check_launch("tc_conv_kernel<gemm>");
+    return launch_conv(P, x, wf, (uint64_t)B * taps * Cout, "tc_conv_kernel<gemm>", (cudaStream_t)stream);
 }
 
 extern "C" int sdfg_upconv_gather(const uint16_t* y, uint32_t B, uint32_t H, uint32_t W, uint32_t C, const float* bias, const float* noise,
@@ -346,11 +281,16 @@ extern "C" int sdfg_to_rgb(const uint16_t* x, const float* weight, const float* 
                            uint32_t B, uint32_t H, uint32_t W, uint32_t C, float* wrgb_scratch, float* out_nhwc, float* out_nchw, void* stream) {
     if (B == 0) return SDFG_OK;
     SDFG_REQUIRE(x && weight && style && bias && wrgb_scratch && (out_nhwc || out_nchw), SDFG_ERR_INVALID, "to_rgb: null pointer");
-    SDFG_REQUIRE(C == 128 || C == 256 || C == 512, SDFG_ERR_UNSUPPORTED, "to_rgb: 128, 256 or 512 channels (got %u)", C);
+    SDFG_REQUIRE(C % 64 == 0, SDFG_ERR_UNSUPPORTED, "to_rgb: channels must be a multiple of 64 (got %u)", C);
+    SDFG_REQUIRE(W >= 8 && (W & (W - 1)) == 0, SDFG_ERR_UNSUPPORTED, "to_rgb: width must be a power of two >= 8 (got %u)", W);
     cudaStream_t st = (cudaStream_t)stream;
-    rgb_weight_kernel<<<ceil_div<uint32_t>(B * C, 256), 256, 0, st>>>(weight, style, scale, C, B, reinterpret_cast<float4*>(wrgb_scratch));
-    if (int e = check_launch("rgb_weight_kernel")) return e;
-    to_rgb_kernel<<<B * ceil_div<uint32_t>(H * W, RGB_PIX), 256, 0, st>>>(x, reinterpret_cast<const float4*>(wrgb_scratch), bias, skip, B, H, W, C, out_nhwc,
-                                                                           out_nchw);
-    return check_launch("to_rgb_kernel");
+    // the scratch ([B, C, 4] floats = 16 B per sample and channel) holds the fp16 weight rows [B * 8, C]
+    rgb_weight16_kernel<<<ceil_div<uint32_t>(B * C, 256), 256, 0, st>>>(weight, style, scale, C, B, reinterpret_cast<__half*>(wrgb_scratch));
+    if (int e = check_launch("rgb_weight16_kernel")) return e;
+    tc::ConvParams P = {};
+    P.B = B; P.H = H; P.W = W; P.Cin = C;
+    P.taps = 1; P.ncols = 16; P.NT = 16; P.wrows_per_sample = 8;        // CTA 1's weight rows (8..15 of the tile) are the next sample's / out of range: columns never read
+    P.epi = tc::EPI_RGB;
+    P.bias = bias; P.skip = skip; P.out_nhwc = out_nhwc; P.out_nchw = out_nchw;
+    return launch_conv(P, x, reinterpret_cast<const uint16_t*>(wrgb_scratch), (uint64_t)B * 8, "tc_conv_kernel<rgb>", st);
 }

@@ -11,6 +11,10 @@
 //   and a gather kernel (conv.cu) adds the nine shifted taps, blurs and activates.
 //   epilogue (EPI_ACT):  v = acc + noise_w * noise[b, y, x] + bias[o];  v = leaky_relu(v, 0.2) * sqrt(2)  -> fp16   (NoiseInjection
 //   sdf_model.py:783-790 + FusedLeakyReLU sdf_op.py:83-117);  EPI_RAW: fp16 store of the accumulator.
+//   EPI_RGB (ToRGB, sdf_model.py:887-909): the 1 x 1 modulated convolution to 3 channels as a GEMM with NT = 16 (8 weight rows per CTA,
+//   3 of them real) -- the tensor pipe idles, the point is that the activation streams through TMA at the HBM rate instead of
+//   through 100 SIMT instructions per pixel and 16 channels; the epilogue adds the bias and the up-sampled skip image
+//   (upfirdn2d [1,3,3,1], up 2, pad (2,1): sdf_model.py:624-641) and writes fp32 NHWC (next skip) and / or NCHW (the image).
 //
 //   warp 0      TMA producer (both CTAs): own 128-pixel A box + own half (NT/2 rows) of the B box per K chunk, ring of NSTG stages
 //   warp 1      MMA issuer (leader CTA): tcgen05.mma.cta_group::2, M = 256 (2 x 128 pixels), N = NT, K = 16 per instruction
@@ -26,7 +30,7 @@ namespace tc {
 constexpr uint32_t CV_THREADS = 320;
 constexpr uint32_t CV_A_BYTES = 128 * 128;                  // [128 pixels x 64 channels] fp16
 constexpr uint32_t CV_NSTG = 5;
-enum ConvEpi : uint32_t { EPI_RAW = 0, EPI_ACT = 1 };
+enum ConvEpi : uint32_t { EPI_RAW = 0, EPI_ACT = 1, EPI_RGB = 2 };
 
 struct ConvParams {
     uint32_t B, H, W, Cin;
@@ -45,6 +49,9 @@ struct ConvParams {
     const float* noise_w;       // device scalar or NULL
     uint16_t* out;              // [B, H, W, ld_out]
     int64_t ld_out;
+    const float* skip;          // EPI_RGB: [B, H/2, W/2, 3] fp32 or NULL
+    float* out_nhwc;            // EPI_RGB: [B, H, W, 3] or NULL
+    float* out_nchw;            // EPI_RGB: [B, 3, H, W] or NULL
 };
 
 struct ConvSmem {
@@ -163,6 +170,44 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&S.tmem_full[wg], (local >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((q * 32) << 16) + wg * 256;
+            if (P.epi == EPI_RGB) {
+                uint32_t raw[16];
+                tmem_ld16(taddr, raw);
+                tmem_ld_wait16(raw);
+                if (valid) {
+                    float v[3];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) v[c] = __uint_as_float(raw[c]) + __ldg(P.bias + c);
+                    if (P.skip) {
+                        const uint32_t Hs = P.H / 2, Ws = P.W / 2;
+                        const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};      // [1,3,3,1] / 8 * 2 per axis
+                        // U[2y, 2x] = skip[y, x]: of the 4 x 4 taps the two per axis with Y + p even contribute
+#pragma unroll
+                        for (int pi = 0; pi < 2; pi++) {
+                            const int p = (int)(py & 1) + 2 * pi, rr = ((int)py + p - 2) >> 1;
+                            if (rr < 0 || rr >= (int)Hs) continue;
+#pragma unroll
+                            for (int qi = 0; qi < 2; qi++) {
+                                const int qq = (int)(px & 1) + 2 * qi, cc = ((int)px + qq - 2) >> 1;
+                                if (cc < 0 || cc >= (int)Ws) continue;
+                                const float* sp = P.skip + (((size_t)b * Hs + rr) * Ws + cc) * 3;
+                                const float kw = k4[p] * k4[qq];
+#pragma unroll
+                                for (int c = 0; c < 3; c++) v[c] = fmaf(kw, __ldg(sp + c), v[c]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        if (P.out_nhwc) P.out_nhwc[pix * 3 + c] = v[c];
+                        if (P.out_nchw) P.out_nchw[(((size_t)b * 3 + c) * P.H + py) * P.W + px] = v[c];
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (leader) mbar_arrive(&S.tmem_empty[wg]); else mbar_arrive_remote(&S.tmem_empty[wg], 0); }
+                continue;
+            }
             uint16_t* orow = P.out + pix * P.ld_out + nt * P.NT;
             for (uint32_t c = 0; c < P.NT; c += 32) {
                 uint32_t raw[32];
