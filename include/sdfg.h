@@ -281,19 +281,19 @@ int sdfg_nhwc16(const float* in, uint16_t* out, uint64_t n_elems, void* stream);
 int sdfg_modconv_fold(const float* weight, const float* style, float scale, uint32_t B, uint32_t Cin, uint32_t Cout, uint32_t taps,
                       int demodulate, float* demod_scratch, uint16_t* out, void* stream);
 
-/* gemm_mode 0: 3 x 3 (taps = 9) / 1 x 1 (taps = 1) convolution, stride 1, zero padding, on per-sample weights wf (sdfg_modconv_fold),
- *   fused with out = leaky_relu(conv + noise_w[0] * noise[b,y,x] + bias[o], 0.2) * sqrt(2) (NoiseInjection + FusedLeakyReLU);
- *   out [B, H, W, Cout].  noise [B, H, W] / noise_w (device scalar) / bias [Cout] may be NULL.
- * gemm_mode 1: the tap matrices side by side, out[b, pixel, tap * Cout + o] = sum_i x[b, pixel, i] * wf[b][tap][o][i]  (raw fp16):
- *   the transposed convolution of an up-sampling StyledConv before sdfg_upconv_gather.  out [B, H, W, taps * Cout].
- * Cin % 64 == 0, Cout % 128 == 0, W a power of two >= 8. */
+/* 3 x 3 (taps = 9) / 1 x 1 (taps = 1) convolution, stride 1, zero padding, on per-sample weights wf [B, taps, Cout, Cin] (sdfg_modconv_fold),
+ * fused with out = leaky_relu(conv + noise_w[0] * noise[b,y,x] + bias[o], 0.2) * sqrt(2) (NoiseInjection + FusedLeakyReLU);
+ * out [B, H, W, Cout].  noise [B, H, W] / noise_w (device scalar) / bias [Cout] may be NULL.  Cin % 64 == 0, Cout % 128 == 0, W a power of two >= 8.
+ * ref ModulatedConv2d.forward :685-704 + StyledConv.forward :812-816. */
 int sdfg_conv_forward(const uint16_t* x, const uint16_t* wf, uint32_t B, uint32_t H, uint32_t W, uint32_t Cin, uint32_t Cout, uint32_t taps,
-                      int gemm_mode, const float* bias, const float* noise, const float* noise_w, uint16_t* out, void* stream);
+                      const float* bias, const float* noise, const float* noise_w, uint16_t* out, void* stream);
 
-/* y [B, H, W, 9 * C] (gemm_mode output) -> out [B, 2H, 2W, C]: conv_transpose2d(stride 2) tap sum, Blur(outer([1,3,3,1]) / 16, pad (1,1)),
- * + noise_w[0] * noise[b, Y, X] + bias[o], leaky_relu(0.2) * sqrt(2).  ref ModulatedConv2d.forward :671-684 + StyledConv.forward :812-816. */
-int sdfg_upconv_gather(const uint16_t* y, uint32_t B, uint32_t H, uint32_t W, uint32_t C, const float* bias, const float* noise,
-                       const float* noise_w, uint16_t* out, void* stream);
+/* up-sampling StyledConv: conv_transpose2d(x, wf, stride 2) -> Blur(outer([1,3,3,1]) / 16 * 4, pad (1,1)) -> + noise_w[0] * noise[b, Y, X] + bias[o]
+ * -> leaky_relu(0.2) * sqrt(2).  x [B, H, W, Cin], wf [B, 9, Cout, Cin] (sdfg_modconv_fold), out [B, 2H, 2W, Cout],
+ * t_scratch [B, 2H + 1, 2W + 1, Cout] fp16 (the transposed convolution before the blur).  noise [B, 2H, 2W].  Same shape limits as
+ * sdfg_conv_forward.  ref ModulatedConv2d.forward :671-684 + StyledConv.forward :812-816. */
+int sdfg_upconv_forward(const uint16_t* x, const uint16_t* wf, uint32_t B, uint32_t H, uint32_t W, uint32_t Cin, uint32_t Cout, uint16_t* t_scratch,
+                        const float* bias, const float* noise, const float* noise_w, uint16_t* out, void* stream);
 
 /* ToRGB (:821-843): 1 x 1 modulated convolution without demodulation to 3 channels + bias [3] + (skip != NULL) the previous level's
  * rgb [B, H/2, W/2, 3] up-sampled by Upsample (upfirdn2d up = 2, outer([1,3,3,1]) / 16, pad (2, 1)).  weight [3, C], style [B, C],

@@ -33,8 +33,6 @@ for (H, Cin, Cout) in ((64, 256, 512), (128, 256, 256), (256, 128, 128)):
 for (H, Cin, Cout) in ((64, 512, 256), (128, 256, 128)):
     x = torch.randn(B, H, H, Cin, device=dev).half()
     wf = torch.randn(B, 9, Cout, Cin, device=dev).half() * 0.02
-    t = timed(lambda: ops.conv_forward(x, wf, gemm_mode=True))
-    y = ops.conv_forward(x, wf, gemm_mode=True)
-    tg = timed(lambda: ops.upconv_gather(y, Cout))
+    t = timed(lambda: ops.upconv_forward(x, wf))
     fl = 2 * 9 * B * H * H * Cin * Cout
-    print("upconv H=%d %d->%d: gemm %.3f ms = %.0f TFLOP/s, gather %.3f ms (%.2f GB in + %.2f GB out)" % (H, Cin, Cout, t, fl / t / 1e9, tg, y.numel() * 2 / 1e9, B * 4 * H * H * Cout * 2 / 1e9))
+    print("upconv H=%d %d->%d: %.3f ms (transposed convolution + blur; %.2f TFLOP, T %.2f GB, out %.2f GB)" % (H, Cin, Cout, t, fl / 1e12, B * (2 * H + 1) ** 2 * Cout * 2 / 1e9, B * 4 * H * H * Cout * 2 / 1e9))

@@ -71,8 +71,8 @@ PROTOTYPES = {
     "sdfg_composite_forward_h": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "sdfg_nhwc16": (i32, [vp, vp, u64, vp]),
     "sdfg_modconv_fold": (i32, [vp, vp, f32, u32, u32, u32, u32, i32, vp, vp, vp]),
-    "sdfg_conv_forward": (i32, [vp, vp, u32, u32, u32, u32, u32, u32, i32, vp, vp, vp, vp, vp]),
-    "sdfg_upconv_gather": (i32, [vp, u32, u32, u32, u32, vp, vp, vp, vp, vp]),
+    "sdfg_conv_forward": (i32, [vp, vp, u32, u32, u32, u32, u32, u32, vp, vp, vp, vp, vp]),
+    "sdfg_upconv_forward": (i32, [vp, vp, u32, u32, u32, u32, u32, vp, vp, vp, vp, vp, vp]),
     "sdfg_to_rgb": (i32, [vp, vp, vp, f32, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp]),
     "sdfg_align_volume": (i32, [vp, vp, u32, u32, u32, u32, u32, f32, f32, vp]),
     "sdfg_composite_backward": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp,

@@ -1,9 +1,9 @@
 // StyleGAN2 decoder (ref sdf_model.py:614-1056 + sdf_op.py) -- forward kernels behind the C ABI (include/sdfg.h):
 //   sdfg_nhwc16                 fp32 [B, H*W, C] (the renderer's feature map, channels last) -> fp16 [B, H, W, C]
 //   sdfg_modconv_fold           per-sample weights of a ModulatedConv2d: scale * W * style, demodulated           (:655-669)
-//   sdfg_conv_forward           3 x 3 convolution / plain GEMM on tcgen05 (tc_conv.cuh) + noise + bias + leaky ReLU (:790-818)
-//   sdfg_upconv_gather          transposed-convolution taps -> blur -> noise + bias + leaky ReLU                 (:671-684, Blur :522-538)
-//   sdfg_to_rgb                 1 x 1 modulated convolution to 3 channels + bias + up-sampled skip               (:821-843, Upsample :480-499)
+//   sdfg_conv_forward           3 x 3 / 1 x 1 convolution on tcgen05 (tc_conv.cuh) + noise + bias + leaky ReLU           (:790-818)
+//   sdfg_upconv_forward         transposed convolution (four parity classes on tcgen05) -> blur -> noise + bias + leaky ReLU (:671-684, Blur :522-538)
+//   sdfg_to_rgb                 1 x 1 modulated convolution to 3 channels (tcgen05, N = 16) + bias + up-sampled skip     (:821-843, Upsample :480-499)
 // Activations are channels-last fp16; every kernel takes a stream; nothing allocates.
 #include <algorithm>
 #include <memory>
@@ -71,114 +71,71 @@ __global__ void __launch_bounds__(256) modconv_fold_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Up-sampling StyledConv, second half.  Y[b, (y, x), tap * C + o] holds the nine tap products of the transposed convolution
-// (conv_transpose2d, stride 2: T[2y + a, 2x + b'] += Y[(y, x), (a, b')], T is (2H + 1)^2).  out = lrelu(blur(T) + noise + bias) * sqrt(2)
-// with blur = upfirdn2d(T, outer([1,3,3,1]) / 16, pad (1, 1)):  out[Y, X] = sum_{p, q < 4} k[p] k[q] T[Y + p - 1, X + q - 1].
-// Block: 16 x 16 output pixels x 64 channels.  The 19 x 19 patch of T is assembled in shared memory as fp16 (<= 4 reads of Y per
-// element, 16-byte loads: a thread owns 8 channels), then every thread blurs its pixels from shared memory and writes 16 bytes.
-// HBM: Y is read ~1.4x (patch halo), the output written once.
+// Up-sampling StyledConv, second half: out = lrelu(blur(T) + noise + bias) * sqrt(2), T [B, 2H + 1, 2W + 1, C] fp16 = the transposed
+// convolution written by tc_conv_kernel, blur = upfirdn2d(T, outer([1,3,3,1]) / 16 * 4, pad (1, 1)):
+//     out[Y, X] = sum_{p, q < 4} k[p] k[q] T[Y + p - 1, X + q - 1]           (ref Blur :522-531 after conv_transpose2d :671-684)
+// Block: 16 x 16 output pixels x 64 channels.  The 19 x 19 patch of T goes to shared memory with 16-byte loads (a thread owns 8
+// channels); the blur is separable: a thread owns a column of 8 output pixels, forms the horizontal 4-tap sums of the 11 patch rows it
+// needs once and combines them vertically -- 8.5 instead of 16 taps per output.  HBM: T is read ~1.4x (halo, mostly L2 hits), the
+// output written once.
 constexpr int UG_T = 16, UG_P = UG_T + 3;
-__global__ void __launch_bounds__(256) upconv_gather_kernel(const uint16_t* __restrict__ Y, uint32_t B, uint32_t H, uint32_t W, uint32_t C,
-                                                             const float* __restrict__ bias, const float* __restrict__ noise,
-                                                             const float* __restrict__ noise_w, uint16_t* __restrict__ out) {
-    __shared__ uint4 T[UG_P * UG_P][8];                                // [position][8 channel groups of 8 fp16]
+__global__ void __launch_bounds__(256) upconv_blur_kernel(const uint16_t* __restrict__ T, uint32_t B, uint32_t H, uint32_t W, uint32_t C,
+                                                           const float* __restrict__ bias, const float* __restrict__ noise,
+                                                           const float* __restrict__ noise_w, uint16_t* __restrict__ out) {
+    __shared__ uint4 P[UG_P * UG_P][8];                                // [position][8 channel groups of 8 fp16]
     const uint32_t cg = threadIdx.x & 7, slot = threadIdx.x >> 3;       // 8 threads per position / pixel, 32 positions per pass
-    const uint32_t Ho = 2 * H, Wo = 2 * W;
+    const uint32_t Ho = 2 * H, Wo = 2 * W, Ht = Ho + 1, Wt = Wo + 1;
     const uint32_t c0 = blockIdx.y * 64 + cg * 8;
     const uint32_t tiles_x = (Wo + UG_T - 1) / UG_T, tiles_y = (Ho + UG_T - 1) / UG_T;
     const uint32_t b = blockIdx.x / (tiles_x * tiles_y), t = blockIdx.x % (tiles_x * tiles_y);
     const int Y0 = (int)(t / tiles_x) * UG_T, X0 = (int)(t % tiles_x) * UG_T;
-    const size_t ldy = (size_t)9 * C;
-    const uint16_t* Yb = Y + (size_t)b * H * W * ldy + c0;
-    // Positions of the patch by parity class: tile origins are multiples of 16, so patch row tr is T row Y0 + tr - 1 -- ODD for even tr.
-    // An odd T row receives tap a = 1 only, an even one taps a = 0 and 2 (likewise for columns): 1, 2, 2 or 4 reads of Y per position.
-    // One loop per class keeps the bodies branch-free, so the loads of several positions are in flight together.
-    auto ld8 = [&](int y, int x, int tap, float (&acc)[8]) {
-        const bool ok = y >= 0 && x >= 0 && y < (int)H && x < (int)W;
-        const uint4 v = ok ? __ldg(reinterpret_cast<const uint4*>(Yb + ((size_t)y * W + x) * ldy + (size_t)tap * C)) : make_uint4(0, 0, 0, 0);
-        const uint32_t hw[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const float2 f = tc::unpack_f16(hw[k]);
-            acc[2 * k] += f.x; acc[2 * k + 1] += f.y;
-        }
-    };
-    auto put = [&](int tr, int tcn, const float (&acc)[8]) {
-        T[tr * UG_P + tcn][cg] = make_uint4(tc::pack_f16_sat(acc[0], acc[1]), tc::pack_f16_sat(acc[2], acc[3]), tc::pack_f16_sat(acc[4], acc[5]), tc::pack_f16_sat(acc[6], acc[7]));
-    };
-    constexpr int NE = (UG_P + 1) / 2, NO = UG_P / 2;                  // even / odd patch indices: 10 / 9
-    // (even tr, even tc): T row and column odd -> tap (1, 1)
-#pragma unroll 2
-    for (int e = slot; e < NE * NE; e += 32) {
-        const int tr = 2 * (e / NE), tcn = 2 * (e % NE);
-        const int r = Y0 + tr - 1, c = X0 + tcn - 1;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        ld8((r - 1) >> 1, (c - 1) >> 1, 4, acc);
-        put(tr, tcn, acc);
-    }
-    // (even tr, odd tc): row odd (a = 1), column even (b' = 0, 2)
-#pragma unroll 2
-    for (int e = slot; e < NE * NO; e += 32) {
-        const int tr = 2 * (e / NO), tcn = 2 * (e % NO) + 1;
-        const int r = Y0 + tr - 1, c = X0 + tcn - 1;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        ld8((r - 1) >> 1, c >> 1, 3, acc);
-        ld8((r - 1) >> 1, (c >> 1) - 1, 5, acc);
-        put(tr, tcn, acc);
-    }
-    // (odd tr, even tc): row even (a = 0, 2), column odd (b' = 1)
-#pragma unroll 2
-    for (int e = slot; e < NO * NE; e += 32) {
-        const int tr = 2 * (e / NE) + 1, tcn = 2 * (e % NE);
-        const int r = Y0 + tr - 1, c = X0 + tcn - 1;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        ld8(r >> 1, (c - 1) >> 1, 1, acc);
-        ld8((r >> 1) - 1, (c - 1) >> 1, 7, acc);
-        put(tr, tcn, acc);
-    }
-    // (odd tr, odd tc): both even -> four taps
-#pragma unroll 2
-    for (int e = slot; e < NO * NO; e += 32) {
-        const int tr = 2 * (e / NO) + 1, tcn = 2 * (e % NO) + 1;
-        const int r = Y0 + tr - 1, c = X0 + tcn - 1;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        ld8(r >> 1, c >> 1, 0, acc);
-        ld8(r >> 1, (c >> 1) - 1, 2, acc);
-        ld8((r >> 1) - 1, c >> 1, 6, acc);
-        ld8((r >> 1) - 1, (c >> 1) - 1, 8, acc);
-        put(tr, tcn, acc);
+    const uint16_t* Tb = T + (size_t)b * Ht * Wt * C + c0;
+#pragma unroll 4
+    for (int e = slot; e < UG_P * UG_P; e += 32) {
+        const int r = Y0 + e / UG_P - 1, c = X0 + e % UG_P - 1;
+        const bool ok = r >= 0 && c >= 0 && r < (int)Ht && c < (int)Wt;
+        P[e][cg] = ok ? __ldg(reinterpret_cast<const uint4*>(Tb + ((size_t)r * Wt + c) * C)) : make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
     const float nw = (noise && noise_w) ? __ldg(noise_w) : 0.f;
     float bs[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) bs[k] = bias ? __ldg(bias + c0 + k) : 0.f;
-    const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};                  // [1,3,3,1] / 4 per axis: make_kernel (outer / 64) * upsample_factor^2 (Blur :522-531)
-    for (int e = slot; e < UG_T * UG_T; e += 32) {
-        const int oy = e / UG_T, ox = e % UG_T;
-        const int Yo = Y0 + oy, Xo = X0 + ox;
-        if (Yo >= (int)Ho || Xo >= (int)Wo) continue;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};                  // [1,3,3,1] / 4 per axis: make_kernel (outer / 64) * upsample_factor^2
+    const int ox = slot & 15, oy0 = (slot >> 4) * 8;                    // this thread: output column ox, rows oy0 .. oy0 + 7
+    const int Xo = X0 + ox;
+    float hs[4][8];                                                     // sliding window of horizontal sums (patch rows oy + 0 .. 3)
+    auto hsum = [&](int pr, float (&h)[8]) {
 #pragma unroll
-        for (int p = 0; p < 4; p++) {
+        for (int k = 0; k < 8; k++) h[k] = 0.f;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const uint4 v = T[(oy + p) * UG_P + ox + q][cg];
-                const uint32_t hw[4] = {v.x, v.y, v.z, v.w};
-                const float kk = k4[p] * k4[q];
+        for (int q = 0; q < 4; q++) {
+            const uint4 v = P[pr * UG_P + ox + q][cg];
+            const uint32_t hw[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const float2 f = tc::unpack_f16(hw[k]);
-                    acc[2 * k] = fmaf(kk, f.x, acc[2 * k]); acc[2 * k + 1] = fmaf(kk, f.y, acc[2 * k + 1]);
-                }
+            for (int k = 0; k < 4; k++) {
+                const float2 f = tc::unpack_f16(hw[k]);
+                h[2 * k] = fmaf(k4[q], f.x, h[2 * k]); h[2 * k + 1] = fmaf(k4[q], f.y, h[2 * k + 1]);
             }
         }
+    };
+    hsum(oy0, hs[0]); hsum(oy0 + 1, hs[1]); hsum(oy0 + 2, hs[2]);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        hsum(oy0 + j + 3, hs[(j + 3) & 3]);
+        const int Yo = Y0 + oy0 + j;
+        if (Yo >= (int)Ho || Xo >= (int)Wo) continue;
         const size_t pix = ((size_t)b * Ho + Yo) * Wo + Xo;
         const float nz = nw != 0.f ? nw * __ldg(noise + pix) : 0.f;
         uint32_t h[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            float v0 = acc[2 * k] + bs[2 * k] + nz, v1 = acc[2 * k + 1] + bs[2 * k + 1] + nz;
+            float v0 = bs[2 * k] + nz, v1 = bs[2 * k + 1] + nz;
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                v0 = fmaf(k4[p], hs[(j + p) & 3][2 * k], v0);
+                v1 = fmaf(k4[p], hs[(j + p) & 3][2 * k + 1], v1);
+            }
             v0 = (v0 > 0.f ? v0 : 0.2f * v0) * 1.4142135623730951f;
             v1 = (v1 > 0.f ? v1 : 0.2f * v1) * 1.4142135623730951f;
             h[k] = tc::pack_f16_sat(v0, v1);
@@ -222,13 +179,13 @@ extern "C" int sdfg_modconv_fold(const float* weight, const float* style, float 
     return check_launch("modconv_fold_kernel");
 }
 
-// pixel tiling, unit split over the CTA pairs, tensor maps and launch of tc_conv_kernel; P carries B, H, W, Cin, taps, ncols, NT, epi and the epilogue pointers
+// unit split over the CTA pairs, tensor maps and launch of tc_conv_kernel; P carries the shapes, the tap classes, the pixel tile (bw x bh;
+// tiles_x/y default to covering H x W), NT, epi and the epilogue pointers
 static int launch_conv(tc::ConvParams& P, const uint16_t* x, const uint16_t* wf, uint64_t w_rows, const char* name, cudaStream_t stream) {
-    P.bw = std::min(P.W, 128u); P.bh = 128 / P.bw;
-    P.tiles_x = P.W / P.bw; P.tiles_y = ceil_div<uint32_t>(P.H, P.bh);
+    if (P.tiles_x == 0) { P.tiles_x = P.W / P.bw; P.tiles_y = ceil_div<uint32_t>(P.H, P.bh); }
     P.pairs_per_sample = ceil_div<uint32_t>(P.tiles_x * P.tiles_y, 2);
     P.n_nt = P.ncols / P.NT;
-    P.n_units = P.B * P.pairs_per_sample * P.n_nt;
+    P.n_units = P.B * P.pairs_per_sample * P.n_cls * P.n_nt;
     const uint32_t pairs = std::max(1u, std::min<uint32_t>((uint32_t)sm_count() / 2, P.n_units));
     P.units_per_pair = ceil_div<uint32_t>(P.n_units, pairs);
     const uint32_t grid = 2 * ceil_div<uint32_t>(P.n_units, P.units_per_pair);
@@ -248,33 +205,80 @@ static int launch_conv(tc::ConvParams& P, const uint16_t* x, const uint16_t* wf,
     return check_launch(name);
 }
 
+// tap table of a 3 x 3 (stride 1, zero padding 1) or 1 x 1 convolution
+static void plain_conv_class(tc::ConvClass& K, uint32_t taps) {
+    K.n_taps = taps; K.oy = 0; K.ox = 0;
+    for (uint32_t t = 0; t < taps; t++) {
+        K.dy[t] = taps == 9 ? (int8_t)((int)(t / 3) - 1) : 0;
+        K.dx[t] = taps == 9 ? (int8_t)((int)(t % 3) - 1) : 0;
+        K.wtap[t] = (uint8_t)t;
+    }
+}
+
 extern "C" int sdfg_conv_forward(const uint16_t* x, const uint16_t* wf, uint32_t B, uint32_t H, uint32_t W, uint32_t Cin, uint32_t Cout, uint32_t taps,
-                                 int gemm_mode, const float* bias, const float* noise, const float* noise_w, uint16_t* out, void* stream) {
+                                 const float* bias, const float* noise, const float* noise_w, uint16_t* out, void* stream) {
     if (B == 0) return SDFG_OK;
     SDFG_REQUIRE(x && wf && out, SDFG_ERR_INVALID, "conv_forward: null pointer");
     SDFG_REQUIRE(Cin % 64 == 0 && Cout % 128 == 0, SDFG_ERR_UNSUPPORTED, "conv_forward: Cin must be a multiple of 64 and Cout of 128 (got %u, %u)", Cin, Cout);
     SDFG_REQUIRE(taps == 9 || taps == 1, SDFG_ERR_UNSUPPORTED, "conv_forward: 3 x 3 (taps = 9) or 1 x 1 (taps = 1) only");
     SDFG_REQUIRE(W >= 8 && (W & (W - 1)) == 0, SDFG_ERR_UNSUPPORTED, "conv_forward: width must be a power of two >= 8 (got %u)", W);
+    SDFG_REQUIRE(Cout <= 2304, SDFG_ERR_UNSUPPORTED, "conv_forward: too many output channels");      // bias table in shared memory
     tc::ConvParams P = {};
     P.B = B; P.H = H; P.W = W; P.Cin = Cin;
-    // gemm_mode: the nine tap matrices are NOT summed over shifted inputs but laid side by side as 9 * Cout output columns
-    P.taps = gemm_mode ? 1 : taps;
-    P.ncols = gemm_mode ? taps * Cout : Cout;
-    P.wrows_per_sample = taps * Cout;
-    P.NT = (P.ncols % 256 == 0) ? 256 : 128;
-    P.epi = gemm_mode ? tc::EPI_RAW : tc::EPI_ACT;
-    P.bias = bias; P.noise = noise; P.noise_w = noise_w; P.out = out; P.ld_out = P.ncols;
-    SDFG_REQUIRE(gemm_mode || P.ncols <= 2304, SDFG_ERR_UNSUPPORTED, "conv_forward: too many output channels");      // bias table in shared memory
-    return launch_conv(P, x, wf, (uint64_t)B * taps * Cout, "tc_conv_kernel<gemm>", (cudaStream_t)stream);
+    P.n_cls = 1; plain_conv_class(P.cls[0], taps);
+    P.y_end = H; P.x_end = W; P.sy = P.sx = 1; P.out_h = H; P.out_w = W;
+    P.ncols = Cout; P.wrows_per_sample = taps * Cout;
+    P.NT = (Cout % 256 == 0) ? 256 : 128;
+    P.epi = tc::EPI_ACT;
+    P.bias = bias; P.noise = noise; P.noise_w = noise_w; P.out = out; P.ld_out = Cout;
+    P.bw = std::min(W, 128u); P.bh = 128 / P.bw;
+    return launch_conv(P, x, wf, (uint64_t)B * taps * Cout, "tc_conv_kernel<conv>", (cudaStream_t)stream);
 }
 
-extern "C" int sdfg_upconv_gather(const uint16_t* y, uint32_t B, uint32_t H, uint32_t W, uint32_t C, const float* bias, const float* noise,
-                                  const float* noise_w, uint16_t* out, void* stream) {
+extern "C" int sdfg_upconv_forward(const uint16_t* x, const uint16_t* wf, uint32_t B, uint32_t H, uint32_t W, uint32_t Cin, uint32_t Cout,
+                                   uint16_t* t_scratch, const float* bias, const float* noise, const float* noise_w, uint16_t* out, void* stream) {
     if (B == 0) return SDFG_OK;
-    SDFG_REQUIRE(y && out && C % 64 == 0, SDFG_ERR_INVALID, "upconv_gather: null pointer or channels not a multiple of 64");
+    SDFG_REQUIRE(x && wf && t_scratch && out, SDFG_ERR_INVALID, "upconv_forward: null pointer");
+    SDFG_REQUIRE(Cin % 64 == 0 && Cout % 128 == 0, SDFG_ERR_UNSUPPORTED, "upconv_forward: Cin must be a multiple of 64 and Cout of 128 (got %u, %u)", Cin, Cout);
+    SDFG_REQUIRE(W >= 8 && (W & (W - 1)) == 0, SDFG_ERR_UNSUPPORTED, "upconv_forward: width must be a power of two >= 8 (got %u)", W);
+    cudaStream_t st = (cudaStream_t)stream;
+    tc::ConvParams P = {};
+    P.B = B; P.H = H; P.W = W; P.Cin = Cin;
+    P.sy = P.sx = 2; P.out_h = 2 * H + 1; P.out_w = 2 * W + 1;
+    P.ncols = Cout; P.wrows_per_sample = 9 * Cout;
+    P.NT = (Cout % 256 == 0) ? 256 : 128;
+    P.epi = tc::EPI_RAW;
+    P.out = t_scratch; P.ld_out = Cout;
+    // class (cy, cx): T[2y' + cy, 2x' + cx] = sum over taps a = cy (mod 2), b' = cx (mod 2) of in[y' - (a - cy) / 2, x' - (b' - cx) / 2] * W[a, b']
+    auto fill = [&](tc::ConvClass& K, int cy, int cx) {
+        K.n_taps = 0; K.oy = cy; K.ox = cx;
+        for (int a = cy; a < 3; a += 2)
+            for (int bb = cx; bb < 3; bb += 2) {
+                K.dy[K.n_taps] = (int8_t)(-(a - cy) / 2); K.dx[K.n_taps] = (int8_t)(-(bb - cx) / 2);
+                K.wtap[K.n_taps] = (uint8_t)(a * 3 + bb);
+                K.n_taps++;
+            }
+    };
+    // interior: y' < H, x' < W, all four classes
+    P.n_cls = 4;
+    fill(P.cls[0], 0, 0); fill(P.cls[1], 0, 1); fill(P.cls[2], 1, 0); fill(P.cls[3], 1, 1);
+    P.y_org = P.x_org = 0; P.y_end = H; P.x_end = W;
+    P.bw = std::min(W, 128u); P.bh = 128 / P.bw; P.tiles_x = W / P.bw; P.tiles_y = ceil_div<uint32_t>(H, P.bh);
+    if (int e = launch_conv(P, x, wf, (uint64_t)B * 9 * Cout, "tc_conv_kernel<upconv>", st)) return e;
+    // bottom strip: y' = H (output row 2H), x' < W, the classes with cy = 0
+    P.n_cls = 2;
+    fill(P.cls[0], 0, 0); fill(P.cls[1], 0, 1);
+    P.y_org = H; P.y_end = H + 1; P.x_org = 0; P.x_end = W;
+    P.tiles_x = W / P.bw; P.tiles_y = 1;
+    if (int e = launch_conv(P, x, wf, (uint64_t)B * 9 * Cout, "tc_conv_kernel<upconv edge>", st)) return e;
+    // right strip: x' = W (output column 2W), y' <= H, the classes with cx = 0 (the odd row 2H + 1 of class (1, 0) falls outside T)
+    fill(P.cls[0], 0, 0); fill(P.cls[1], 1, 0);
+    P.x_org = W; P.x_end = W + 1; P.y_org = 0; P.y_end = H + 1;
+    P.bw = 8; P.bh = 16; P.tiles_x = 1; P.tiles_y = ceil_div<uint32_t>(H + 1, 16);
+    if (int e = launch_conv(P, x, wf, (uint64_t)B * 9 * Cout, "tc_conv_kernel<upconv edge>", st)) return e;
     const uint32_t tiles = ceil_div<uint32_t>(2 * W, UG_T) * ceil_div<uint32_t>(2 * H, UG_T);
-    upconv_gather_kernel<<<dim3(B * tiles, C / 64), 256, 0, (cudaStream_t)stream>>>(y, B, H, W, C, bias, noise, noise_w, out);
-    return check_launch("upconv_gather_kernel");
+    upconv_blur_kernel<<<dim3(B * tiles, Cout / 64), 256, 0, st>>>(t_scratch, B, H, W, Cout, bias, noise, noise_w, out);
+    return check_launch("upconv_blur_kernel");
 }
 
 extern "C" int sdfg_to_rgb(const uint16_t* x, const float* weight, const float* style, float scale, const float* bias, const float* skip,
@@ -289,7 +293,10 @@ extern "C" int sdfg_to_rgb(const uint16_t* x, const float* weight, const float* 
     if (int e = check_launch("rgb_weight16_kernel")) return e;
     tc::ConvParams P = {};
     P.B = B; P.H = H; P.W = W; P.Cin = C;
-    P.taps = 1; P.ncols = 16; P.NT = 16; P.wrows_per_sample = 8;        // CTA 1's weight rows (8..15 of the tile) are the next sample's / out of range: columns never read
+    P.n_cls = 1; plain_conv_class(P.cls[0], 1);
+    P.y_end = H; P.x_end = W; P.sy = P.sx = 1; P.out_h = H; P.out_w = W;
+    P.bw = std::min(W, 128u); P.bh = 128 / P.bw;
+    P.ncols = 16; P.NT = 16; P.wrows_per_sample = 8;        // CTA 1's weight rows (8..15 of the tile) are the next sample's / out of range: columns never read
     P.epi = tc::EPI_RGB;
     P.bias = bias; P.skip = skip; P.out_nhwc = out_nhwc; P.out_nchw = out_nchw;
     return launch_conv(P, x, reinterpret_cast<const uint16_t*>(wrgb_scratch), (uint64_t)B * 8, "tc_conv_kernel<rgb>", st);

@@ -6,9 +6,12 @@
 //   the TMA unit, which is the convolution's zero padding; no im2col buffer exists.  Wf are per-SAMPLE weights with the style
 //   modulation and the demodulation folded in (ref ModulatedConv2d.forward sdf_model.py:655-704 builds the same per-sample
 //   weights and runs a grouped convolution), [B * taps * Cout, Cin] fp16, streamed as [NT/2 x 64] boxes per CTA.
-//   taps = 1 is a plain GEMM over Ncols columns: the transposed convolution of the up-sampling layers runs as
-//       Y[b, pixel, (tap, o)] = sum_i in[b, pixel, i] * Wf[b][tap][o][i]                                (Ncols = 9 * Cout)
-//   and a gather kernel (conv.cu) adds the nine shifted taps, blurs and activates.
+//   The transposed convolution of the up-sampling layers (conv_transpose2d, stride 2: T[2y + a, 2x + b'] += in[y, x] * W[a, b'], T is
+//   (2H + 1)^2) runs as its four output-parity CLASSES: T[2y' + cy, 2x' + cx] is an ordinary convolution of the low-resolution input with
+//   the taps a = cy (mod 2), b' = cx (mod 2) -- 4, 2, 2 and 1 taps, shifts 0 / -1 -- i.e. the same implicit GEMM with a per-class tap
+//   table and a stride-2 store.  The same 9 * Cin * Cout MACs per input pixel as the tap-by-tap product, but no 9 * Cout-wide
+//   intermediate: T is written once (fp16) and the blur kernel (conv.cu) reads it once.  Row 2H / column 2W of T (y' = H, x' = W) are
+//   two thin extra launches of the same kernel over a one-tile-wide pixel grid.
 //   epilogue (EPI_ACT):  v = acc + noise_w * noise[b, y, x] + bias[o];  v = leaky_relu(v, 0.2) * sqrt(2)  -> fp16   (NoiseInjection
 //   sdf_model.py:783-790 + FusedLeakyReLU sdf_op.py:83-117);  EPI_RAW: fp16 store of the accumulator.
 //   EPI_RGB (ToRGB, sdf_model.py:887-909): the 1 x 1 modulated convolution to 3 channels as a GEMM with NT = 16 (8 weight rows per CTA,
@@ -32,18 +35,30 @@ constexpr uint32_t CV_A_BYTES = 128 * 128;                  // [128 pixels x 64 
 constexpr uint32_t CV_NSTG = 5;
 enum ConvEpi : uint32_t { EPI_RAW = 0, EPI_ACT = 1, EPI_RGB = 2 };
 
+struct ConvClass {
+    uint32_t n_taps;            // K steps of this class = n_taps * Cin / 64
+    int32_t oy, ox;             // output pixel = (sy * y + oy, sx * x + ox)
+    int8_t dy[9], dx[9];        // input shift of each tap
+    uint8_t wtap[9];            // which of the sample's tap matrices [tap][Cout][Cin] it multiplies with
+};
+
 struct ConvParams {
-    uint32_t B, H, W, Cin;
-    uint32_t taps;              // 9: 3 x 3 convolution; 1: plain GEMM
-    uint32_t ncols;             // output columns: Cout (convolution) or taps' * Cout (GEMM mode)
-    uint32_t NT;                // N tile: 128 or 256 (divides ncols)
+    uint32_t B, H, W, Cin;      // input activation [B, H, W, Cin]
+    uint32_t n_cls;             // 1, or the output-parity classes of a transposed convolution
+    ConvClass cls[4];
+    uint32_t y_org, x_org;      // origin of the pixel grid the tiles cover (0 except for the edge strips of a transposed convolution)
+    uint32_t y_end, x_end;      // pixels at or beyond are not stored
+    uint32_t sy, sx;            // output stride (1; 2 for the transposed convolution)
+    uint32_t out_h, out_w;      // output image
+    uint32_t ncols;             // output columns (Cout)
+    uint32_t NT;                // N tile: 16, 128 or 256 (divides ncols)
     uint32_t bw, bh;            // pixel tile = bw x bh = 128 pixels of one sample
     uint32_t tiles_x, tiles_y;  // pixel tiles per sample
     uint32_t pairs_per_sample;  // ceil(tiles / 2): a unit = 2 adjacent pixel tiles (one per CTA) x one N tile
     uint32_t n_nt;              // ncols / NT
     uint32_t n_units, units_per_pair;
     uint32_t epi;
-    uint32_t wrows_per_sample;  // rows of Wf per sample: taps * ncols (convolution: 9 * Cout; GEMM: ncols)
+    uint32_t wrows_per_sample;  // rows of Wf per sample: tap matrices * ncols
     const float* bias;          // [ncols]   (EPI_ACT)
     const float* noise;         // [B, H, W] or NULL
     const float* noise_w;       // device scalar or NULL
@@ -84,7 +99,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool leader = rank == 0;
     const uint32_t u_begin = (blockIdx.x / 2) * P.units_per_pair;
     const uint32_t u_end = min(P.n_units, u_begin + P.units_per_pair);
-    const uint32_t n_kc = P.Cin / 64, n_k = P.taps * n_kc;
+    const uint32_t n_kc = P.Cin / 64;
     const uint32_t tiles = P.tiles_x * P.tiles_y;
 
     if (threadIdx.x == 0) {
@@ -101,10 +116,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem_base = S.tmem_base;
 
-    // unit -> (sample, pixel tile of THIS CTA, N tile); the N tile is the fastest index: consecutive units of a pair share their A boxes (L2 hits)
-    auto decode = [&](uint32_t u, uint32_t& b, uint32_t& tile, uint32_t& nt) {
+    // unit -> (sample, pixel tile of THIS CTA, class, N tile); the N tile is the fastest index, then the class: consecutive units of a
+    // pair share their A boxes (L2 hits)
+    auto decode = [&](uint32_t u, uint32_t& b, uint32_t& tile, uint32_t& cl, uint32_t& nt) {
         nt = u % P.n_nt;
-        const uint32_t pp = u / P.n_nt;
+        uint32_t pp = u / P.n_nt;
+        cl = pp % P.n_cls;
+        pp /= P.n_cls;
         b = pp / P.pairs_per_sample;
         tile = (pp % P.pairs_per_sample) * 2 + rank;
     };
@@ -114,18 +132,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (uint32_t u = u_begin; u < u_end; u++) {
-                uint32_t b, tile, nt;
-                decode(u, b, tile, nt);
+                uint32_t b, tile, cl, nt;
+                decode(u, b, tile, cl, nt);
+                const ConvClass& K = P.cls[cl];
                 // a pixel tile beyond the sample's last one (odd tile count): coordinates past the image -> the box is zero-filled
-                const int32_t x0 = (int32_t)((tile % P.tiles_x) * P.bw), y0 = tile < tiles ? (int32_t)((tile / P.tiles_x) * P.bh) : (int32_t)(P.H + 8);
+                const int32_t x0 = (int32_t)(P.x_org + (tile % P.tiles_x) * P.bw), y0 = tile < tiles ? (int32_t)(P.y_org + (tile / P.tiles_x) * P.bh) : (int32_t)(P.H + 8);
+                const uint32_t n_k = K.n_taps * n_kc;
                 for (uint32_t k = 0; k < n_k; k++) {
                     const uint32_t tap = k / n_kc, kc = k % n_kc;
-                    const int32_t dy = P.taps == 9 ? (int32_t)(tap / 3) - 1 : 0, dx = P.taps == 9 ? (int32_t)(tap % 3) - 1 : 0;
+                    const int32_t dy = K.dy[tap], dx = K.dx[tap];
                     mbar_wait(&S.empty[stage], phase ^ 1);
                     if (leader) mbar_arrive_expect_tx(&S.full[stage], 2 * stage_bytes);
                     uint8_t* dst = smem + stage * stage_bytes;
                     tma_load_4d_2cta(dst, &tmA, &S.full[stage], (int32_t)(kc * 64), x0 + dx, y0 + dy, (int32_t)b);
-                    const int32_t wrow = (int32_t)(b * P.wrows_per_sample + (P.taps == 9 ? tap * P.ncols : 0u) + nt * P.NT + rank * (P.NT / 2));
+                    const int32_t wrow = (int32_t)(b * P.wrows_per_sample + K.wtap[tap] * P.ncols + nt * P.NT + rank * (P.NT / 2));
                     tma_load_2d_2cta(dst + CV_A_BYTES, &tmB, &S.full[stage], (int32_t)(kc * 64), wrow);
                     if (++stage == CV_NSTG) { stage = 0; phase ^= 1; }
                 }
@@ -141,6 +161,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(&S.tmem_empty[acc], acc_phase ^ 1);          // both CTAs' epilogues have drained this accumulator stage
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * 256;
+                const uint32_t n_k = P.cls[(u / P.n_nt) % P.n_cls].n_taps * n_kc;
                 for (uint32_t k = 0; k < n_k; k++) {
                     mbar_wait(&S.full[stage], phase);
                     tc_fence_after();
@@ -161,11 +182,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float nw = (P.epi == EPI_ACT && P.noise && P.noise_w) ? __ldg(P.noise_w) : 0.f;
         uint32_t local = wg;
         for (uint32_t u = u_begin + wg; u < u_end; u += 2, local += 2) {
-            uint32_t b, tile, nt;
-            decode(u, b, tile, nt);
-            const uint32_t px = (tile % P.tiles_x) * P.bw + r % P.bw, py = (tile / P.tiles_x) * P.bh + r / P.bw;
-            const bool valid = tile < tiles && px < P.W && py < P.H;
-            const uint64_t pix = ((uint64_t)b * P.H + py) * P.W + px;
+            uint32_t b, tile, cl, nt;
+            decode(u, b, tile, cl, nt);
+            const uint32_t gx = P.x_org + (tile % P.tiles_x) * P.bw + r % P.bw, gy = P.y_org + (tile / P.tiles_x) * P.bh + r / P.bw;
+            const uint32_t px = P.sx * gx + (uint32_t)P.cls[cl].ox, py = P.sy * gy + (uint32_t)P.cls[cl].oy;       // output pixel
+            const bool valid = tile < tiles && gx < P.x_end && gy < P.y_end && px < P.out_w && py < P.out_h;
+            const uint64_t pix = ((uint64_t)b * P.out_h + py) * P.out_w + px;
             const float nz = (valid && nw != 0.f) ? nw * __ldg(P.noise + pix) : 0.f;
             mbar_wait(&S.tmem_full[wg], (local >> 1) & 1);
             tc_fence_after();
@@ -179,7 +201,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int c = 0; c < 3; c++) v[c] = __uint_as_float(raw[c]) + __ldg(P.bias + c);
                     if (P.skip) {
-                        const uint32_t Hs = P.H / 2, Ws = P.W / 2;
+                        const uint32_t Hs = P.out_h / 2, Ws = P.out_w / 2;
                         const float k4[4] = {0.25f, 0.75f, 0.75f, 0.25f};      // [1,3,3,1] / 8 * 2 per axis
                         // U[2y, 2x] = skip[y, x]: of the 4 x 4 taps the two per axis with Y + p even contribute
 #pragma unroll
@@ -200,7 +222,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
                         if (P.out_nhwc) P.out_nhwc[pix * 3 + c] = v[c];
-                        if (P.out_nchw) P.out_nchw[(((size_t)b * 3 + c) * P.H + py) * P.W + px] = v[c];
+                        if (P.out_nchw) P.out_nchw[(((size_t)b * 3 + c) * P.out_h + py) * P.out_w + px] = v[c];
                     }
                 }
                 tc_fence_before();

@@ -55,7 +55,7 @@ class Upsample(nn.Module):
 
 
 class Blur(nn.Module):
-    """parameters of the blur behind an up-sampling convolution (runs inside sdfg_upconv_gather)"""
+    """parameters of the blur behind an up-sampling convolution (runs inside sdfg_upconv_forward)"""
 
     def __init__(self, kernel, pad, upsample_factor=1):
         super().__init__()
@@ -155,8 +155,7 @@ class StyledConv(nn.Module):
         up = 2 if self.conv.upsample else 1
         nz = self.noise.noise_for(B, H * up, W * up, noise, input.device)
         if self.conv.upsample:
-            y = ops.conv_forward(input, wf, gemm_mode=True)
-            return ops.upconv_gather(y, self.conv.out_channel, bias=self.activate.bias, noise=nz, noise_w=self.noise.weight)
+            return ops.upconv_forward(input, wf, bias=self.activate.bias, noise=nz, noise_w=self.noise.weight)
         return ops.conv_forward(input, wf, bias=self.activate.bias, noise=nz, noise_w=self.noise.weight)
 
 

@@ -411,29 +411,32 @@ def modconv_fold(weight, style, scale, demodulate=True):
     return out
 
 
-def conv_forward(x, wf, bias=None, noise=None, noise_w=None, gemm_mode=False):
-    """x [B,H,W,Cin] fp16; wf [B,taps,Cout,Cin] fp16 -> fp16 [B,H,W,Cout] (3x3 / 1x1 convolution + noise + bias + leaky ReLU * sqrt 2), or
-    with gemm_mode the raw tap products [B,H,W,taps*Cout] of a transposed convolution (see upconv_gather)."""
+def conv_forward(x, wf, bias=None, noise=None, noise_w=None):
+    """x [B,H,W,Cin] fp16; wf [B,taps,Cout,Cin] fp16 -> fp16 [B,H,W,Cout] (3x3 / 1x1 convolution + noise + bias + leaky ReLU * sqrt 2)."""
     lib = _lib.load()
     _chk(x, "x", torch.float16); _chk(wf, "wf", torch.float16)
     B, H, W, Cin = x.shape
     _, taps, Cout, _ = wf.shape
-    out = torch.empty(B, H, W, taps * Cout if gemm_mode else Cout, device=x.device, dtype=torch.float16)
+    out = torch.empty(B, H, W, Cout, device=x.device, dtype=torch.float16)
     with torch.cuda.device(x.device):
-        _lib.check(lib.sdfg_conv_forward(_ptr(x), _ptr(wf), B, H, W, Cin, Cout, taps, int(bool(gemm_mode)), _ptr(_chk(bias, "bias")),
+        _lib.check(lib.sdfg_conv_forward(_ptr(x), _ptr(wf), B, H, W, Cin, Cout, taps, _ptr(_chk(bias, "bias")),
                                          _ptr(_chk(noise, "noise")), _ptr(_chk(noise_w, "noise_w")), _ptr(out), _stream()), "sdfg_conv_forward")
     return out
 
 
-def upconv_gather(y, C, bias=None, noise=None, noise_w=None):
-    """y [B,H,W,9*C] fp16 (conv_forward(..., gemm_mode=True)) -> fp16 [B,2H,2W,C]: transposed-convolution tap sum + blur + noise + bias + act."""
+def upconv_forward(x, wf, bias=None, noise=None, noise_w=None):
+    """x [B,H,W,Cin] fp16; wf [B,9,Cout,Cin] fp16 -> fp16 [B,2H,2W,Cout]: transposed convolution (stride 2) + blur + noise + bias + act."""
     lib = _lib.load()
-    _chk(y, "y", torch.float16)
-    B, H, W, _ = y.shape
-    out = torch.empty(B, 2 * H, 2 * W, C, device=y.device, dtype=torch.float16)
-    with torch.cuda.device(y.device):
-        _lib.check(lib.sdfg_upconv_gather(_ptr(y), B, H, W, C, _ptr(_chk(bias, "bias")), _ptr(_chk(noise, "noise")), _ptr(_chk(noise_w, "noise_w")),
-                                          _ptr(out), _stream()), "sdfg_upconv_gather")
+    _chk(x, "x", torch.float16); _chk(wf, "wf", torch.float16)
+    B, H, W, Cin = x.shape
+    _, taps, Cout, _ = wf.shape
+    if taps != 9:
+        raise ValueError("upconv_forward: 3 x 3 kernels only")
+    t = torch.empty(B, 2 * H + 1, 2 * W + 1, Cout, device=x.device, dtype=torch.float16)
+    out = torch.empty(B, 2 * H, 2 * W, Cout, device=x.device, dtype=torch.float16)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.sdfg_upconv_forward(_ptr(x), _ptr(wf), B, H, W, Cin, Cout, _ptr(t), _ptr(_chk(bias, "bias")), _ptr(_chk(noise, "noise")),
+                                           _ptr(_chk(noise_w, "noise_w")), _ptr(out), _stream()), "sdfg_upconv_forward")
     return out
 
 
