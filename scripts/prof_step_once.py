@@ -1,4 +1,5 @@
-"""The bench workload without the measuring: W warm-up + K training steps (configs[1], B = 32) and K inference passes with features.
+"""The bench workload without the measuring: W warm-up + K training steps (configs[1], B = 32), K inference passes with features, or (infer256,
+PROF_B=64) K passes of the full generator.
 The program ncu is wrapped around (scripts/gpu_profile2.sh); prints the number of kernel launches per step for -s / -c."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -24,6 +25,16 @@ if mode == "train":
         g_losses(thumb, sdf, eik).backward()
         opt.step()
         torch.cuda.synchronize()
+elif mode == "infer256":
+    # configs[2]: full generator (renderer + decoder), 256^2 images
+    mo, ro = sg.default_options("ngp", size=256, renderer_res=R, n_samples=S, perturb=0.)
+    g = sg.Generator(mo, ro, full_pipeline=True, ema=True).to(dev).eval()
+    cam, focal, near, far, _ = sg.generate_camera_params(R, dev, batch=B)
+    z = torch.randn(B, STYLE, device=dev)
+    with torch.no_grad():
+        for i in range(3):
+            g([z], cam, focal, near, far)
+            torch.cuda.synchronize()
 else:
     mo, ro = sg.default_options("ngp", renderer_res=R, n_samples=S, perturb=0.)
     g = sg.Generator(mo, ro, full_pipeline=False, ema=True).to(dev).eval()
