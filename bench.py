@@ -287,6 +287,18 @@ def run_ours(args):
             barrier()
             sg._lib.prof_enable(False, "")
             gk_ms, gk_n = sg._lib.prof_collect()
+            # the same pass replayed as a CUDA graph (sg.GraphedGenerator: the serving call for a fixed batch shape)
+            gg = sg.GraphedGenerator(g_full, [z_i], cam_i, focal_i, near_i, far_i)
+            for _ in range(2):
+                gg([z_i], cam_i, focal_i, near_i, far_i)
+            barrier()
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            q0.record()
+            for _ in range(args.steps):
+                gg([z_i], cam_i, focal_i, near_i, far_i)
+            q1.record()
+            barrier()
+            del gg
             # renderer alone (same batch), to split the pass
             style_i = g_full.style(z_i)
             for _ in range(2):
@@ -298,15 +310,16 @@ def run_ours(args):
                 g_full.renderer(cam_i, focal_i, near_i, far_i, styles=style_i)
             r1.record()
             barrier()
-        t = torch.tensor([f0.elapsed_time(f1) / args.steps, r0.elapsed_time(r1) / args.steps], device=dev, dtype=torch.float64)
+        t = torch.tensor([f0.elapsed_time(f1) / args.steps, r0.elapsed_time(r1) / args.steps, q0.elapsed_time(q1) / args.steps], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        full_ms, rend_ms = float(t[0]), float(t[1])
+        full_ms, rend_ms, graph_ms = float(t[0]), float(t[1]), float(t[2])
         # decoder MACs per image: 3x3 modulated convolutions 256->512@64^2, 512->256 (x2 up), 256->256@128^2, 256->128 (x2 up), 128->128@256^2
         dec_flop = 2 * 9 * (64 * 64 * 256 * 512 + 64 * 64 * 512 * 256 + 128 * 128 * 256 * 256 + 128 * 128 * 256 * 128 + 256 * 256 * 128 * 128)
         inf256 = {"workload": "configs[2]: ffhq_256_sdf_ngp generator forward (renderer + decoder), eval, B = 64 over %d GPU(s)" % world,
                   "batch_per_gpu": Bi, "ms_per_pass": full_ms, "images_per_s": 64 / (full_ms * 1e-3), "renderer_ms": rend_ms,
                   "decoder_ms": full_ms - rend_ms, "scaling": "strong",
+                  "graphed_ms_per_pass": graph_ms, "graphed_images_per_s": 64 / (graph_ms * 1e-3),
                   "gemm_kernel_ms_per_pass": gk_ms / args.steps, "gemm_kernel_launches_per_pass": gk_n / args.steps,
                   "generator_tflops_algorithmic": Bi * (SAMPLES_PER_IMAGE * FIELD_FLOP_FWD + dec_flop) / (full_ms * 1e-3) / 1e12,
                   "image_shape": list(img.shape)}

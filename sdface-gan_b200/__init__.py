@@ -9,4 +9,5 @@ from .shencoder import SHEncoder, sh_encode  # noqa: F401
 from .sdf_model import (FCGenerator, FiLMSiren, Generator, LinearLayer, MappingLinear, NGPSIRENGenerator, SirenGenerator,  # noqa: F401
                         VolumeFeatureRenderer, get_encoder, register_decoder)
 from .decoder import Decoder  # noqa: F401
+from .graphed import GraphedGenerator  # noqa: F401
 from .sdf_utils import Munch, align_volume, default_options, generate_camera_params  # noqa: F401

@@ -108,29 +108,6 @@ __host__ __device__ inline uint32_t fchain_smem_bytes(int cg) {
     return 1024 + CH_ACT_BYTES + 2 * CH_CHUNK_BYTES + fc_w_stages(cg) * fc_w_bytes(cg) + 2 * CH_SGN_TILE_BYTES + (uint32_t)sizeof(FChainSmem);
 }
 
-// packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 -- two lanes of fp32 per issue slot)
-__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
-    uint64_t r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-    uint64_t r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-
 template <bool SAVE, bool COS, int CG>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 tc_fchain_fwd_kernel(const __grid_constant__ FChainMaps maps, const __grid_constant__ FChainParams P) {
