@@ -36,24 +36,26 @@ __global__ void __launch_bounds__(256) nhwc16_kernel(const float* __restrict__ i
     reinterpret_cast<uint2*>(out)[i] = make_uint2(tc::pack_f16_sat(v.x, v.y), tc::pack_f16_sat(v.z, v.w));
 }
 
-// demod[b, o] = rsqrt(sum_{i, tap} (scale * W[o, i, tap] * s[b, i])^2 + 1e-8)                      block = (o, b), threads over i * taps
-__global__ void __launch_bounds__(256) demod_kernel(const float* __restrict__ W, const float* __restrict__ style, float scale, uint32_t Cin,
+// demod[b, o] = rsqrt(sum_{i, tap} (scale * W[o, i, tap] * s[b, i])^2 + 1e-8) = rsqrt(scale^2 * sum_i s[b, i]^2 * W2[o, i] + 1e-8) with
+// W2[o, i] = sum_tap W[o, i, tap]^2: a block owns output channel o, squares its weight row ONCE into shared memory and serves every
+// sample from it (a block per (o, b) re-read the row B times: 0.3 ms per configs[2] pass).      grid Cout, dynamic smem Cin floats
+__global__ void __launch_bounds__(256) demod_kernel(const float* __restrict__ W, const float* __restrict__ style, float scale, uint32_t B, uint32_t Cin,
                                                      uint32_t Cout, uint32_t taps, float* __restrict__ demod) {
-    __shared__ float red[8];
-    const uint32_t o = blockIdx.x, b = blockIdx.y;
+    extern __shared__ float w2[];
+    const uint32_t o = blockIdx.x;
     const float* Wo = W + (size_t)o * Cin * taps;
-    float acc = 0.f;
-    for (uint32_t k = threadIdx.x; k < Cin * taps; k += blockDim.x) {
-        const float w = scale * __ldg(Wo + k) * __ldg(style + (size_t)b * Cin + k / taps);
-        acc = fmaf(w, w, acc);
+    for (uint32_t i = threadIdx.x; i < Cin; i += blockDim.x) {
+        float a = 0.f;
+        for (uint32_t t = 0; t < taps; t++) { const float w = __ldg(Wo + i * taps + t); a = fmaf(w, w, a); }
+        w2[i] = a;
     }
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int i = 0; i < 8; i++) t += red[i];
-        demod[(size_t)b * Cout + o] = rsqrtf(t + 1e-8f);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t b = warp; b < B; b += blockDim.x >> 5) {
+        float acc = 0.f;
+        for (uint32_t i = lane; i < Cin; i += 32) { const float sv = __ldg(style + (size_t)b * Cin + i); acc = fmaf(sv * sv, w2[i], acc); }
+        acc = warp_sum(acc);
+        if (lane == 0) demod[(size_t)b * Cout + o] = rsqrtf(fmaf(scale * scale, acc, 1e-8f));
     }
 }
 
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(256) modconv_fold_kernel(const float* __restri
 // needs once and combines them vertically -- 8.5 instead of 16 taps per output.  HBM: T is read ~1.4x (halo, mostly L2 hits), the
 // output written once.
 constexpr int UG_T = 16, UG_P = UG_T + 3;
-__global__ void __launch_bounds__(256) upconv_blur_kernel(const uint16_t* __restrict__ T, uint32_t B, uint32_t H, uint32_t W, uint32_t C,
+__global__ void __launch_bounds__(256, 4) upconv_blur_kernel(const uint16_t* __restrict__ T, uint32_t B, uint32_t H, uint32_t W, uint32_t C,
                                                            const float* __restrict__ bias, const float* __restrict__ noise,
                                                            const float* __restrict__ noise_w, uint16_t* __restrict__ out) {
     __shared__ uint4 P[UG_P * UG_P][8];                                // [position][8 channel groups of 8 fp16]
@@ -90,12 +92,19 @@ __global__ void __launch_bounds__(256) upconv_blur_kernel(const uint16_t* __rest
     const uint32_t b = blockIdx.x / (tiles_x * tiles_y), t = blockIdx.x % (tiles_x * tiles_y);
     const int Y0 = (int)(t / tiles_x) * UG_T, X0 = (int)(t % tiles_x) * UG_T;
     const uint16_t* Tb = T + (size_t)b * Ht * Wt * C + c0;
-#pragma unroll 4
-    for (int e = slot; e < UG_P * UG_P; e += 32) {
-        const int r = Y0 + e / UG_P - 1, c = X0 + e % UG_P - 1;
-        const bool ok = r >= 0 && c >= 0 && r < (int)Ht && c < (int)Wt;
-        P[e][cg] = ok ? __ldg(reinterpret_cast<const uint4*>(Tb + ((size_t)r * Wt + c) * C)) : make_uint4(0, 0, 0, 0);
+    // global -> shared without a register round trip: all 12 copies of a thread are in flight together (with ld + st the loop ran 3-4
+    // loads deep and the load phase, not the arithmetic, set the block time); out-of-image positions are zero-filled (src-size 0)
+#pragma unroll
+    for (int it = 0; it < (UG_P * UG_P + 31) / 32; it++) {
+        const int e = slot + it * 32;
+        if (e < UG_P * UG_P) {
+            const int r = Y0 + e / UG_P - 1, c = X0 + e % UG_P - 1;
+            const bool ok = r >= 0 && c >= 0 && r < (int)Ht && c < (int)Wt;
+            const uint16_t* src = ok ? Tb + ((size_t)r * Wt + c) * C : Tb;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(&P[e][cg])), "l"(src), "r"(ok ? 16 : 0) : "memory");
+        }
     }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     const float nw = (noise && noise_w) ? __ldg(noise_w) : 0.f;
     uint64_t bs2[4];                                                    // bias of this thread's 8 channels as packed fp32 pairs
@@ -178,7 +187,7 @@ extern "C" int sdfg_modconv_fold(const float* weight, const float* style, float 
     SDFG_REQUIRE(weight && style && out && (!demodulate || demod_scratch), SDFG_ERR_INVALID, "modconv_fold: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (demodulate) {
-        demod_kernel<<<dim3(Cout, B), 256, 0, st>>>(weight, style, scale, Cin, Cout, taps, demod_scratch);
+        demod_kernel<<<Cout, 256, Cin * sizeof(float), st>>>(weight, style, scale, B, Cin, Cout, taps, demod_scratch);
         if (int e = check_launch("demod_kernel")) return e;
     }
     modconv_fold_kernel<<<dim3(Cout, B), 256, 0, st>>>(weight, style, demodulate ? demod_scratch : nullptr, scale, Cin, Cout, taps, out);
