@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_render.py tests/test_gpu_fullsize.py tests/test_decoder.py -q -x 2>&1 | tail -3
+timeout 300 python scripts/bench_kernels.py 32 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+for k in ('composite_forward_feat16','composite_forward_feat32','composite_forward_nofeat'): print(k, '%.3f ms' % d[k]['ms'], '%.0f GB/s' % d[k]['hbm_GBps'])
+print(json.dumps(d.get('inference_forward'))[:300])"

@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(256) composite_forward_kernel(
         for (int j = 0; j < kMaxF4; j++) fa[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4* frow = reinterpret_cast<const float4*>(feat + base * F);
         const uint2* frow16 = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(feat) + base * F);
+        // 4 samples per trip: 8 independent loads per lane in flight (one sample at a time left the stream latency-bound at ~60 % of HBM)
+#pragma unroll 4
         for (uint32_t s = 0; s < S; s++) {
             float w = 0.f;
 #pragma unroll
