@@ -52,7 +52,7 @@ for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
     print("%-72s %4d %10.1f" % (k, n, t / 3))
 if os.environ.get("PROF_TIMELINE"):
     # timeline of the last step's long kernels: start (us, relative), duration, stream -- shows whether two streams really overlap
-    last_fwd = [e for e in evs if "tc_chain_fwd" in e.name][-1].time_range.start
+    last_fwd = [e for e in evs if "chain_fwd" in e.name][-1].time_range.start
     for e in evs:
         d = e.time_range.end - e.time_range.start
         if e.time_range.start >= last_fwd and d > 60:

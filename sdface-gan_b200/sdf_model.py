@@ -9,7 +9,6 @@ sample), the field as a fused sequence of layer kernels (csrc/field_*.cu) and on
 instead of ~45 + the [N,272]/[N,260] concatenations.  There is no CPU path: tensors must live on a CUDA device.
 """
 import math
-import os
 import warnings
 
 import numpy as np
@@ -157,10 +156,12 @@ class _field(Function):
         # phase 1: loss scale + gradient chain through the layers -> d x_in (and the gradient tiles phase 2 contracts)
         dx, state = ops.field_backward(*args, grads=grads, want_dx=want_dx, precision=meta["precision"], phases=_lib.BWD_CHAIN)
         d_emb, work, world = None, None, 1
-        side = None
-
-        def scatter():
-            nonlocal work, world
+        if need_table:
+            # The scatter runs ALONE between the two phases.  Overlapping it with the weight-gradient contractions was measured both ways
+            # (DESIGN 6): with equal stream priorities its 12 k pending blocks starve the other stream's kernels (no overlap), with the
+            # contractions on a high-priority stream both run together and both slow down 2-3x (the contractions stream 13 GB through
+            # the L2 that the scatter's 50 MB gradient table wants to stay resident in): 14.8-14.9 ms per step against 14.3-14.4.
+            d_emb = torch.zeros_like(emb)
             ops.grid_encode_backward(dx, grid["pts"], emb, grid["offsets"], grid["S"], grid["H"], bound=grid["bound"], grad_embeddings=d_emb,
                                      gridtype=grid["gridtype"], align_corners=grid["align_corners"], interp=grid["interp"])
             ex = meta.get("exchange")
@@ -168,24 +169,9 @@ class _field(Function):
                 world = torch.distributed.get_world_size(ex["group"])
                 if world > 1:      # SUM + divide: ReduceOp.AVG exists for NCCL only
                     work = torch.distributed.all_reduce(d_emb, op=torch.distributed.ReduceOp.SUM, group=ex["group"], async_op=True)
-
-        if need_table:
-            d_emb = torch.zeros_like(emb)
-            if _SCATTER_OVERLAP and need_param and dx.is_cuda:
-                # the scatter (L2-atomic bound, 3 % of the HBM rate) and the weight-gradient contractions (HBM bound) want different parts of
-                # the chip: the scatter goes to a side stream and is enqueued AFTER phase 2, so that the persistent contraction kernels get
-                # their one CTA per SM first and the scatter's blocks fill in beside them
-                side = _side_stream(dx.device)
-                side.wait_stream(torch.cuda.current_stream(dx.device))
-            else:
-                scatter()
         # phase 2: parameter gradients (HBM-bound contractions) while the table gradient travels
         if need_param:
             ops.field_backward(*args, grads=grads, want_dx=want_dx, precision=meta["precision"], phases=_lib.BWD_WGRAD, state=state)
-        if side is not None:
-            with torch.cuda.stream(side):
-                scatter()
-            torch.cuda.current_stream(dx.device).wait_stream(side)
         if work is not None:
             work.wait()                                        # stream-level for NCCL: the current stream waits for the collective
             d_emb.div_(world)
@@ -222,17 +208,6 @@ def _unpack_weights(spec, w):
 
 
 _WARNED = set()
-
-
-_SCATTER_OVERLAP = os.environ.get("SDFG_SCATTER_OVERLAP", "0") != "0"
-_SIDE_STREAMS = {}
-
-
-def _side_stream(device):
-    st = _SIDE_STREAMS.get(device)
-    if st is None:
-        st = _SIDE_STREAMS[device] = torch.cuda.Stream(device=device)
-    return st
 
 
 def _warn_once(key, msg):
