@@ -136,3 +136,64 @@ def test_graphed_generator_replays_the_eager_forward():
     n2 = gn([z1], cam, focal, near, far)[0].clone()
     assert torch.isfinite(n1).all() and not torch.equal(n1, n2)            # fresh noise per replay
     assert H.max_abs(gn([z1], cam, focal, near, far)[1], e1[1]) == 0.0      # the thumbnail has no noise input
+
+
+def _ref_weights(wf):
+    """wf [B, 9 | 1, Cout, Cin] fp16 (what sdfg_modconv_fold produces) -> fp32 [B, Cout, Cin, k, k]"""
+    B, taps, Cout, Cin = wf.shape
+    k = 3 if taps == 9 else 1
+    return wf.float().permute(0, 2, 3, 1).reshape(B, Cout, Cin, k, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,Hh,Ww,Cin,Cout", [(2, 8, 8, 64, 128), (1, 16, 32, 128, 128), (3, 64, 64, 64, 256), (1, 6, 16, 64, 128)])
+def test_conv_and_upconv_ops_match_torch(B, Hh, Ww, Cin, Cout):
+    """Operator level, against plain torch fp32 on the same fp16-rounded operands: the 3 x 3 convolution and the up-sampling layer
+    (conv_transpose2d stride 2 as four parity classes + two edge strips -> blur -> noise + bias -> leaky ReLU * sqrt 2), at shapes with one
+    pixel tile per sample, odd tile counts, a height that is not a multiple of the tile height, and both N tiles (128 / 256).
+    Tolerance: fp16 output (+ one fp16 intermediate for the up-sampling layer): 3e-3 of the output's max."""
+    import torch.nn.functional as F
+    from sdface_gan_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(Hh * 131 + Cout)
+    x = (torch.randn(B, Hh, Ww, Cin, generator=g) * 0.5).half().cuda()
+    wf = (torch.randn(B, 9, Cout, Cin, generator=g) * (1.0 / (3 * Cin ** 0.5))).half().cuda()
+    bias = torch.randn(Cout, generator=g).cuda() * 0.1
+    nw = torch.tensor([0.3]).cuda()
+    w5 = _ref_weights(wf)
+    xn = x.float().permute(0, 3, 1, 2)                                       # NCHW fp32
+    lrelu = lambda t: F.leaky_relu(t, 0.2) * 2 ** 0.5
+    # 3 x 3
+    noise = torch.randn(B, Hh, Ww, generator=g).cuda()
+    got = ops.conv_forward(x, wf, bias=bias, noise=noise, noise_w=nw).float().permute(0, 3, 1, 2)
+    ref = torch.stack([F.conv2d(xn[b:b + 1], w5[b], padding=1)[0] for b in range(B)])
+    ref = lrelu(ref + nw * noise[:, None] + bias.view(1, -1, 1, 1))
+    assert H.max_abs(got, ref) < 3e-3 * float(ref.abs().max())
+    # up-sampling layer
+    noise2 = torch.randn(B, 2 * Hh, 2 * Ww, generator=g).cuda()
+    got = ops.upconv_forward(x, wf, bias=bias, noise=noise2, noise_w=nw).float().permute(0, 3, 1, 2)
+    t = torch.stack([F.conv_transpose2d(xn[b:b + 1], w5[b].transpose(0, 1), stride=2)[0] for b in range(B)])      # [B, Cout, 2H+1, 2W+1]
+    ref = do.upfirdn2d(t.cpu(), do._blur_kernel(4.0), pad=(1, 1)).cuda()
+    ref = lrelu(ref + nw * noise2[:, None] + bias.view(1, -1, 1, 1))
+    assert got.shape == ref.shape == (B, Cout, 2 * Hh, 2 * Ww)
+    assert H.max_abs(got, ref) < 3e-3 * float(ref.abs().max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,Hh,C,with_skip", [(2, 8, 64, False), (3, 16, 128, True), (1, 64, 512, True)])
+def test_to_rgb_op_matches_torch(B, Hh, C, with_skip):
+    """ToRGB as the N = 16 GEMM of the conv kernel: modulated 1 x 1 convolution (no demodulation) + bias + up-sampled skip, both output
+    layouts, against torch fp32 on the fp16-rounded activation (weights are rounded to fp16 inside: 2e-3 of the output's max)."""
+    from sdface_gan_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(C + Hh)
+    x = (torch.randn(B, Hh, Hh, C, generator=g) * 0.5).half().cuda()
+    w = torch.randn(1, 3, C, 1, 1, generator=g).cuda()
+    style = (1 + 0.3 * torch.randn(B, C, generator=g)).cuda()
+    bias = torch.randn(1, 3, 1, 1, generator=g).cuda() * 0.1
+    skip = torch.randn(B, Hh // 2, Hh // 2, 3, generator=g).cuda() if with_skip else None
+    scale = 1 / C ** 0.5
+    nhwc, nchw = ops.to_rgb(x, w, style, scale, bias, skip, want_nhwc=True, want_nchw=True)
+    ref = torch.einsum("bhwc,oc,bc->bohw", x.float(), w.view(3, C), style) * scale + bias
+    if with_skip:
+        ref = ref + do.upfirdn2d(skip.permute(0, 3, 1, 2).cpu(), do._blur_kernel(4.0), up=2, pad=(2, 1)).cuda()
+    assert torch.equal(nhwc.permute(0, 3, 1, 2), nchw)
+    assert H.max_abs(nchw, ref) < 2e-3 * float(ref.abs().max())
