@@ -45,7 +45,25 @@ tab = enc.embeddings.detach()
 threads, rounds = 148 * 2048 * 4, 64
 ms = timed(lambda: ops.l2_gather_probe(tab, threads, rounds))
 gathers = threads * 8 * rounds
-out["l2_gather_probe"] = {"table_MB": tab.numel() * 4 / 1e6, "Ggathers_per_s": gathers / ms / 1e6, "GBps_8B": gathers * 8 / ms / 1e6}
+out["l2_gather_probe"] = {"table_MB": tab.numel() * 4 / 1e6, "Ggathers_per_s": gathers / ms / 1e6, "GBps_8B": gathers * 8 / ms / 1e6,
+                          "note": "rate of INDEPENDENT random 8-byte gathers over a table-sized buffer -- a yardstick, not a ceiling: the encoder's "
+                                  "coarse levels beat it because neighbouring samples share sectors (x_random_gather_probe > 1).  The bound "
+                                  "fractions are the hardware's own counters in ncu_bound."}
+# the kernels' bound as the hardware counts it (ncu --set full, profiles/r02k_summary.txt): busiest unit, percent of its peak
+out["ncu_bound"] = {}
+try:
+    import re
+    blocks = open(os.path.join(ROOT, "profiles", "r02k_summary.txt")).read().split("---\n")
+    for blk in blocks:
+        m = re.search(r"Kernel Name\s+(?:void )?(?:sdfg::)?(\w+)", blk)
+        if not m or not m.group(1).startswith(("grid_", "composite_")):
+            continue
+        g1 = lambda key: float(re.search(key + r"\s+([\d.]+)", blk).group(1)) if re.search(key + r"\s+([\d.]+)", blk) else None
+        out["ncu_bound"].setdefault(m.group(1), {"l1tex_pct": g1("l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
+                                                 "lts_pct": g1("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+                                                 "dram_pct": g1("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")})
+except Exception as e:                                  # the summary is a committed file; absent only in a stripped checkout
+    out["ncu_bound"] = {"unavailable": str(e)}
 
 # --- encoder on the real ray samples (the points are NOT uniform: SURVEY 8d)
 with torch.no_grad():
@@ -61,10 +79,10 @@ gt = torch.zeros_like(tab)
 ms_b = timed(lambda: ops.grid_encode_backward(grad, pts, tab, enc.offsets, Sg, H, bound=2.0, grad_embeddings=gt))
 probe = out["l2_gather_probe"]["Ggathers_per_s"]
 out["grid_forward"] = {"ms": ms_f, "hbm_GBps": N * 140 / ms_f / 1e6, "Ggathers_per_s": N * 128 / ms_f / 1e6,
-                       "frac_of_l2_gather_probe": N * 128 / ms_f / 1e6 / probe}
+                       "x_random_gather_probe": N * 128 / ms_f / 1e6 / probe}
 out["grid_forward_dydx"] = {"ms": ms_fd, "hbm_GBps": N * (140 + 384) / ms_fd / 1e6, "frac_of_hbm": N * (140 + 384) / ms_fd / 1e6 / hbm_peak,
-                            "frac_of_l2_gather_probe": N * 128 / ms_fd / 1e6 / probe}
-out["grid_backward"] = {"ms": ms_b, "Greductions_8B_per_s": N * 128 / ms_b / 1e6, "frac_of_l2_gather_probe": N * 128 / ms_b / 1e6 / probe}
+                            "x_random_gather_probe": N * 128 / ms_fd / 1e6 / probe}
+out["grid_backward"] = {"ms": ms_b, "Greductions_8B_per_s": N * 128 / ms_b / 1e6, "x_random_gather_probe": N * 128 / ms_b / 1e6 / probe}
 
 # --- the reference's own kernels (gridencoder.cu / shencoder.cu compiled UNCHANGED for sm_100a into oracle/_ref/, same box, same
 #     inputs): SURVEY 2.3 sets "beat the reference kernel recompiled for sm_100a" as the bar
@@ -156,6 +174,13 @@ for Rm in (128, 256):
     with torch.no_grad():
         ms_m = timed(lambda: gm([z[:1]], cam_m, focal_m, near_m, far_m, return_sdf=True, return_xyz=True), reps=3, warm=2)
     out["sdf_mesh_query"]["R%d" % Rm] = {"points": Rm ** 3, "ms": ms_m, "Mpoints_per_s": Rm ** 3 / ms_m / 1e3}
-    del gm
+    # the SDF-only fast path: trunk + sigma head only -- no view layer, rgb or feature map -- then the frustum -> box resample
+    gm.renderer.sdf_only = True
+    with torch.no_grad():
+        ms_s = timed(lambda: gm([z[:1]], cam_m, focal_m, near_m, far_m, return_sdf=True, return_xyz=True), reps=3, warm=2)
+        sdf_vol = gm([z[:1]], cam_m, focal_m, near_m, far_m, return_sdf=True, return_xyz=True)[3]
+        ms_a = timed(lambda: sg.align_volume(sdf_vol), reps=3, warm=1)
+    out["sdf_mesh_query"]["R%d" % Rm].update({"sdf_only_ms": ms_s, "sdf_only_Mpoints_per_s": Rm ** 3 / ms_s / 1e3, "align_volume_ms": ms_a})
+    del gm, sdf_vol
     torch.cuda.empty_cache()
 print(json.dumps(out))
