@@ -360,6 +360,11 @@ def run_ours(args):
                 "kernel_share_of_step": (k_ms / args.steps) / ms,
                 "algorithmic_flop_per_step": flop_step, "executed_flop_per_step": flop_exec if args.precision == "tc16" else flop_step,
                 "achieved_executed": (flop_exec / (k_ms / args.steps * 1e-3) / 1e12) if (k_n and args.precision == "tc16") else achieved,
+                # the same launches against the OTHER roof: measured dram bytes (traffic) / their summed time / the measured HBM peak.  The
+                # step saves every layer's activations for the backward, so its GEMM kernels sit closer to the HBM roof than to the tensor one.
+                "hbm_GBps": (traffic / (k_ms / args.steps * 1e-3) / 1e9) if (traffic and k_n) else None,
+                "hbm_peak_GBps": peaks.get("hbm_gbs"),
+                "hbm_frac": (traffic / (k_ms / args.steps * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6547.0)) if (traffic and k_n) else None,
                 "note": "achieved = algorithmic GEMM flop of the reference network for this step (SURVEY 8d: forward 550 912 flop/sample incl. heads' "
                         "GEMM part, eikonal dgrads, backward dgrad + wgrad) / summed CUDA-event time of the tcgen05 launches of the step"}
         cpu = None

@@ -1,6 +1,6 @@
 """The bench workload without the measuring: W warm-up + K training steps (configs[1], B = 32), K inference passes with features, or (infer256,
 PROF_B=64) K passes of the full generator.
-The program ncu is wrapped around (scripts/gpu_profile2.sh); prints the number of kernel launches per step for -s / -c."""
+The program ncu is wrapped around (scripts/gpu_profile3.sh); prints the number of kernel launches per step for -s / -c."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
