@@ -299,6 +299,24 @@ def run_ours(args):
             q1.record()
             barrier()
             del gg
+            # single-image latency (the interactive / demo case): eager (launch-bound: ~230 launches) and as a graph
+            lat = {}
+            if rank == 0:
+                one = (cam_i[:1].contiguous(), focal_i[:1].contiguous(), near_i[:1].contiguous(), far_i[:1].contiguous())
+                g1 = sg.GraphedGenerator(g_full, [z_i[:1]], *one)
+                for name, fn in (("eager", lambda: g_full([z_i[:1]], *one)), ("graphed", lambda: g1([z_i[:1]], *one))):
+                    for _ in range(3):
+                        fn()
+                    torch.cuda.synchronize()
+                    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    l0.record()
+                    for _ in range(20):
+                        fn()
+                    l1.record()
+                    torch.cuda.synchronize()
+                    lat[name] = l0.elapsed_time(l1) / 20
+                del g1
+            barrier()
             # renderer alone (same batch), to split the pass
             style_i = g_full.style(z_i)
             for _ in range(2):
@@ -320,6 +338,7 @@ def run_ours(args):
                   "batch_per_gpu": Bi, "ms_per_pass": full_ms, "images_per_s": 64 / (full_ms * 1e-3), "renderer_ms": rend_ms,
                   "decoder_ms": full_ms - rend_ms, "scaling": "strong",
                   "graphed_ms_per_pass": graph_ms, "graphed_images_per_s": 64 / (graph_ms * 1e-3),
+                  "latency_ms_batch1": lat,
                   "gemm_kernel_ms_per_pass": gk_ms / args.steps, "gemm_kernel_launches_per_pass": gk_n / args.steps,
                   "generator_tflops_algorithmic": Bi * (SAMPLES_PER_IMAGE * FIELD_FLOP_FWD + dec_flop) / (full_ms * 1e-3) / 1e12,
                   "image_shape": list(img.shape)}
