@@ -283,7 +283,7 @@ int sdfg_modconv_fold(const float* weight, const float* style, float scale, uint
 
 /* 3 x 3 (taps = 9) / 1 x 1 (taps = 1) convolution, stride 1, zero padding, on per-sample weights wf [B, taps, Cout, Cin] (sdfg_modconv_fold),
  * fused with out = leaky_relu(conv + noise_w[0] * noise[b,y,x] + bias[o], 0.2) * sqrt(2) (NoiseInjection + FusedLeakyReLU);
- * out [B, H, W, Cout].  noise [B, H, W] / noise_w (device scalar) / bias [Cout] may be NULL.  Cin % 64 == 0, Cout % 128 == 0, W a power of two >= 8.
+ * out [B, H, W, Cout].  noise [B, H, W] / noise_w (device scalar) / bias [Cout] may be NULL.  Cin % 64 == 0, Cout % 64 == 0 (N tile 256 / 128 / 64), W a power of two >= 8.
  * ref ModulatedConv2d.forward :685-704 + StyledConv.forward :812-816. */
 int sdfg_conv_forward(const uint16_t* x, const uint16_t* wf, uint32_t B, uint32_t H, uint32_t W, uint32_t Cin, uint32_t Cout, uint32_t taps,
                       const float* bias, const float* noise, const float* noise_w, uint16_t* out, void* stream);

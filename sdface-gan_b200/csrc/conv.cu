@@ -234,7 +234,7 @@ extern "C" int sdfg_conv_forward(const uint16_t* x, const uint16_t* wf, uint32_t
                                  const float* bias, const float* noise, const float* noise_w, uint16_t* out, void* stream) {
     if (B == 0) return SDFG_OK;
     SDFG_REQUIRE(x && wf && out, SDFG_ERR_INVALID, "conv_forward: null pointer");
-    SDFG_REQUIRE(Cin % 64 == 0 && Cout % 128 == 0, SDFG_ERR_UNSUPPORTED, "conv_forward: Cin must be a multiple of 64 and Cout of 128 (got %u, %u)", Cin, Cout);
+    SDFG_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, SDFG_ERR_UNSUPPORTED, "conv_forward: Cin and Cout must be multiples of 64 (got %u, %u)", Cin, Cout);
     SDFG_REQUIRE(taps == 9 || taps == 1, SDFG_ERR_UNSUPPORTED, "conv_forward: 3 x 3 (taps = 9) or 1 x 1 (taps = 1) only");
     SDFG_REQUIRE(W >= 8 && (W & (W - 1)) == 0, SDFG_ERR_UNSUPPORTED, "conv_forward: width must be a power of two >= 8 (got %u)", W);
     SDFG_REQUIRE(Cout <= 2304, SDFG_ERR_UNSUPPORTED, "conv_forward: too many output channels");      // bias table in shared memory
@@ -243,7 +243,7 @@ extern "C" int sdfg_conv_forward(const uint16_t* x, const uint16_t* wf, uint32_t
     P.n_cls = 1; plain_conv_class(P.cls[0], taps);
     P.y_end = H; P.x_end = W; P.sy = P.sx = 1; P.out_h = H; P.out_w = W;
     P.ncols = Cout; P.wrows_per_sample = taps * Cout;
-    P.NT = (Cout % 256 == 0) ? 256 : 128;
+    P.NT = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : 64;
     P.epi = tc::EPI_ACT;
     P.bias = bias; P.noise = noise; P.noise_w = noise_w; P.out = out; P.ld_out = Cout;
     P.bw = std::min(W, 128u); P.bh = 128 / P.bw;
@@ -254,14 +254,14 @@ extern "C" int sdfg_upconv_forward(const uint16_t* x, const uint16_t* wf, uint32
                                    uint16_t* t_scratch, const float* bias, const float* noise, const float* noise_w, uint16_t* out, void* stream) {
     if (B == 0) return SDFG_OK;
     SDFG_REQUIRE(x && wf && t_scratch && out, SDFG_ERR_INVALID, "upconv_forward: null pointer");
-    SDFG_REQUIRE(Cin % 64 == 0 && Cout % 128 == 0, SDFG_ERR_UNSUPPORTED, "upconv_forward: Cin must be a multiple of 64 and Cout of 128 (got %u, %u)", Cin, Cout);
+    SDFG_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, SDFG_ERR_UNSUPPORTED, "upconv_forward: Cin and Cout must be multiples of 64 (got %u, %u)", Cin, Cout);
     SDFG_REQUIRE(W >= 8 && (W & (W - 1)) == 0, SDFG_ERR_UNSUPPORTED, "upconv_forward: width must be a power of two >= 8 (got %u)", W);
     cudaStream_t st = (cudaStream_t)stream;
     tc::ConvParams P = {};
     P.B = B; P.H = H; P.W = W; P.Cin = Cin;
     P.sy = P.sx = 2; P.out_h = 2 * H + 1; P.out_w = 2 * W + 1;
     P.ncols = Cout; P.wrows_per_sample = 9 * Cout;
-    P.NT = (Cout % 256 == 0) ? 256 : 128;
+    P.NT = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0) ? 128 : 64;
     P.epi = tc::EPI_RAW;
     P.out = t_scratch; P.ld_out = Cout;
     // class (cy, cx): T[2y' + cy, 2x' + cx] = sum over taps a = cy (mod 2), b' = cx (mod 2) of in[y' - (a - cy) / 2, x' - (b' - cx) / 2] * W[a, b']

@@ -51,7 +51,7 @@ struct ConvParams {
     uint32_t sy, sx;            // output stride (1; 2 for the transposed convolution)
     uint32_t out_h, out_w;      // output image
     uint32_t ncols;             // output columns (Cout)
-    uint32_t NT;                // N tile: 16, 128 or 256 (divides ncols)
+    uint32_t NT;                // N tile: 16 (ToRGB), 64, 128 or 256 (divides ncols)
     uint32_t bw, bh;            // pixel tile = bw x bh = 128 pixels of one sample
     uint32_t tiles_x, tiles_y;  // pixel tiles per sample
     uint32_t pairs_per_sample;  // ceil(tiles / 2): a unit = 2 adjacent pixel tiles (one per CTA) x one N tile

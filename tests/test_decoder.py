@@ -32,10 +32,11 @@ def test_decoder_oracle_matches_reference_golden():
         assert H.max_abs(img_b, z["image_buffers"]) < 2e-4 * float(np.abs(z["image_buffers"]).max())
 
 
-def _product_decoder(size, res, tab=None, seed=0):
+def _product_decoder(size, res, tab=None, seed=0, channel_multiplier=2):
     import sdface_gan_b200 as sg
     mo, _ = sg.default_options("ngp", size=size, renderer_res=res)
     mo.feature_encoder_in_channels = 256
+    mo.channel_multiplier = channel_multiplier
     dec = sg.Decoder(mo)
     if tab is not None:
         pf.fill_state(dec, tab, seed)
@@ -64,11 +65,13 @@ def test_decoder_matches_reference_golden():
 
 
 @pytest.mark.gpu
-def test_decoder_full_size_matches_oracle():
-    """BASELINE configs[2] decoder shape: [B, 256, 64, 64] features -> [B, 3, 256, 256], seeded weights with live noise / biases."""
+@pytest.mark.parametrize("channel_multiplier", [2, 1])
+def test_decoder_full_size_matches_oracle(channel_multiplier):
+    """BASELINE configs[2] decoder shape: [B, 256, 64, 64] features -> [B, 3, 256, 256], seeded weights with live noise / biases.
+    channel_multiplier 1 halves the widths (256 / 128 / 64 channels: the N = 64 tile of the conv kernel, 64-channel ToRGB and blur)."""
     import sdface_gan_b200 as sg
     torch.manual_seed(1)
-    dec = _product_decoder(256, 64)
+    dec = _product_decoder(256, 64, channel_multiplier=channel_multiplier)
     with torch.no_grad():
         for n, p in dec.named_parameters():
             if n.endswith("noise.weight"):
@@ -146,11 +149,11 @@ def _ref_weights(wf):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,Hh,Ww,Cin,Cout", [(2, 8, 8, 64, 128), (1, 16, 32, 128, 128), (3, 64, 64, 64, 256), (1, 6, 16, 64, 128)])
+@pytest.mark.parametrize("B,Hh,Ww,Cin,Cout", [(2, 8, 8, 64, 128), (1, 16, 32, 128, 128), (3, 64, 64, 64, 256), (1, 6, 16, 64, 128), (2, 16, 16, 128, 64)])
 def test_conv_and_upconv_ops_match_torch(B, Hh, Ww, Cin, Cout):
     """Operator level, against plain torch fp32 on the same fp16-rounded operands: the 3 x 3 convolution and the up-sampling layer
     (conv_transpose2d stride 2 as four parity classes + two edge strips -> blur -> noise + bias -> leaky ReLU * sqrt 2), at shapes with one
-    pixel tile per sample, odd tile counts, a height that is not a multiple of the tile height, and both N tiles (128 / 256).
+    pixel tile per sample, odd tile counts, a height that is not a multiple of the tile height, and all N tiles (64 / 128 / 256).
     Tolerance: fp16 output (+ one fp16 intermediate for the up-sampling layer): 3e-3 of the output's max."""
     import torch.nn.functional as F
     from sdface_gan_b200 import ops
