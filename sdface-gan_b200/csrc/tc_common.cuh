@@ -36,9 +36,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // waiter that found the phase incomplete sleeps until the barrier completes (or the hint elapses) instead of re-polling every ~20
 // clk.  The role threads of the chain kernels sit at the highest warp ids (issue priority): their polling loops measured 15 % of
 // all issued instructions of the forward chain (ncu source page, profiles/r02a), taken from the epilogue warps of the same SMSP.
-// rounding bit of the saved sines: 0 = off, 1 = RN vs RZ conversion, 2 = first dropped mantissa bit
+// rounding bit of the saved sines; 0 switches it off for A/B timing (scripts/gpu_r02m.sh)
 #ifndef SDFG_RBIT
-#define SDFG_RBIT 2
+#define SDFG_RBIT 1
 #endif
 #ifndef SDFG_WAIT_HINT_NS
 #define SDFG_WAIT_HINT_NS 20000
@@ -379,12 +379,6 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-// round toward zero: differs from pack_f16 exactly where round-to-nearest rounded the magnitude up
-__device__ __forceinline__ uint32_t pack_f16_rz(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rz.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
 // fp16 with saturation to +-65504 (gradients: an overflow must not become inf)

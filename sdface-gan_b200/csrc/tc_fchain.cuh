@@ -448,19 +448,16 @@ tc_fchain_fwd_kernel(const __grid_constant__ FChainMaps maps, const __grid_const
                             const uint4 h0 = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                             const uint4 h1 = make_uint4(hp[4], hp[5], hp[6], hp[7]);
                             if (do_sgn) {
-                                // rounding bits: round-to-nearest and round-toward-zero differ (by one ulp: the LSB flips) exactly where
-                                // the stored sine's magnitude was rounded UP; pair j contributes bit j (low half) and bit 16 + j (high half)
+                                // rounding bits: the fp16 conversion rounded the magnitude UP exactly where the first dropped mantissa bit (bit 12 of
+                                // the fp32 word) is set (ties and fp16 subnormals aside); pair j contributes bit j (low half) and bit 16 + j (high half)
                                 uint32_t rm = 0;
+#if SDFG_RBIT
 #pragma unroll
                                 for (int j = 0; j < 8; j++) {
-#if SDFG_RBIT == 1
-                                    rm += ((hp[j] ^ pack_f16_rz(v[2 * j], v[2 * j + 1])) & 0x00010001u) << j;
-#elif SDFG_RBIT == 2
-                                    // RN != RZ <=> the first dropped mantissa bit (bit 12 of the fp32 word) is set (ties and fp16 subnormals aside)
-                                    const uint32_t t = __byte_perm(__float_as_uint(v[2 * j]), __float_as_uint(v[2 * j + 1]), 0x5511);
+                                    const uint32_t t = __byte_perm(__float_as_uint(v[2 * j]), __float_as_uint(v[2 * j + 1]), 0x5511);   // bit 12 -> bits 4, 20
                                     rm |= (j >= 4 ? t << (j - 4) : t >> (4 - j)) & (0x00010001u << j);
-#endif
                                 }
+#endif
                                 const uint32_t plane = (sgn_m >> 16) | __byte_perm(rm, 0, 0x2044);      // [sign16 | rounding16]
                                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_u32(smSGN) + (((n & 1) * 16 + c * 4 + sb) * 128 + r) * 4), "r"(plane) : "memory");
                             }
