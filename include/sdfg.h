@@ -215,6 +215,16 @@ int sdfg_field_backward_phase(const sdfg_field_params* p, const sdfg_field_grads
                               uint64_t N, const float* d_sdf, const float* d_rgb, const float* d_feat, const float* out_feat,
                               const void* workspace, void* scratch, float* d_x_in, int precision, int phases, void* stream);
 
+/* eikonal pass (get_eikonal_term sdf_model.py:224-229 through _grid_encode.backward's grad_inputs, grid.py:77-93 / kernel_input_backward
+ * gridencoder.cu:343-369): the trunk-only backward with upstream d_sdf [N] and no parameter gradients, contracted ON CHIP with the hash
+ * encoder's dy_dx (sdfg_grid_encode_forward, [L * D * C, N] component-major, D = 3, C = 2, in_dim = L * C):
+ *     d_pts[n, d] += scale * sum_{l, c} d_x_in[n, l * C + c] * dy_dx[(l * D + d) * C + c, n]
+ * d_pts [N, 3] must be zeroed by the caller; d_x_in [N, in_dim] is never written.  Tensor-core path on shapes the two-tile chain takes
+ * (SDFG_ERR_UNSUPPORTED otherwise: run sdfg_field_backward with d_x_in and sdfg_grid_encode_backward with grad_inputs instead). */
+int sdfg_field_eikonal(const sdfg_field_params* p, const float* x_in, const float* view_feat, uint64_t N, const float* d_sdf,
+                       const void* workspace, void* scratch, const float* dy_dx, uint32_t D, uint32_t C, float scale, float* d_pts,
+                       int precision, void* stream);
+
 /* probe of the tcgen05 pipeline for the parity tests: out[M,N] (fp32) = fp16(x)[M,K] * fp16(w)[N,K]^T with fp32 accumulation.
  * N multiple of 32 in 32..256, K <= 320. */
 uint64_t sdfg_tc_linear_probe_workspace_bytes(uint32_t M, uint32_t K, uint32_t N);

@@ -15,6 +15,7 @@ SDFG_MAX_FILM = 9
 LAYOUT_NLC, LAYOUT_LNC = 0, 1
 PRECISION_FP32, PRECISION_TC16 = 0, 1
 BWD_CHAIN, BWD_WGRAD, BWD_BOTH = 1, 2, 3
+ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA = -1, -2, -3
 
 c_f = ctypes.POINTER(ctypes.c_float)
 vp = ctypes.c_void_p
@@ -62,6 +63,7 @@ PROTOTYPES = {
                                   vp, i32, vp]),
     "sdfg_field_backward_phase": (i32, [ctypes.POINTER(FieldParams), ctypes.POINTER(FieldGrads), vp, vp, u64, vp, vp, vp, vp, vp, vp,
                                         vp, i32, i32, vp]),
+    "sdfg_field_eikonal": (i32, [ctypes.POINTER(FieldParams), vp, vp, u64, vp, vp, vp, vp, u32, u32, ctypes.c_float, vp, i32, vp]),
     "sdfg_field_backward_2s": (i32, [ctypes.POINTER(FieldParams), ctypes.POINTER(FieldGrads), vp, vp, u64, vp, vp, vp, vp, vp, vp,
                                      vp, i32, vp, vp]),
     "sdfg_tc_linear_probe_workspace_bytes": (u64, [u32, u32, u32]),

@@ -75,3 +75,16 @@ extern "C" int sdfg_field_backward_2s(const sdfg_field_params* p, const sdfg_fie
     SDFG_REQUIRE(x_in && workspace && scratch, SDFG_ERR_INVALID, "field_backward: null pointer");
     return field_backward_tc(p, g, x_in, view_feat, N, d_sdf, d_rgb, d_feat, workspace, scratch, d_x_in, (cudaStream_t)stream, (cudaStream_t)wgrad_stream);
 }
+
+extern "C" int sdfg_field_eikonal(const sdfg_field_params* p, const float* x_in, const float* view_feat, uint64_t N, const float* d_sdf,
+                                  const void* workspace, void* scratch, const float* dy_dx, uint32_t D, uint32_t C, float scale, float* d_pts,
+                                  int precision, void* stream) {
+    SDFG_REQUIRE(precision == SDFG_PRECISION_TC16, SDFG_ERR_UNSUPPORTED, "field_eikonal: tensor-core path only (use sdfg_field_backward + sdfg_grid_encode_backward)");
+    SDFG_REQUIRE(D == 3 && C == 2, SDFG_ERR_UNSUPPORTED, "field_eikonal: 3-D points and 2 features per level (got D = %u, C = %u)", D, C);
+    if (int e = field_check_params(p, N)) return e;
+    if (N == 0) return SDFG_OK;
+    SDFG_REQUIRE(x_in && workspace && scratch && d_sdf && dy_dx && d_pts, SDFG_ERR_INVALID, "field_eikonal: null pointer");
+    const EikFuse eik = {dy_dx, d_pts, scale};
+    return field_backward_tc(p, nullptr, x_in, view_feat, N, d_sdf, nullptr, nullptr, workspace, scratch, nullptr, (cudaStream_t)stream,
+                             (cudaStream_t)stream, SDFG_BWD_BOTH, &eik);
+}

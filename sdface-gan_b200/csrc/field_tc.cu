@@ -167,7 +167,7 @@ static bool chain_eligible(const sdfg_field_params* p, bool want_views) {
     return n_main <= tc::CH_MAX_MAPS;
 }
 
-static bool bchain_eligible(const sdfg_field_params* p, const float* d_x_in) {
+static bool bchain_eligible(const sdfg_field_params* p, bool d_x_in) {
     if (p->width != 256 || p->n_film < 1 || p->n_film + 1 > tc::BC_MAX_LAYERS) return false;
     if (p->has_input_linear && (p->in_dim % 16 != 0 || p->in_dim > 256)) return false;
     if (d_x_in && !p->has_input_linear) return false;
@@ -697,11 +697,14 @@ uint64_t field_backward_scratch_bytes_tc(const sdfg_field_params* p, uint64_t N)
 
 int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, const float* x_in, const float* view_feat, uint64_t N,
                       const float* d_sdf, const float* d_rgb, const float* d_feat, const void* workspace, void* scratch, float* d_x_in,
-                      cudaStream_t st, cudaStream_t st_w, int phases) {
+                      cudaStream_t st, cudaStream_t st_w, int phases, const EikFuse* eik) {
     (void)x_in; (void)view_feat;
     if (int e = check_tc(p, N)) return e;
+    SDFG_REQUIRE(!eik || (!g && !d_x_in && eik->dy_dx && eik->d_pts && p->in_dim % 16 == 0), SDFG_ERR_INVALID,
+                 "field_eikonal: no parameter gradients / d_x_in next to the fused contraction; in_dim must be a multiple of 16");
+    const bool want_dx = d_x_in || eik;
     SDFG_REQUIRE(d_sdf || d_rgb || d_feat, SDFG_ERR_INVALID, "field_backward: no output gradient given");
-    SDFG_REQUIRE(!d_x_in || (p->has_input_linear && p->in_dim % 32 == 0), SDFG_ERR_UNSUPPORTED,
+    SDFG_REQUIRE(!want_dx || (p->has_input_linear && p->in_dim % 32 == 0), SDFG_ERR_UNSUPPORTED,
                  "tc field_backward: d_x_in needs an input_linear layer and in_dim %% 32 == 0");
     SDFG_REQUIRE(phases & SDFG_BWD_BOTH, SDFG_ERR_INVALID, "field_backward: no phase requested");
     const TcLayout L = tc_layout(p, N, 1);
@@ -724,7 +727,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
     auto layer_Kx = [&](uint32_t l) { return l == nf ? W + p->view_dim : ((l == 0 && !p->has_input_linear) ? p->in_dim : W); };
 
     const bool has_views = d_rgb || d_feat;
-    if (chain_enabled() && bchain_eligible(p, d_x_in) && chain_eligible(p, true)) {
+    if (chain_enabled() && bchain_eligible(p, want_dx) && chain_eligible(p, true)) {
         // ---------------------------------------------------------------- backward chain on the saved activations + sign planes (tc_bchain2.cuh)
         // (chain_eligible(with views): whatever outputs the forward produced, it was the fused chain -- the one that saves the sign planes)
         const bool store = g != nullptr;
@@ -733,7 +736,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
             const bool collapse = collapse_enabled(p);
             // not collapsed: the bottom layer's D GEMM yields dh_0 for the input stage d x_in = dh_0 W_in and for input_linear's weight
             // gradient.  Collapsed: no D GEMM for the bottom layer; d x_in = du_0 (gamma_b o W10) straight from its gradient tile.
-            const bool need_dh0 = !collapse && p->has_input_linear && (d_x_in || (g && g->input_w));
+            const bool need_dh0 = !collapse && p->has_input_linear && (want_dx || (g && g->input_w));
             static const int cg_env = []() { const char* e = getenv("SDFG_TC_CG"); return e ? atoi(e) : 2; }();
             const int cg = (cg_env == 2 && spi % 256 == 0 && (N / tc::CH_TILE_M) % 2 == 0 && (!p->has_input_linear || p->in_dim % 32 == 0)) ? 2 : 1;
             const uint32_t wrows = 256 / cg;
@@ -774,14 +777,16 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
             P.n_layers = nl;
             if (need_dh0) {
                 P.has_in = 1; P.in_dim = p->in_dim; P.d_x_in = d_x_in;
+                if (eik) { P.eik_dydx = eik->dy_dx; P.eik_out = eik->d_pts; P.eik_scale = eik->scale; }
                 h16* wgt_in = (h16*)(sc + SC.off_wgt_in);
                 wgt_kernel<<<dim3(p->in_dim, 1), 256, 0, st>>>(p->input_w, p->in_dim, nullptr, 0, wgt_in, p->in_dim, 1);
                 if (int e = check_launch("wgt_kernel")) return e;
                 if (int e = make_tensor_map_16(&maps->wgt_in, wgt_in, p->in_dim, W, W, p->in_dim / cg, 64, tc::FMT_F16)) return e;
                 if (store)
                     if (int e = make_tensor_map_16(&maps->dh0, DH, N, W, W, tc::CH_TILE_M, 64, tc::FMT_F16)) return e;
-            } else if (collapse && d_x_in) {
+            } else if (collapse && want_dx) {
                 P.has_in = 1; P.in_per_image = 1; P.in_dim = p->in_dim; P.d_x_in = d_x_in;
+                if (eik) { P.eik_dydx = eik->dy_dx; P.eik_out = eik->d_pts; P.eik_scale = eik->scale; }
                 h16* wgt_in = (h16*)(sc + SC.off_wgt_in);
                 wgt_kernel<<<dim3(p->in_dim, B), 256, 0, st>>>((const float*)(ws + L.off_w10), p->in_dim, p->gamma, gstride, wgt_in, p->in_dim, B);
                 if (int e = check_launch("wgt_kernel")) return e;
@@ -795,6 +800,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
             // them.  SDFG_TC_PP=0 never, =2 always.
             static const int pp_env = []() { const char* e = getenv("SDFG_TC_PP"); return e ? atoi(e) : 1; }();
             const bool pingpong = cg == 2 && (pp_env == 2 || (pp_env == 1 && !store));
+            SDFG_REQUIRE(!eik || pingpong, SDFG_ERR_UNSUPPORTED, "field_eikonal: the fused contraction lives in the two-tile chain (CTA pairs, no stores)");
             const uint32_t smem = pingpong ? tc::bchain3_smem_bytes() : tc::bchain2_smem_bytes(cg);
             typedef void (*b2kern_t)(const tc::B2ChainMaps, const tc::B2ChainParams);
             const b2kern_t kern = pingpong ? (store ? (b2kern_t)tc::tc_chain_bwd3_kernel<true> : (b2kern_t)tc::tc_chain_bwd3_kernel<false>)
@@ -872,6 +878,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
     // ---------------------------------------------------------------- per-layer kernels (tc_layer.cuh): shapes the fused chains do not
     // take (in_dim > 32, view_dim > 16, SDFG_TC_CHAIN=0).  Gradient GEMMs and weight gradients interleave layer by layer, so the two
     // phases cannot be separated: everything runs in the call that carries SDFG_BWD_CHAIN.
+    SDFG_REQUIRE(!eik, SDFG_ERR_UNSUPPORTED, "field_eikonal: the fused contraction needs the chain kernels (this shape runs per layer)");
     if (!(phases & SDFG_BWD_CHAIN)) return SDFG_OK;
     if (int e = compute_loss_scale(d_sdf, N, d_rgb, N * 3, d_feat, N * 256, (uint32_t*)(sc + SC.off_scale), gscale, st)) return e;
     // R: DZ = dh * cos(z_l), z recomputed from A_l

@@ -54,6 +54,11 @@ struct B2ChainParams {
     const float* top_rank_s;
     const float* top_dfeat;             // fp32 [M, 256] or NULL
     float* d_x_in;
+    // eikonal pass: instead of writing d_x_in [M, in_dim], contract it with the hash encoder's dy_dx ([in_dim / 2 levels][3][2][M], component
+    // major) in the input-stage epilogue: eik_out[row, d] += eik_scale * sum_j d_x_in[row, j] dy_dx[level(j), d, c(j)][row]   (tc_bchain3 only)
+    const float* eik_dydx;
+    float* eik_out;                     // [M, 3], pre-zeroed (each row receives in_dim / 16 partial sums)
+    float eik_scale;
     const float* gscale;                // {s, 1/s}
     const float* vecs[4];               // 0 = w_sigma, 1..3 = w_rgb rows
     unsigned long long* dbg;

@@ -289,6 +289,19 @@ tc_chain_bwd3_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
             const float rsA[3] = {gs * rA[0], gs * rA[1], gs * rA[2]}, rsB[3] = {gs * rB[0], gs * rB[1], gs * rB[2]};
             const float dsA = gs * dA, dsB = gs * dB;
             if (p + 1 < n_pairs) fetch_pair(p + 1);
+            if (P.eik_out) {
+                // the input-stage epilogue of this pair will read 48 dy_dx lines per thread: pull the tiles' 3 * in_dim component rows
+                // (512 bytes each) into L2 now, a whole chain ahead
+                const uint32_t tid = warp * 32 + lane;
+                for (uint32_t s = 0; s < n_act; s++) {
+                    const uint64_t row0 = (uint64_t)((u_begin + 2 * p + s) * CG + rank) * CH_TILE_M;
+                    for (uint32_t li = tid; li < P.in_dim * 3 * 4; li += CH_EPI_WARPS * 32) {
+                        const uint64_t col = row0 + (li & 3) * 32;
+                        if (col < P.M_total)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.eik_dydx + (size_t)(li >> 2) * P.M_total + col));
+                    }
+                }
+            }
             for (uint32_t e = 0; e < n_ev; e++)
                 for (uint32_t s = 0; s < n_act; s++) {
                     const uint32_t t = (u_begin + 2 * p + s) * CG + rank;
@@ -372,7 +385,29 @@ tc_chain_bwd3_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
                     const uint32_t n_acc = p * n_gemm + (n_gemm - 1);
                     mbar_wait(&S.acc_full[s], n_acc & 1);
                     tc_fence_after();
-                    if (sb * 16 < P.in_dim && P.d_x_in) {               // warp-uniform: tcgen05.ld is a whole-warp instruction
+                    if (sb * 16 < P.in_dim && P.eik_out) {              // eikonal pass: d sdf / d point without the [M, in_dim] round trip
+                        uint32_t raw[16];
+                        tmem_ld16(tmem_base + lane_base + s * 256 + sb * 16, raw);
+                        tmem_ld_wait();
+                        if (row < P.M_total) {
+                            // this thread's 16 columns = 8 levels x 2 features; per level the 6 components (d, c) of dy_dx are rows of a
+                            // component-major matrix: lanes = consecutive samples, every load a full 128-byte line
+                            const float* q = P.eik_dydx + (size_t)(sb * 8) * 6 * P.M_total + row;
+                            float dv[48];
+#pragma unroll
+                            for (int i = 0; i < 48; i++) dv[i] = __ldg(q + (size_t)i * P.M_total);
+                            float e[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int l = 0; l < 8; l++) {
+                                const float a0 = __uint_as_float(raw[2 * l]), a1 = __uint_as_float(raw[2 * l + 1]);
+#pragma unroll
+                                for (int d = 0; d < 3; d++) e[d] = fmaf(a1, dv[l * 6 + d * 2 + 1], fmaf(a0, dv[l * 6 + d * 2], e[d]));
+                            }
+                            const float k = gs_inv * P.eik_scale;
+#pragma unroll
+                            for (int d = 0; d < 3; d++) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(P.eik_out + row * 3 + d), "f"(e[d] * k) : "memory");
+                        }
+                    } else if (sb * 16 < P.in_dim && P.d_x_in) {        // warp-uniform: tcgen05.ld is a whole-warp instruction
                         uint32_t raw[16];
                         tmem_ld16(tmem_base + lane_base + s * 256 + sb * 16, raw);
                         tmem_ld_wait();

@@ -4,6 +4,7 @@ Every function here takes CUDA float32 tensors, calls exactly one C entry point 
 RuntimeError on a non-zero status.  Nothing in this module (or anywhere in the package) computes on the CPU.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -281,6 +282,29 @@ def field_backward(spec, x_in, view_feat, gamma, beta, weights, samples_per_imag
                                            _ptr(out_feat), _ptr(workspace), _ptr(scratch), _ptr(dx), int(precision), _stream()),
                    "sdfg_field_backward")
     return dx
+
+
+def field_eikonal(spec, x_in, view_feat, gamma, beta, weights, samples_per_image, samples_per_ray, workspace, d_sdf, dy_dx, scale,
+                  precision=_lib.PRECISION_TC16):
+    """The eikonal pass with the encoder's chain rule fused in (sdfg_field_eikonal): d sdf / d point [N,3] from the saved forward state
+    and dy_dx [L*3*2, N], without materialising d sdf / d feature [N,in_dim].  Returns None when the shape / precision has no fused
+    kernel (the caller then runs field_backward(want_dx=True) + grid_encode_backward(want_grad_inputs=True))."""
+    lib = _lib.load()
+    if int(precision) != _lib.PRECISION_TC16 or dy_dx is None or dy_dx.shape[0] * 2 != spec.in_dim * 6 or os.environ.get("SDFG_EIK_FUSE", "1") == "0":
+        return None
+    N = x_in.shape[0]
+    dev = x_in.device
+    p = _field_params(spec, samples_per_image, samples_per_ray, gamma, beta, weights)
+    nbytes = int(lib.sdfg_field_backward_scratch_bytes(ctypes.byref(p), N, int(precision)))
+    scratch = torch.empty(max(nbytes, 16) // 4, device=dev, dtype=torch.float32)
+    d_pts = torch.zeros(N, 3, device=dev)
+    with torch.cuda.device(dev):
+        code = lib.sdfg_field_eikonal(ctypes.byref(p), _ptr(x_in), _ptr(view_feat), N, _ptr(_chk(d_sdf, "d_sdf")), _ptr(workspace), _ptr(scratch),
+                                      _ptr(_chk(dy_dx, "dy_dx")), 3, 2, float(scale), _ptr(d_pts), int(precision), _stream())
+    if code == _lib.ERR_UNSUPPORTED:
+        return None
+    _lib.check(code, "sdfg_field_eikonal")
+    return d_pts
 
 
 def tc_linear_probe(x, w):

@@ -112,18 +112,22 @@ class _field(Function):
         if meta["want_dsdf"]:
             # d sdf / d x_in for the eikonal term (ref get_eikonal_term :224-229): a trunk-only backward with d_sdf = 1
             ones = torch.ones_like(sdf)
-            dsdf = ops.field_backward(spec, x_in, view_feat, gamma, beta, weights, meta["spi"], meta["spr"], ws, feat, ones, None, None,
-                                      grads=None, want_dx=True, precision=meta["precision"])
+            eik = meta.get("eik")
+            if eik is not None:
+                # hash-grid field: the encoder's chain rule (d feature / d point, dy_dx) is applied inside the chain's last epilogue --
+                # d sdf / d point [N,3] comes back directly, d sdf / d feature [N,32] never exists.  None = no fused kernel for this shape.
+                dsdf = ops.field_eikonal(spec, x_in, view_feat, gamma, beta, weights, meta["spi"], meta["spr"], ws, ones, eik["dy_dx"],
+                                         eik["scale"], precision=meta["precision"])
+            if dsdf is None:
+                dsdf = ops.field_backward(spec, x_in, view_feat, gamma, beta, weights, meta["spi"], meta["spr"], ws, feat, ones, None, None,
+                                          grads=None, want_dx=True, precision=meta["precision"])
         if need_bwd:
             ctx.save_for_backward(x_in, view_feat, gamma, beta, feat, ws, emb, *wts)
         ctx.spec, ctx.meta = spec, meta
         empty = x_in.new_empty(0)
         outs = (sdf, rgb if rgb is not None else empty, feat if feat is not None else empty, dsdf if dsdf is not None else empty)
-        ctx.mark_non_differentiable(outs[3])
-        if rgb is None:
-            ctx.mark_non_differentiable(outs[1])
-        if feat is None:
-            ctx.mark_non_differentiable(outs[2])
+        # one call: mark_non_differentiable REPLACES the set on every call.  dsdf is constant w.r.t. the parameters (SURVEY finding 4)
+        ctx.mark_non_differentiable(*([outs[3]] + ([outs[1]] if rgb is None else []) + ([outs[2]] if feat is None else [])))
         return outs
 
     @staticmethod
@@ -263,14 +267,14 @@ class _FieldNetwork(nn.Module):
         return out[:, 0], out[:, 1]                                      # gamma, beta: [B, n+1, W] (made contiguous by the field node)
 
     def _run_field(self, x_in, view_feat, styles, samples_per_image, samples_per_ray, want_rgb=True, want_feat=True, want_dsdf=False,
-                   feat_f16=False, emb=None, grid=None):
+                   feat_f16=False, emb=None, grid=None, eik=None):
         spec = self._spec
         gamma, beta = self._modulation(styles)
         want_dx = bool(want_dsdf) or (torch.is_grad_enabled() and x_in.requires_grad)
         meta = dict(spi=int(samples_per_image), spr=int(samples_per_ray), want_rgb=bool(want_rgb), want_feat=bool(want_feat),
                     want_dsdf=bool(want_dsdf), precision=self._pick_precision(int(samples_per_image), want_dx),
                     grad=torch.is_grad_enabled(), feat_f16=bool(feat_f16), grid=grid,   # Function.forward itself always runs with grad mode off
-                    exchange=self._table_exchange)
+                    exchange=self._table_exchange, eik=eik if want_dsdf else None)
         sdf, rgb, feat, dsdf = _field.apply(spec, meta, x_in, view_feat, gamma, beta, emb, *_pack_weights(spec, self))
         return sdf, (rgb if rgb.numel() else None), (feat if feat.numel() else None), (dsdf if dsdf.numel() else None)
 
@@ -287,14 +291,18 @@ class _FieldNetwork(nn.Module):
             out.append(feat)
         return torch.cat(out, -1).view(prefix + [-1])
 
+    def _eikonal_fusion(self, grid_ctx):
+        """what the field node needs to apply the encoder's chain rule itself (None: the caller does it in _dsdf_to_points)"""
+        return None
+
     def forward_rays(self, npts, viewdirs, styles, want_rgb=True, want_feat=True, want_dsdf=False, feat_f16=False):
         """Renderer entry: npts [B,R,R,S,3], viewdirs [B,R,R,3] (one per ray) -> (sdf [N], rgb [N,3], feat [N,W], dsdf_dnpts [N,3])."""
         B, R1, R2, S, _ = npts.shape
         flat = npts.reshape(-1, 3)
         x_in, view_feat, grid_ctx, emb, grid = self._encode_rays(flat, viewdirs.reshape(-1, 3), want_dsdf)
         sdf, rgb, feat, dsdf = self._run_field(x_in, view_feat, styles, R1 * R2 * S, S, want_rgb, want_feat, want_dsdf, feat_f16,
-                                               emb=emb, grid=grid)
-        if want_dsdf:
+                                               emb=emb, grid=grid, eik=self._eikonal_fusion(grid_ctx))
+        if want_dsdf and not (grid_ctx is not None and dsdf.shape[1] == 3):      # [N,3] from a hash-grid field: the chain rule was fused in
             dsdf = self._dsdf_to_points(dsdf, flat, grid_ctx)
         return sdf, rgb, feat, dsdf
 
@@ -402,6 +410,12 @@ class NGPSIRENGenerator(_FieldNetwork):
                                                    interp=grid["interp"])
             sh = self.encoder_dir(ray_dirs)
         return feats, sh, dy_dx, enc.embeddings, grid
+
+    def _eikonal_fusion(self, grid_ctx):
+        enc = self.encoder
+        if grid_ctx is None or enc.input_dim != 3 or enc.level_dim != 2:
+            return None
+        return dict(dy_dx=grid_ctx, scale=1.0 / (2.0 * float(self.bound)))      # the 1 / (2 bound) of the affine map folded into the encoder (grid.py:149)
 
     def _dsdf_to_points(self, dsdf, flat_pts, dy_dx):
         enc = self.encoder

@@ -250,3 +250,20 @@ def test_tc_training_step_small_and_ragged_shapes(B, R, S):
     assert set(g0) == set(g1)
     worst = max((H.rel_err(g1[n], g0[n]), n) for n in g0 if g0[n].abs().max() > 0)
     assert worst[0] < 2e-2, worst
+
+
+def test_fused_eikonal_contraction_matches_the_two_kernel_form(monkeypatch):
+    """sdfg_field_eikonal applies the hash encoder's chain rule (dy_dx) inside the eikonal chain's last epilogue; SDFG_EIK_FUSE=0 runs the
+    older form -- d sdf / d feature [N,32] written by the chain, contracted by grid_input_backward_kernel.  Same arithmetic up to the
+    order of one fp32 sum: 1e-5 relative.  The eikonal term stays detached from the parameters (ngp mode, SURVEY finding 4)."""
+    z = H.load_fixture("ngp_train")
+    inp = H.fixture_inputs(z, DEV)
+    g = H.product_generator(z, DEV, precision="tc16")
+    res = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("SDFG_EIK_FUSE", fuse)
+        out = g([inp["z"]], inp["cam"], inp["focal"], inp["near"], inp["far"], t_rand=inp["t_rand"], return_sdf=True, return_eikonal=True)
+        res[fuse] = out[3].detach().clone()
+        assert not out[3].requires_grad
+    assert torch.isfinite(res["1"]).all() and float(res["0"].abs().max()) > 0
+    assert H.rel_err(res["1"], res["0"]) < 1e-5
