@@ -15,6 +15,20 @@ tag = sys.argv[1]
 out = []
 
 lp = os.path.join(ROOT, "gpurun_out", "launches_%s.csv" % tag)
+lall = os.path.join(ROOT, "gpurun_out", "launches_all_%s.csv" % tag)
+if os.path.exists(lall):
+    # the whole run (several steps / passes): keep the LAST one, cut at its sample_rays_kernel launch -- the first kernel of the path; the
+    # few host-side torch kernels before it (latent mapping) are taken from the previous step so that the list still holds one full step
+    rows = [r for r in csv.reader(l for l in open(lall) if not l.startswith("=="))]
+    hdr, body = rows[0], [r for r in rows[1:] if len(r) == len(rows[0])]
+    ki = hdr.index("Kernel Name")
+    marks = [i for i, r in enumerate(body) if "sample_rays_kernel" in r[ki]]
+    if len(marks) >= 2:
+        per = marks[-1] - marks[-2]
+        with open(lp, "w") as fh:
+            w = csv.writer(fh, quoting=csv.QUOTE_ALL)
+            w.writerow(hdr)
+            w.writerows(body[len(body) - per:])
 if os.path.exists(lp):
     rows = list(csv.reader(l for l in open(lp) if not l.startswith("==")))
     hdr = rows[0]
