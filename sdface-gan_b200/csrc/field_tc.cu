@@ -700,8 +700,8 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
                       cudaStream_t st, cudaStream_t st_w, int phases, const EikFuse* eik) {
     (void)x_in; (void)view_feat;
     if (int e = check_tc(p, N)) return e;
-    SDFG_REQUIRE(!eik || (!g && !d_x_in && eik->dy_dx && eik->d_pts && p->in_dim % 16 == 0), SDFG_ERR_INVALID,
-                 "field_eikonal: no parameter gradients / d_x_in next to the fused contraction; in_dim must be a multiple of 16");
+    SDFG_REQUIRE(!eik || (!g && !d_x_in && eik->dy_dx && eik->d_pts), SDFG_ERR_INVALID, "field_eikonal: no parameter gradients / d_x_in next to the fused contraction");
+    SDFG_REQUIRE(!eik || p->in_dim == 32, SDFG_ERR_UNSUPPORTED, "field_eikonal: the fused contraction is built for 16 levels x 2 features (in_dim = 32, got %u)", p->in_dim);
     const bool want_dx = d_x_in || eik;
     SDFG_REQUIRE(d_sdf || d_rgb || d_feat, SDFG_ERR_INVALID, "field_backward: no output gradient given");
     SDFG_REQUIRE(!want_dx || (p->has_input_linear && p->in_dim % 32 == 0), SDFG_ERR_UNSUPPORTED,

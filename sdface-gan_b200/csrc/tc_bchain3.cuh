@@ -385,21 +385,24 @@ tc_chain_bwd3_kernel(const __grid_constant__ B2ChainMaps maps, const __grid_cons
                     const uint32_t n_acc = p * n_gemm + (n_gemm - 1);
                     mbar_wait(&S.acc_full[s], n_acc & 1);
                     tc_fence_after();
-                    if (sb * 16 < P.in_dim && P.eik_out) {              // eikonal pass: d sdf / d point without the [M, in_dim] round trip
+                    if (P.eik_out) {
+                        // eikonal pass: d sdf / d point without the [M, in_dim] round trip.  The four warps of a row quarter split the
+                        // 32 columns (the host admits in_dim = 32 only): warp sb takes 8 of them = 4 levels x 2 features
+                        const uint32_t c0 = (sb & 1) * 16, half = (sb >> 1) * 8;
                         uint32_t raw[16];
-                        tmem_ld16(tmem_base + lane_base + s * 256 + sb * 16, raw);
+                        tmem_ld16(tmem_base + lane_base + s * 256 + c0, raw);
                         tmem_ld_wait();
                         if (row < P.M_total) {
-                            // this thread's 16 columns = 8 levels x 2 features; per level the 6 components (d, c) of dy_dx are rows of a
-                            // component-major matrix: lanes = consecutive samples, every load a full 128-byte line
-                            const float* q = P.eik_dydx + (size_t)(sb * 8) * 6 * P.M_total + row;
-                            float dv[48];
+                            // per level the 6 components (d, c) of dy_dx are rows of a component-major matrix: lanes = consecutive
+                            // samples, every load a full 128-byte line
+                            const float* q = P.eik_dydx + (size_t)((c0 + half) / 2) * 6 * P.M_total + row;
+                            float dv[24];
 #pragma unroll
-                            for (int i = 0; i < 48; i++) dv[i] = __ldg(q + (size_t)i * P.M_total);
+                            for (int i = 0; i < 24; i++) dv[i] = __ldg(q + (size_t)i * P.M_total);
                             float e[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-                            for (int l = 0; l < 8; l++) {
-                                const float a0 = __uint_as_float(raw[2 * l]), a1 = __uint_as_float(raw[2 * l + 1]);
+                            for (int l = 0; l < 4; l++) {
+                                const float a0 = __uint_as_float(half ? raw[8 + 2 * l] : raw[2 * l]), a1 = __uint_as_float(half ? raw[9 + 2 * l] : raw[2 * l + 1]);
 #pragma unroll
                                 for (int d = 0; d < 3; d++) e[d] = fmaf(a1, dv[l * 6 + d * 2 + 1], fmaf(a0, dv[l * 6 + d * 2], e[d]));
                             }
