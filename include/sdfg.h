@@ -193,15 +193,7 @@ int sdfg_field_backward(const sdfg_field_params* p, const sdfg_field_grads* g, c
                         uint64_t N, const float* d_sdf, const float* d_rgb, const float* d_feat, const float* out_feat,
                         const void* workspace, void* scratch, float* d_x_in, int precision, void* stream);
 
-/* two-stream variant (tensor-core path): d_x_in is complete on `stream` when the call returns to the host's stream order, while the
- * parameter gradients (g) are produced on `wgrad_stream`, which the library makes wait for the gradient chain.  The caller may
- * enqueue work that only needs d_x_in on `stream` (the hash-grid scatter) and must make `stream` wait for `wgrad_stream` before
- * g, scratch or the upstream gradients are reused.  Falls back to sdfg_field_backward for fp32 or a NULL wgrad_stream. */
-int sdfg_field_backward_2s(const sdfg_field_params* p, const sdfg_field_grads* g, const float* x_in, const float* view_feat,
-                           uint64_t N, const float* d_sdf, const float* d_rgb, const float* d_feat, const float* out_feat,
-                           const void* workspace, void* scratch, float* d_x_in, int precision, void* stream, void* wgrad_stream);
-
-/* two-call variant (the two-stream variant's ordering on ONE stream): `phases` selects SDFG_BWD_CHAIN (loss scale, gradient chain
+/* two-call variant: `phases` selects SDFG_BWD_CHAIN (loss scale, gradient chain
  * through the layers -> d_x_in, and the gradient tiles the second phase reads from `scratch`), SDFG_BWD_WGRAD (parameter
  * gradients into g) or both.  A data-parallel caller runs CHAIN, enqueues the hash-table scatter of d_x_in, starts the
  * all-reduce of the table gradient and then calls WGRAD with the same arguments: the exchange overlaps the weight-gradient

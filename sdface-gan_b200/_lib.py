@@ -64,8 +64,6 @@ PROTOTYPES = {
     "sdfg_field_backward_phase": (i32, [ctypes.POINTER(FieldParams), ctypes.POINTER(FieldGrads), vp, vp, u64, vp, vp, vp, vp, vp, vp,
                                         vp, i32, i32, vp]),
     "sdfg_field_eikonal": (i32, [ctypes.POINTER(FieldParams), vp, vp, u64, vp, vp, vp, vp, u32, u32, ctypes.c_float, vp, i32, vp]),
-    "sdfg_field_backward_2s": (i32, [ctypes.POINTER(FieldParams), ctypes.POINTER(FieldGrads), vp, vp, u64, vp, vp, vp, vp, vp, vp,
-                                     vp, i32, vp, vp]),
     "sdfg_tc_linear_probe_workspace_bytes": (u64, [u32, u32, u32]),
     "sdfg_tc_linear_probe": (i32, [vp, vp, vp, u32, u32, u32, vp, vp]),
     "sdfg_tc_wgrad_probe": (i32, [vp, vp, vp, u32, u32, u32, u32, ctypes.POINTER(u32), ctypes.POINTER(u32), vp, vp]),

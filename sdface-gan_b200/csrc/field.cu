@@ -47,7 +47,7 @@ extern "C" int sdfg_field_backward(const sdfg_field_params* p, const sdfg_field_
     if (precision == SDFG_PRECISION_FP32)
         return field_backward_f32(p, g, x_in, view_feat, N, d_sdf, d_rgb, d_feat, out_feat, workspace, scratch, d_x_in, (cudaStream_t)stream);
     if (precision == SDFG_PRECISION_TC16)
-        return field_backward_tc(p, g, x_in, view_feat, N, d_sdf, d_rgb, d_feat, workspace, scratch, d_x_in, (cudaStream_t)stream, (cudaStream_t)stream);
+        return field_backward_tc(p, g, x_in, view_feat, N, d_sdf, d_rgb, d_feat, workspace, scratch, d_x_in, (cudaStream_t)stream);
     return set_error(SDFG_ERR_UNSUPPORTED, "field_backward: unknown precision %d", precision);
 }
 
@@ -62,18 +62,7 @@ extern "C" int sdfg_field_backward_phase(const sdfg_field_params* p, const sdfg_
     if (int e = field_check_params(p, N)) return e;
     if (N == 0) return SDFG_OK;
     SDFG_REQUIRE(x_in && workspace && scratch, SDFG_ERR_INVALID, "field_backward: null pointer");
-    return field_backward_tc(p, g, x_in, view_feat, N, d_sdf, d_rgb, d_feat, workspace, scratch, d_x_in, (cudaStream_t)stream, (cudaStream_t)stream, phases);
-}
-
-extern "C" int sdfg_field_backward_2s(const sdfg_field_params* p, const sdfg_field_grads* g, const float* x_in, const float* view_feat,
-                                      uint64_t N, const float* d_sdf, const float* d_rgb, const float* d_feat, const float* out_feat,
-                                      const void* workspace, void* scratch, float* d_x_in, int precision, void* stream, void* wgrad_stream) {
-    if (precision != SDFG_PRECISION_TC16 || !wgrad_stream)
-        return sdfg_field_backward(p, g, x_in, view_feat, N, d_sdf, d_rgb, d_feat, out_feat, workspace, scratch, d_x_in, precision, stream);
-    if (int e = field_check_params(p, N)) return e;
-    if (N == 0) return SDFG_OK;
-    SDFG_REQUIRE(x_in && workspace && scratch, SDFG_ERR_INVALID, "field_backward: null pointer");
-    return field_backward_tc(p, g, x_in, view_feat, N, d_sdf, d_rgb, d_feat, workspace, scratch, d_x_in, (cudaStream_t)stream, (cudaStream_t)wgrad_stream);
+    return field_backward_tc(p, g, x_in, view_feat, N, d_sdf, d_rgb, d_feat, workspace, scratch, d_x_in, (cudaStream_t)stream, phases);
 }
 
 extern "C" int sdfg_field_eikonal(const sdfg_field_params* p, const float* x_in, const float* view_feat, uint64_t N, const float* d_sdf,
@@ -86,5 +75,5 @@ extern "C" int sdfg_field_eikonal(const sdfg_field_params* p, const float* x_in,
     SDFG_REQUIRE(x_in && workspace && scratch && d_sdf && dy_dx && d_pts, SDFG_ERR_INVALID, "field_eikonal: null pointer");
     const EikFuse eik = {dy_dx, d_pts, scale};
     return field_backward_tc(p, nullptr, x_in, view_feat, N, d_sdf, nullptr, nullptr, workspace, scratch, nullptr, (cudaStream_t)stream,
-                             (cudaStream_t)stream, SDFG_BWD_BOTH, &eik);
+                             SDFG_BWD_BOTH, &eik);
 }

@@ -27,6 +27,6 @@ struct EikFuse {
 };
 int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, const float* x_in, const float* view_feat, uint64_t N,
                       const float* d_sdf, const float* d_rgb, const float* d_feat, const void* workspace, void* scratch, float* d_x_in,
-                      cudaStream_t st, cudaStream_t st_w, int phases = SDFG_BWD_BOTH, const EikFuse* eik = nullptr);
+                      cudaStream_t st, int phases = SDFG_BWD_BOTH, const EikFuse* eik = nullptr);
 
 }  // namespace sdfg

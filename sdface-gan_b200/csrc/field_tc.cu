@@ -697,7 +697,7 @@ uint64_t field_backward_scratch_bytes_tc(const sdfg_field_params* p, uint64_t N)
 
 int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, const float* x_in, const float* view_feat, uint64_t N,
                       const float* d_sdf, const float* d_rgb, const float* d_feat, const void* workspace, void* scratch, float* d_x_in,
-                      cudaStream_t st, cudaStream_t st_w, int phases, const EikFuse* eik) {
+                      cudaStream_t st, int phases, const EikFuse* eik) {
     (void)x_in; (void)view_feat;
     if (int e = check_tc(p, N)) return e;
     SDFG_REQUIRE(!eik || (!g && !d_x_in && eik->dy_dx && eik->d_pts), SDFG_ERR_INVALID, "field_eikonal: no parameter gradients / d_x_in next to the fused contraction");
@@ -822,16 +822,7 @@ int field_backward_tc(const sdfg_field_params* p, const sdfg_field_grads* g, con
         if (!g || !(phases & SDFG_BWD_WGRAD)) return SDFG_OK;
         // ---- parameter gradients from the stored du tiles (sample-axis contractions) and the fp32 head gradients.  They only depend
         // on the chain's outputs, and the caller's next step (hash-grid scatter of d_x_in) does not depend on them: a caller may run
-        // them as a second call (phases = SDFG_BWD_WGRAD) after it has enqueued the scatter and started the table-gradient exchange,
-        // or on a second stream (st_w).
-        if (st_w != st) {
-            cudaEvent_t ev;
-            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return set_error(SDFG_ERR_CUDA, "field_backward: event");
-            cudaEventRecord(ev, st);
-            cudaStreamWaitEvent(st_w, ev, 0);
-            cudaEventDestroy(ev);                                      // released once the wait has consumed it
-            st = st_w;
-        }
+        // them as a second call (phases = SDFG_BWD_WGRAD) after it has enqueued the scatter and started the table-gradient exchange.
         if (has_views && g->rgb_w && d_rgb) {
             head_wgrad16_kernel<3><<<(unsigned)ceil_div<uint64_t>(N, 512), 256, 0, st>>>(d_rgb, (const h16*)(ws + L.off_hv), W, g->rgb_w, g->rgb_b, N, 512);
             if (int e = check_launch("head_wgrad16_kernel<3>")) return e;

@@ -228,13 +228,9 @@ def field_forward(spec, x_in, view_feat, gamma, beta, weights, samples_per_image
 
 
 def field_backward(spec, x_in, view_feat, gamma, beta, weights, samples_per_image, samples_per_ray, workspace, out_feat,
-                   d_sdf, d_rgb, d_feat, grads=None, want_dx=False, precision=_lib.PRECISION_FP32, wgrad_stream=None,
-                   phases=_lib.BWD_BOTH, state=None):
+                   d_sdf, d_rgb, d_feat, grads=None, want_dx=False, precision=_lib.PRECISION_FP32, phases=_lib.BWD_BOTH, state=None):
     """grads: None (no parameter gradients) or dict like `weights` + gamma/beta of pre-zeroed (or live .grad) buffers that are
     accumulated into.  Returns d_x_in [N,in_dim] or None.
-    wgrad_stream (torch.cuda.Stream): the parameter gradients are produced on that stream (sdfg_field_backward_2s) while d_x_in is
-    ready in the current stream's order; returns (d_x_in, scratch) -- the caller must keep `scratch` alive and make the current
-    stream wait for wgrad_stream before it lets go of scratch / grads / the upstream gradients.
     phases (sdfg_field_backward_phase): BWD_CHAIN returns (d_x_in, state); a later call with phases=BWD_WGRAD, state=state and
     otherwise identical arguments produces the parameter gradients (the caller enqueues whatever should run in between)."""
     lib = _lib.load()
@@ -271,12 +267,6 @@ def field_backward(spec, x_in, view_feat, gamma, beta, weights, samples_per_imag
                                                      _ptr(out_feat), _ptr(workspace), _ptr(scratch), _ptr(dx), int(precision), int(phases),
                                                      _stream()), "sdfg_field_backward_phase")
             return dx, (scratch, dx)
-        if wgrad_stream is not None:
-            _lib.check(lib.sdfg_field_backward_2s(ctypes.byref(p), gref, _ptr(x_in), _ptr(view_feat), N,
-                                                  _ptr(_chk(d_sdf, "d_sdf")), _ptr(_chk(d_rgb, "d_rgb")), _ptr(_chk(d_feat, "d_feat")),
-                                                  _ptr(out_feat), _ptr(workspace), _ptr(scratch), _ptr(dx), int(precision), _stream(),
-                                                  ctypes.c_void_p(wgrad_stream.cuda_stream)), "sdfg_field_backward_2s")
-            return dx, scratch
         _lib.check(lib.sdfg_field_backward(ctypes.byref(p), gref, _ptr(x_in), _ptr(view_feat), N,
                                            _ptr(_chk(d_sdf, "d_sdf")), _ptr(_chk(d_rgb, "d_rgb")), _ptr(_chk(d_feat, "d_feat")),
                                            _ptr(out_feat), _ptr(workspace), _ptr(scratch), _ptr(dx), int(precision), _stream()),
