@@ -654,6 +654,7 @@ static int launch_wgrad(const h16* dz, const h16* x, uint32_t Kx, int64_t ldx, u
     P.rows_per_image = rows_per_image;
     P.Kx = Kx;
     P.n_xbox = ceil_div<uint32_t>(Kx, 64);
+    P.n_ring = tc::wgrad_ring_depth(P.n_xbox);
     P.n_main = std::min<uint32_t>(round_up(Kx, 64), 256);
     P.n_extra = P.n_xbox > 4 ? 64 : 0;
     P.ones_col = P.n_main + P.n_extra;

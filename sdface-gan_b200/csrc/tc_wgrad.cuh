@@ -18,7 +18,7 @@ namespace tc {
 
 constexpr uint32_t WG_ROWS = 64;                    // samples per pipeline stage
 constexpr uint32_t WG_BOX_BYTES = WG_ROWS * 128;    // one [64 samples x 64 features] box = 8 KB
-constexpr uint32_t WG_STAGES = 3;
+constexpr uint32_t WG_MAX_STAGES = 8;                // ring depth = as many stages as fit in ~200 KB (3 .. 8, WgradParams::n_ring)
 constexpr uint32_t WG_MAX_XBOX = 5;                 // Kx <= 320
 constexpr uint32_t WG_THREADS = 192;
 
@@ -32,20 +32,27 @@ struct WgradParams {
     uint32_t n_extra;           // 0 or 64: second x block for Kx > 256
     uint32_t ones_col;          // n_main + n_extra: TMEM / G column of the ones accumulator
     uint32_t ldg;               // pitch of G rows (floats) >= ones_col + 16
+    uint32_t n_ring;            // pipeline stages resident in shared memory (wgrad_ring_depth)
     uint32_t x_fmt;             // FMT_F16 / FMT_BF16 of x and dz (tcgen05.mma .kind::f16 rejects mixed 16-bit operand types)
     float* G;                   // [B, 256, ldg] fp32, pre-zeroed
 };
 
 struct WgradSmem {
-    uint64_t full[WG_STAGES], empty[WG_STAGES];
+    uint64_t full[WG_MAX_STAGES], empty[WG_MAX_STAGES];
     uint64_t acc_full, acc_empty;
     uint32_t tmem_base;
     uint32_t pad;
 };
 
 __host__ __device__ inline uint32_t wgrad_stage_bytes(uint32_t n_xbox) { return (2 + n_xbox) * WG_BOX_BYTES; }
+// A stage holds 64 samples: 16 KB of gradient tile + 8 KB per 64 input columns.  HBM needs ~50 KB in flight per SM: three stages of the
+// K = 32 input-stage contraction (24 KB each) were not enough (4.9 TB/s against 6.5 for the K = 256 layers), so the ring takes what fits.
+__host__ __device__ inline uint32_t wgrad_ring_depth(uint32_t n_xbox) {
+    const uint32_t fit = (200u * 1024u) / wgrad_stage_bytes(n_xbox);
+    return fit < 3 ? 3 : (fit > WG_MAX_STAGES ? WG_MAX_STAGES : fit);
+}
 __host__ __device__ inline uint32_t wgrad_smem_bytes(uint32_t n_xbox) {
-    return 1024 + WG_STAGES * wgrad_stage_bytes(n_xbox) + 2048 /* ones tile */ + (uint32_t)sizeof(WgradSmem);
+    return 1024 + wgrad_ring_depth(n_xbox) * wgrad_stage_bytes(n_xbox) + 2048 /* ones tile */ + (uint32_t)sizeof(WgradSmem);
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -53,7 +60,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant_
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t stage_bytes = wgrad_stage_bytes(P.n_xbox);
-    uint8_t* ones = smem + WG_STAGES * stage_bytes;                  // 16 rows x 128 B of 1.0 (layout-agnostic: all equal)
+    uint8_t* ones = smem + P.n_ring * stage_bytes;                  // 16 rows x 128 B of 1.0 (layout-agnostic: all equal)
     WgradSmem& S = *reinterpret_cast<WgradSmem*>(ones + 2048);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -63,7 +70,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant_
     const uint32_t stages_per_image = P.rows_per_image / WG_ROWS;
 
     if (threadIdx.x == 0) {
-        for (uint32_t i = 0; i < WG_STAGES; i++) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
+        for (uint32_t i = 0; i < P.n_ring; i++) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
         mbar_init(&S.acc_full, 1);
         mbar_init(&S.acc_empty, 4);
         fence_barrier_init();
@@ -94,7 +101,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant_
                 tma_load_2d_hint(base + WG_BOX_BYTES, &tmDZ, &S.full[stage], (int32_t)(half * 128 + 64), row, stream);
                 for (uint32_t b = 0; b < P.n_xbox; b++)
                     tma_load_2d(base + (2 + b) * WG_BOX_BYTES, &tmX, &S.full[stage], (int32_t)(b * 64), row);
-                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == P.n_ring) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -121,7 +128,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDZ, const __grid_constant_
                 }
                 fresh = false;
                 umma_commit(&S.empty[stage]);
-                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == P.n_ring) { stage = 0; phase ^= 1; }
                 const bool last = s + 1 == s_end;
                 if (last || (s + 1) / stages_per_image != s / stages_per_image) {
                     umma_commit(&S.acc_full);                        // image finished: epilogue flushes the accumulators
