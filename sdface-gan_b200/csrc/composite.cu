@@ -126,7 +126,31 @@ __global__ void __launch_bounds__(256) composite_forward_kernel(
         }
         if (xyz_map) { xyz_map[ray * 3] = acc[3]; xyz_map[ray * 3 + 1] = acc[4]; xyz_map[ray * 3 + 2] = acc[5]; }
     }
-    if (feat_map) {
+    if (FEAT16 && feat_map && F == 256) {
+        // the tensor-core field's fp16 features at the model width: a lane owns 8 consecutive channels = one 16-byte load per sample
+        // (a warp reads the 512-byte row in one instruction), 4 samples per trip
+        float fa8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const uint4* frow = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(feat) + base * F) + lane;
+#pragma unroll 4
+        for (uint32_t s = 0; s < S; s++) {
+            float w = 0.f;
+#pragma unroll
+            for (int i = 0; i < KS; i++) {
+                const float wi = __shfl_sync(0xffffffffu, st.w[i], (int)(s / KS));
+                if ((int)(s % KS) == i) w = wi;
+            }
+            const uint4 h = __ldg(frow + (size_t)s * 32);
+            const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[k]));
+                fa8[2 * k] = fmaf(w, a.x, fa8[2 * k]); fa8[2 * k + 1] = fmaf(w, a.y, fa8[2 * k + 1]);
+            }
+        }
+        float4* orow = reinterpret_cast<float4*>(feat_map + (size_t)ray * F) + 2 * lane;
+        orow[0] = make_float4(fa8[0], fa8[1], fa8[2], fa8[3]);
+        orow[1] = make_float4(fa8[4], fa8[5], fa8[6], fa8[7]);
+    } else if (feat_map) {
         // lanes across channels, samples streamed in order; w broadcast from the lane that owns the sample
         const uint32_t F4 = F >> 2;
         float4 fa[kMaxF4];
