@@ -22,8 +22,8 @@
 // The first FiLM layer (K = in_dim <= 32, |W| ~ 1/3, gamma ~ 30) is where 16-bit operand rounding hurts: with split_x its x part runs
 // as hi + lo pairs -- x = x_hi + x_lo (a second small operand tile), W = W_hi + W_lo (a second weight chunk), three products
 // W_hi x_hi + W_hi x_lo + W_lo x_hi -- i.e. ~fp32 operands for 4 extra K-steps per tile (tests/test_operand_precision.py).
-// The sine: MUFU.SIN runs at 16 / clk / SM -- 2048 clk per layer and SM, exactly the layer's MMA time -- so CH_POLY_PAIRS of the 8
-// element pairs of every piece take the FMA pipe instead: r = u - k pi with k = rint(u / pi) (the same fma against 1.5 * 2^23 that
+// The sine: MUFU.SIN runs at 16 / clk / SM -- 2048 clk per layer and SM, exactly the layer's MMA time -- so some of the 8
+// element pairs of every piece (POLY_PAIRS below) can take the FMA pipe instead: r = u - k pi with k = rint(u / pi) (the same fma against 1.5 * 2^23 that
 // yields the sign bit), an odd degree-7 minimax polynomial on [-pi/2, pi/2] (max error 1e-6, the level of sin.approx) in packed
 // fma.rn.f32x2, and the sign (-1)^k xor-ed in.
 // CTA pairs (CG = 2): each CTA stages its own 128 rows of A and HALF of every weight chunk, halving the L2 -> SM weight stream
@@ -36,10 +36,16 @@
 namespace sdfg {
 namespace tc {
 
+// How many of the 8 element pairs per thread and piece take the polynomial.  Measured (B = 32, scripts/gpu_poly.sh), pairs 0 / 1 / 2 / 3:
+// inference chain 1.59 / 1.55 / 1.55 / 1.57 ms (thumbnail), 1.60 / 1.61 / 1.63 / 1.67 ms (with features); training forward 2.23 / 2.28 /
+// 2.33 / 2.36 ms -- there the epilogue is issue-bound on recording the derivative planes and MUFU.SIN costs fewer issue slots than the
+// polynomial (the range reduction fma is needed for the sign bit either way).
 #ifndef SDFG_POLY_PAIRS
-#define SDFG_POLY_PAIRS 2
+#define SDFG_POLY_PAIRS 1
 #endif
-constexpr int CH_POLY_PAIRS = SDFG_POLY_PAIRS;              // of the 8 element pairs per thread and piece: sine on the FMA pipe
+#ifndef SDFG_POLY_PAIRS_TRAIN
+#define SDFG_POLY_PAIRS_TRAIN 0
+#endif
 
 constexpr uint32_t FC_MAX_LAYERS = SDFG_MAX_FILM + 1;
 __host__ __device__ constexpr uint32_t fc_w_bytes(int cg) { return 32768u / (uint32_t)cg; }
@@ -112,6 +118,7 @@ template <bool SAVE, bool COS, int CG>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 tc_fchain_fwd_kernel(const __grid_constant__ FChainMaps maps, const __grid_constant__ FChainParams P) {
     constexpr bool PAIR = CG == 2;
+    constexpr int POLY_PAIRS = COS ? SDFG_POLY_PAIRS_TRAIN : SDFG_POLY_PAIRS;      // sine on the FMA pipe for that many of the 8 pairs
     constexpr uint32_t W_BYTES = fc_w_bytes(CG), NW = fc_w_stages(CG), W_ROWS = 256 / CG;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -400,7 +407,7 @@ tc_fchain_fwd_kernel(const __grid_constant__ FChainMaps maps, const __grid_const
                             uint64_t t2[8];
 #pragma unroll
                             for (int j = 0; j < 8; j++)
-                                if (do_sgn || j >= 8 - CH_POLY_PAIRS) t2[j] = fma2(pk2(v[2 * j], v[2 * j + 1]), inv_pi2, magic2);
+                                if (do_sgn || j >= 8 - POLY_PAIRS) t2[j] = fma2(pk2(v[2 * j], v[2 * j + 1]), inv_pi2, magic2);
                             if (do_sgn) {
                                 // A funnel shift per element moves the parity bit into the mask: even elements first, then odd ones, so that
                                 // bit j = element 2j and bit 8 + j = element 2j + 1 (the order the backward chain's packed-half sign flip wants).
@@ -411,7 +418,7 @@ tc_fchain_fwd_kernel(const __grid_constant__ FChainMaps maps, const __grid_const
                             }
 #pragma unroll
                             for (int j = 0; j < 8; j++) {
-                                if (j >= 8 - CH_POLY_PAIRS) {
+                                if (j >= 8 - POLY_PAIRS) {
                                     const uint64_t x2 = pk2(v[2 * j], v[2 * j + 1]);
                                     const uint64_t rr = fma2(add2(t2[j], nmagic2), npi2, x2);          // r = u - k pi in [-pi/2, pi/2]
                                     const uint64_t r2 = mul2(rr, rr);
