@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu evidence, end of round 2: launch list of the last training step, --set full of the tensor-core chain kernels, launch list + --set full of
 # the decoder kernels of one configs[2] pass.  $1 = tag.  Every ncu run follows a plain run of the same command that exited 0.
-TAG=${1:-r02g}
+TAG=${1:-r02h}
 mkdir -p gpurun_out
 python scripts/prof_step_once.py train > gpurun_out/plain_$TAG.log 2>&1 || { tail -5 gpurun_out/plain_$TAG.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_all_$TAG.csv python scripts/prof_step_once.py train > gpurun_out/ncu_launch_$TAG.log 2>&1
