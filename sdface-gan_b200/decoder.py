@@ -8,9 +8,11 @@ signature and return values.  What differs is HOW an image is decoded:
   * a ModulatedConv2d is a per-sample weight fold (style modulation + demodulation folded into fp16 weights, like the reference's
     grouped-convolution trick) followed by an implicit-GEMM 3 x 3 convolution on tcgen05 (csrc/tc_conv.cuh) whose epilogue applies
     NoiseInjection, the FusedLeakyReLU bias and the activation;
-  * an up-sampling StyledConv is one GEMM producing the nine taps of the transposed convolution and one gather kernel that sums
-    them, blurs (upfirdn2d) and activates -- the (2H+1)^2 intermediate of conv_transpose2d never exists;
-  * ToRGB, its bias, the skip up-sampling (upfirdn2d) and the skip addition are one kernel per resolution.
+  * an up-sampling StyledConv runs conv_transpose2d as its four output-parity classes in the same convolution kernel (per-class tap
+    tables, stride-2 store into the fp16 (2H+1)^2 intermediate) and one kernel that blurs (upfirdn2d, separable), adds noise + bias and
+    activates;
+  * ToRGB is a 16-column GEMM in the same kernel whose epilogue adds the bias and the up-sampled skip (upfirdn2d): one launch per
+    resolution.
 The mapping network (5 EqualLinear on [B, 512]) stays torch.  Forward / inference only: with autograd enabled the decoder raises
 (the generator's stage-2 training step, BASELINE configs[3], is not built).  `project_noise` (pytorch3d) is not supported.
 """
