@@ -9,7 +9,8 @@
 // GEMM hide behind the other tile's epilogue.  The price is shared memory: the sin tiles stream through a 3 x 16 KB ring instead
 // of a 64 KB buffer and the weights through 2 x 16 KB stages (CTA pairs only: each CTA stages half of every weight chunk); both
 // are prefetched by dedicated producer threads, and a weight stall of up to (epilogue - GEMM) ~ 1000 clk per layer is free.
-//   shared memory: G_A, G_B 128 KB | sin ring 48 KB | weight ring 32 KB | sign planes 8 KB | barriers + head vectors 4.4 KB
+//   shared memory: G_A, G_B 128 KB | sin ring 48 KB | weight ring 32 KB | derivative planes (sign + rounding bit) 2 x 8 KB | barriers 0.4 KB
+//   (the head vectors are read from global memory: L1 hits after the first tile)
 // Measured on B200 (N = 3.1 M): eikonal pass 1.95 -> 1.83 ms, backward with stores 3.00 -> 3.11 ms -- far from the ~1.7x the
 // latency picture promised: with the GEMM fully concurrent the epilogue's pieces take longer (~1750 instead of ~1100 clk), so a layer
 // still costs about epilogue + GEMM.  It is not the shared-memory port (scripts/ubench/umma_rate.cu: the MMAs keep their nominal

@@ -19,7 +19,7 @@ constexpr uint32_t CH_ACT_BYTES = 4 * CH_CHUNK_BYTES;       // K = 256
 // |stored| > |sin u|) -- it halves the interval the backward's cos = sqrt(1 - sin^2) has to guess in where |sin| -> 1.
 // Bit j = element 2j, bit 8 + j = element 2j + 1 in both halves.
 constexpr uint32_t CH_SGN_TILE_BYTES = 8192;
-constexpr uint32_t CH_AUX_BYTES = 32768;                    // inference: resident small weights; training: 2 sign-mask tiles
+constexpr uint32_t CH_AUX_BYTES = 32768;                    // inference: resident small weights; training: 2 derivative-plane tiles
 constexpr uint32_t CH_W_STAGE_BYTES = 256 * 128;            // one streamed weight chunk
 constexpr uint32_t CH_W_STAGES = 3;
 constexpr uint32_t CH_MAX_LAYERS = SDFG_MAX_FILM + 1;
