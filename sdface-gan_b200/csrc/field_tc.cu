@@ -552,12 +552,16 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restri
 }
 
 // head weight gradient: dw[c, k] += sum_n dout[n, c] * h[n, k]   (h fp16 [*, 256], pitch ld), db[c] += sum_n dout[n, c].
-// A warp reads one 512-byte row per load instruction (16 bytes per lane), 8 warps x 4 rows are in flight per block; the
-// per-warp partial sums meet in shared memory and one warp per head issues the global reductions.
+// A warp owns every 8th row of the block's range and streams them through its own ring of HW_RING rows in shared memory with
+// cp.async (512 bytes of h + NOUT floats of dout per row): the bytes in flight no longer cost registers -- with register-staged
+// loads the 3-output variant ran 4 blocks per SM at 4 rows per warp and 4.4 TB/s.  The per-warp partial sums meet in the same
+// shared memory after the loop and one thread per column issues the global reductions.
+constexpr int HW_RING = 8;
 template <int NOUT>
 __global__ void __launch_bounds__(256) head_wgrad16_kernel(const float* __restrict__ dout, const h16* __restrict__ h, int64_t ld,
                                                             float* __restrict__ dw, float* __restrict__ db, uint64_t M, uint32_t rows_per_block) {
-    __shared__ float red[8][NOUT][256 + 8];
+    constexpr int ROW_BYTES = 512 + 16;                                 // 256 fp16 + up to 4 floats of dout
+    __shared__ __align__(16) uint8_t ring[8][HW_RING][ROW_BYTES];       // 33 KB; reused as red[8][NOUT][264] floats (<= 25 KB) after the loop
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t m0 = (uint64_t)blockIdx.x * rows_per_block, m1 = min(M, m0 + rows_per_block);
     float acc[NOUT][8], gb[NOUT];
@@ -567,34 +571,47 @@ __global__ void __launch_bounds__(256) head_wgrad16_kernel(const float* __restri
 #pragma unroll
         for (int k = 0; k < 8; k++) acc[c][k] = 0.f;
     }
-    constexpr int U = 4;
-    for (uint64_t m = m0 + warp; m < m1; m += 8 * U) {
-        uint4 hv[U];
-        float d[U][NOUT];
-#pragma unroll
-        for (int j = 0; j < U; j++) {
-            const uint64_t mm = min(m + 8 * j, m1 - 1);
-            const float live = (m + 8 * j < m1) ? 1.f : 0.f;
-            hv[j] = __ldg(reinterpret_cast<const uint4*>(h + mm * ld) + lane);
-#pragma unroll
-            for (int c = 0; c < NOUT; c++) d[j][c] = live * __ldg(dout + mm * NOUT + c);
+    // row i of this warp = m0 + warp + 8 i
+    const uint32_t n_rows = m0 + warp < m1 ? (uint32_t)((m1 - m0 - warp + 7) / 8) : 0u;
+    auto issue = [&](uint32_t i) {
+        if (i < n_rows) {
+            const uint64_t mm = m0 + warp + 8ull * i;
+            uint8_t* slot = ring[warp][i % HW_RING];
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(slot + lane * 16)), "l"(h + mm * ld + lane * 8) : "memory");
+            if (lane < NOUT)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tc::smem_u32(slot + 512 + lane * 4)), "l"(dout + mm * NOUT + lane) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");          // one group per ring step, empty past the end
+    };
 #pragma unroll
-        for (int j = 0; j < U; j++) {
-            const uint32_t w[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w};
+    for (int i = 0; i < HW_RING - 1; i++) issue(i);
+    for (uint32_t i = 0; i < n_rows; i++) {
+        issue(i + HW_RING - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(HW_RING - 1) : "memory");     // row i has landed (this thread's copies)
+        __syncwarp();                                                   // ... and every other lane's
+        const uint8_t* slot = ring[warp][i % HW_RING];
+        const uint4 hv = *reinterpret_cast<const uint4*>(slot + lane * 16);
+        float d[NOUT];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float2 f = tc::unpack_f16(w[k]);
+        for (int c = 0; c < NOUT; c++) d[c] = *reinterpret_cast<const float*>(slot + 512 + c * 4);
+        const uint32_t w[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
-                for (int c = 0; c < NOUT; c++) {
-                    acc[c][2 * k] = fmaf(d[j][c], f.x, acc[c][2 * k]);
-                    acc[c][2 * k + 1] = fmaf(d[j][c], f.y, acc[c][2 * k + 1]);
-                }
+        for (int k = 0; k < 4; k++) {
+            const float2 f = tc::unpack_f16(w[k]);
+#pragma unroll
+            for (int c = 0; c < NOUT; c++) {
+                acc[c][2 * k] = fmaf(d[c], f.x, acc[c][2 * k]);
+                acc[c][2 * k + 1] = fmaf(d[c], f.y, acc[c][2 * k + 1]);
             }
-#pragma unroll
-            for (int c = 0; c < NOUT; c++) gb[c] += d[j][c];
         }
+#pragma unroll
+        for (int c = 0; c < NOUT; c++) gb[c] += d[c];
+        __syncwarp();                                                   // the slot is overwritten HW_RING - 1 steps from now: all lanes are done reading
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    float (*red)[NOUT][256 + 8] = reinterpret_cast<float (*)[NOUT][256 + 8]>(&ring[0][0][0]);
+    static_assert(sizeof(float) * 8 * NOUT * (256 + 8) <= sizeof(ring), "reduction buffer must fit in the ring");
 #pragma unroll
     for (int c = 0; c < NOUT; c++) {
 #pragma unroll
